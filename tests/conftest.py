@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def refdata():
+    """Directory of the reference's own fixtures; absent on the GPU box."""
+    d = "/root/reference/src"
+    if not os.path.isdir(d):
+        pytest.skip("reference tree not present on this machine")
+    return d
