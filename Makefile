@@ -1,0 +1,26 @@
+# Builds the product: libvstree_b200.so (CUDA kernels + C ABI, sm_100a only) and the mkvtree host driver.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC := vstree_b200/csrc
+LIBDIR := vstree_b200/lib
+BINDIR := vstree_b200/bin
+OBJDIR := build/obj
+CU := $(wildcard $(CSRC)/*.cu)
+OBJ := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU))
+HDR := $(wildcard $(CSRC)/*.cuh) include/vstree_b200.h
+
+all: $(LIBDIR)/libvstree_b200.so
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(LIBDIR)/libvstree_b200.so: $(OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+
+clean:
+	rm -rf build $(LIBDIR) $(BINDIR)
+
+.PHONY: all clean

@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- mkvtree index build throughput (suf+lcp+bwt) on B200, next to the reference mkvtree on the host.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+
+One "step" = one enhanced-suffix-array build (esa_construct: suffix array, inverse suffix array, lcp/llv, bwt,
+64-bit suftab) of the workload's transformed sequence.  `value` times the device-resident build (text already in
+HBM, CUDA events on the library's launching stream); `e2e` times esa_build through the C ABI with HOST buffers
+(pinned input, H2D + build + D2H of every demanded table inside the timed region).  The dominant kernel
+(radix_pass) is timed per launch with CUDA events inside the library and reported against the measured HBM peak.
+N > 1 (torchrun): every rank builds an independent index of its own sequence (weak scaling, no data-path
+collective); value = all ranks' symbols / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, n, alphabet size, flag, generator name, generator kwargs, prefix length (auto value))
+    "c2": ("synthetic 100 Mbp random DNA (BASELINE.json configs[1]), -dna -pl 11 -suf -lcp -bwt", 100_000_000, 4,
+           "-dna", "random_dna", {"seed": 42}),
+    "c3": ("synthetic 250 Mbp repeat-rich DNA (configs[2])", 250_000_000, 4, "-dna", "repeat_rich_dna", {"seed": 7}),
+    "c4": ("synthetic 500 M-residue protein (configs[3])", 500_000_000, 20, "-protein", "random_protein", {"seed": 11}),
+    "small": ("synthetic 4 Mbp random DNA (smoke size)", 4_000_000, 4, "-dna", "random_dna", {"seed": 42}),
+}
+TABLES = ("suf", "lcp", "bwt")
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_tis(workload, rank=0):
+    from vstree_b200 import synth
+    desc, n, sigma, flag, gen, kw = WORKLOADS[workload]
+    kw = dict(kw)
+    kw["seed"] = kw.get("seed", 0) + 1000 * rank  # every rank its own sequence
+    return getattr(synth, gen)(n, **kw), sigma, flag
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference_cli(tis, sigma, flag, k, repeats=1):
+    """Wall time of the UNMODIFIED reference mkvtree (oracle/_ref/mkvtree.x) on a FASTA rendering of tis; falls back
+    to the C restatement (oracle port) when the binary did not travel.  Returns (seconds, kind, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_util as ou
+    from vstree_b200 import synth
+    if ou.have_ref():
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        with tempfile.TemporaryDirectory(dir=shm) as d:
+            path = os.path.join(d, "in.fna")
+            with open(path, "wb") as f:
+                f.write(synth.to_fasta(tis, "dna" if flag == "-dna" else "protein", width=1 << 20))
+            best = None
+            for _ in range(repeats):
+                for fn in os.listdir(d):
+                    if fn.startswith("idx."):
+                        os.unlink(os.path.join(d, fn))
+                t0 = time.perf_counter()
+                pr = subprocess.run([ou.REF_MKVTREE, "-db", "in.fna", "-indexname", "idx", flag, "-pl", str(k), "-suf",
+                                     "-lcp", "-bwt"], cwd=d, capture_output=True)
+                dt = time.perf_counter() - t0
+                if pr.returncode != 0:
+                    raise RuntimeError("reference mkvtree failed: " + pr.stderr.decode(errors="replace"))
+                best = dt if best is None else min(best, dt)
+        return best, "reference", 1
+    t0 = time.perf_counter()
+    ou.oracle_build(tis, sigma, k, bck=False, sti1=False)
+    return time.perf_counter() - t0, "port", 1
+
+
+def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    desc, n, sigma, flag, gen, kw = WORKLOADS[args.workload]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vstree_b200 import load_library
+    lib = load_library()  # host-side scalar math only (no GPU call)
+    # bounded sample: the whole run should end within a few minutes at ~5 Msymbols/s on one core
+    budget = 150.0
+    sample = int(min(n, max(2_000_000, budget * 5e6 / (args.steps + args.warmup))))
+    from vstree_b200 import synth
+    tis = getattr(synth, gen)(sample, **kw)
+    k = lib.esa_recommended_prefixlength(sigma, sample)
+    times = []
+    kind, cores = "reference", 1
+    for i in range(args.warmup + args.steps):
+        dt, kind, cores = time_reference_cli(tis, sigma, flag, k)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total / 1e6
+    line = {"impl": "reference", "metric": "mkvtree index build throughput (suf+lcp+bwt)", "value": value,
+            "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "sample": f"first-principles regeneration at n={sample} (same generator/seed)",
+                       "prefixlength": int(k), "tables": list(TABLES)},
+            "cpu_baseline": {"value": value, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "cores": cores,
+                             "kind": kind, "sample": f"{sample} symbols per step, CLI wall time incl. parse and file "
+                                                     "output to tmpfs"},
+            "e2e": {"value": value, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vstree_b200 import Esa, load_library
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the host arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    desc, n, sigma, flag, gen, kw = WORKLOADS[args.workload]
+    lib = load_library()
+    k = int(lib.esa_recommended_prefixlength(sigma, n))
+    tis = np.ascontiguousarray(make_tis(args.workload, rank)[0])
+    pinned = torch.from_numpy(tis).pin_memory()  # the e2e leg copies from pinned host memory
+    esa = Esa(local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------------------------
+    esa.upload(pinned, sigma)
+    for _ in range(args.warmup):
+        esa.construct(k, TABLES)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    kern = {}
+    last = None
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict the previous step's tables from L2 (outside the event-timed region)
+        torch.cuda.synchronize()
+        st = esa.construct(k, TABLES)
+        dev_ms += st["ms_total"]
+        launches += st["launches"]
+        for name, ks in st["kernel"].items():
+            a = kern.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0.0})
+            for f in a:
+                a[f] += ks[f]
+        last = st
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    clocks = sampler.stop()
+    esa.check()  # the tables of the last timed step are consistent (device-side property checks)
+
+    # ---- end-to-end leg: esa_build through the C ABI with host buffers --------------------------------------
+    e2e_ms, h2d, d2h = 0.0, 0, 0
+    for i in range(1 + args.e2e_steps):
+        barrier()
+        t1 = time.perf_counter()
+        tabs, st = esa.build(pinned, sigma, k, TABLES, want_stats=True, copy=False)
+        dt = (time.perf_counter() - t1) * 1000.0
+        checksum = int(tabs["suf"][:: max(1, n // 1000)].sum())  # touch the result on the host
+        esa.free(tabs)
+        if i > 0:
+            e2e_ms += dt
+            h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+    e2e_ms_step = e2e_ms / args.e2e_steps
+
+    t = torch.tensor([dev_ms, e2e_ms_step], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            sec, kind, cores = time_reference_cli(tis, sigma, flag, k)
+            cpu = {"value": n / sec / 1e6, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "cores": cores,
+                   "kind": kind, "sample": f"the whole workload once ({n} symbols), CLI wall time incl. FASTA parse and "
+                                           f"file output to tmpfs: {sec:.2f} s"}
+        except Exception as e:  # the baseline is a report, not a gate
+            cpu = {"value": None, "unit": "Mbp/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        unit = "Mbp/s" if flag == "-dna" else "Mres/s"
+        peak, peak_src = measured_peak_gbs()
+        rp = kern.get("radix_pass", {"launches": 0, "ms": 0.0, "bytes": 0.0})
+        achieved = rp["bytes"] / (rp["ms"] * 1e-3) / 1e9 if rp["ms"] > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        stage = {name: {"launches": v["launches"] // args.steps, "ms": v["ms"] / args.steps,
+                        "GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None)}
+                 for name, v in kern.items() if v["launches"]}
+        line = {
+            "metric": "mkvtree index build throughput (suf+lcp+bwt)",
+            "value": world * n * args.steps / (dev_ms_max * 1e-3) / 1e6,
+            "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": desc, "n": n, "prefixlength": k, "tables": list(TABLES),
+                       "parallelism": "one independent index per GPU" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush buffer written between timed steps; working set >> 126 MB L2",
+                       "timing": "sum of per-step CUDA-event times on the library stream; wall incl. flush "
+                                 f"{wall_ms / args.steps:.2f} ms/step",
+                       "h0": last["h0"], "doubling_rounds": last["rounds"], "active_first": last["active_first"],
+                       "active_sum": last["active_sum"], "device_bytes_peak": last["device_bytes_peak"]},
+            "roofline": {"bound": "hbm", "kernel": "radix_pass_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "peak_source": peak_src, "launches_per_step": rp["launches"] // args.steps,
+                         "avg_launch_ms": rp["ms"] / rp["launches"] if rp["launches"] else None,
+                         "algorithmic_bytes_per_launch": rp["bytes"] / rp["launches"] if rp["launches"] else None,
+                         "share_of_step": rp["ms"] / dev_ms if dev_ms else None},
+            "stages": stage,
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    esa.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

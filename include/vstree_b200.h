@@ -1,0 +1,176 @@
+/*
+ * vstree_b200.h -- C ABI of the B200-native enhanced-suffix-array builder (libvstree_b200.so).
+ *
+ * This is the compute seam inside mkvtree's `mkvtreeprocess` (reference: src/Mkvtree/mkvprocess.c:875-1089):
+ * the host driver keeps option parsing, alphabet transformation and all file I/O, and hands the transformed
+ * sequence `tis` to this library, which builds the tables on one B200 (sm_100a) with hand-written CUDA kernels.
+ * There is no CPU fallback: every entry point that needs the GPU fails with a negative code and a message
+ * when no device is usable.
+ *
+ * Conventions (the reference's own, src/include/errordef.h:45-110): return 0 on success, a negative code on
+ * error with a NUL-terminated message in `errbuf` (may be NULL); plain pointers and sizes only; no exceptions
+ * cross this boundary.  One build at a time per context; a context is bound to one device.
+ *
+ * Sizes: n = totallength (letters + wildcards + separators), N = n + 1 (the sentinel suffix at position n is a
+ * member of every table).  `Uint` of the reference is 8 bytes, little endian (src/include/types.h:41-49).
+ */
+#ifndef VSTREE_B200_H
+#define VSTREE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Table demand bits; same values as the reference's TISTAB..STITAB (src/include/virtualdef.h:24-64). */
+#define ESA_TISTAB  (1u << 0)
+#define ESA_OISTAB  (1u << 1)
+#define ESA_DESTAB  (1u << 2)
+#define ESA_SSPTAB  (1u << 3)
+#define ESA_BWTTAB  (1u << 4)   /* .bwt  replaces encodeburrowswheeler, src/kurtz/bwtcode.c:293-311 */
+#define ESA_SUFTAB  (1u << 5)   /* .suf  replaces besesuffixsort[special], src/Mkvtree/bese.c:855-1105 */
+#define ESA_LCPTAB  (1u << 6)   /* .lcp/.llv  replaces outlcpsubtab, src/Mkvtree/bese.c:533-591 */
+#define ESA_BCKTAB  (1u << 7)   /* .bck  replaces bucketsortsuffixes + makebcktab, ppsort.c:83-313, mkvprocess.c:251-327 */
+#define ESA_STI1TAB (1u << 8)   /* .sti1 replaces makestitab1, src/Mkvtree/mkvprocess.c:583-643 */
+#define ESA_SKPTAB  (1u << 9)   /* .skp  replaces makeskiptable, src/kurtz/mkskip.c:53-91 */
+#define ESA_STITAB  (1u << 13)  /* .sti  full inverse suffix array, src/Mkvtree/mksti.c:15-34 */
+
+/* Symbol codes of the transformed sequence (src/include/chardef.h:19-50). */
+#define ESA_WILDCARD     254u
+#define ESA_SEPARATOR    255u
+#define ESA_UNDEFBWTCHAR 253u
+
+/* Error codes. */
+#define ESA_OK              0
+#define ESA_ERR_ARGUMENT   (-1)   /* inconsistent arguments (e.g. -bck without a prefix length) */
+#define ESA_ERR_NODEVICE   (-2)   /* no usable CUDA device: there is no CPU fallback */
+#define ESA_ERR_CUDA       (-3)   /* a CUDA call or kernel failed */
+#define ESA_ERR_MEMORY     (-4)   /* host or device memory exhausted */
+#define ESA_ERR_TOOLARGE   (-5)   /* n + 1 does not fit the 32-bit device index (n < 2^32 - 1 required) */
+#define ESA_ERR_PREFIXLEN  (-6)   /* prefix length larger than vm_whatisthemaximalprefixlength allows */
+#define ESA_ERR_STATE      (-7)   /* call sequence violated (e.g. construct before upload) */
+#define ESA_ERR_CHECK      (-8)   /* esa_check found an inconsistent table */
+#define ESA_ERR_COMM       (-9)   /* NCCL / multi-GPU communication failed */
+
+typedef struct esa_ctx esa_ctx;   /* opaque; owns the device, its streams and the device arena */
+
+/* PairUint of the reference (src/include/types.h:289-292): .llv entry. */
+typedef struct
+{
+  uint64_t uint0;   /* index into lcptab */
+  uint64_t uint1;   /* the lcp value (>= 255) */
+} esa_pairuint;
+
+/*
+ * Tables in PINNED HOST memory owned by the library until esa_free().  A pointer is NULL when the table was
+ * not demanded.  Mirrors the table members of Virtualtree (src/include/virtualdef.h:186-219).
+ */
+typedef struct
+{
+  uint64_t n;                /* totallength */
+  uint64_t numofcodes;       /* numofchars^prefixlength (0 when prefixlength == 0) */
+  uint64_t *suftab;          /* [N]   suffix array */
+  uint8_t *lcptab;           /* [N]   min(lcp,255) */
+  esa_pairuint *llv;         /* [nllv] (index,value) for lcp >= 255, increasing index */
+  uint64_t nllv;             /* largelcpvalues */
+  uint64_t maxbranchdepth;   /* max lcp */
+  uint64_t longest;          /* index i with suftab[i] == 0 (determinelongest, mkvprocess.c:857-873) */
+  uint8_t *bwttab;           /* [N]   tis[suftab[i]-1], 253 where suftab[i] == 0 */
+  uint64_t *bcktab;          /* [2*numofcodes] (left, mid) per k-mer code */
+  uint8_t *stitab1;          /* [N]   min(rank - bucket left, 255), by text position */
+  uint64_t *stitab;          /* [N]   full inverse suffix array */
+  uint64_t *skiptab;         /* [N]   skip table */
+} esa_result;
+
+/* Kernel families, for esa_stats.kernel[]. */
+enum
+{
+  ESA_K_CLASSIFY = 0,   /* special-distance classification + initial h0-mer keys */
+  ESA_K_RADIX_HIST,     /* all-digit histogram of a radix sort */
+  ESA_K_RADIX_PASS,     /* one onesweep LSD pass (the dominant kernel) */
+  ESA_K_REGROUP,        /* group heads, rank scatter, active-set compaction */
+  ESA_K_GATHER_RANK,    /* doubling key gather rank[sa+h] */
+  ESA_K_BCK,            /* bucket boundaries */
+  ESA_K_PLCP,           /* irreducible lcp values in text order + fill */
+  ESA_K_FINALIZE,       /* lcp/llv/bwt/suf widening in suffix-array order */
+  ESA_K_STI1,           /* reduced inverse suffix array */
+  ESA_K_MISC,           /* scans over tile summaries, small helpers */
+  ESA_K_MEMOP,          /* cudaMemsetAsync / device-to-device cudaMemcpyAsync nodes (not kernels of this library) */
+  ESA_K_NUM
+};
+
+typedef struct
+{
+  uint64_t launches;         /* kernel launches of this family */
+  double ms;                 /* summed device time (CUDA events on the launching stream) */
+  double bytes;              /* summed ALGORITHMIC bytes (DESIGN.md lists the per-unit figure of each family) */
+} esa_kernel_stat;
+
+typedef struct
+{
+  double ms_total;           /* device time of esa_construct (CUDA events) */
+  double ms_initial_sort;    /* classification + h0-mer radix sort + first regroup */
+  double ms_doubling;        /* all prefix-doubling rounds */
+  double ms_lcp;             /* PLCP + fill */
+  double ms_derive;          /* finalize (lcp8, llv, bwt, suf64), bck, sti1 */
+  uint32_t h0;               /* symbols per initial key */
+  uint32_t rounds;           /* prefix-doubling rounds after the initial sort */
+  uint64_t active_sum;       /* sum over rounds of the active-set sizes */
+  uint64_t active_first;     /* active-set size of round 1 */
+  uint64_t launches;         /* kernel launches of this library inside esa_construct (ESA_K_MEMOP excluded) */
+  uint64_t device_bytes_peak;/* arena high-water mark */
+  esa_kernel_stat kernel[ESA_K_NUM];
+  /* end-to-end legs, filled by esa_build (0 otherwise) */
+  double ms_h2d, ms_d2h;
+  uint64_t h2d_bytes, d2h_bytes;
+} esa_stats;
+
+/* ---- lifetime ---- */
+
+/* Bind a context to CUDA device `device` (>= 0).  Fails with ESA_ERR_NODEVICE when there is none. */
+int esa_init(esa_ctx **ctx, int device, char *errbuf, size_t errlen);
+void esa_shutdown(esa_ctx *ctx);
+
+/* ---- the one-call seam: host buffers in, pinned host tables out ----
+ * Replaces besesuffixsort[special] + makelargelcp + makebcktab + determinelongest + makestitab1 + makebwttab
+ * (src/Mkvtree/mkvprocess.c:976-1060).  `tis` holds n symbols (codes < numofchars, 254, 255) in ordinary host
+ * memory.  prefixlength 0 means "no bucket table" (then ESA_BCKTAB/ESA_STI1TAB are an argument error, as
+ * mkvtree.c:470-473).  ESA_STI1TAB implies lcp and bck are computed (mkvtree.c:376).  `stats` may be NULL. */
+int esa_build(esa_ctx *ctx, const uint8_t *tis, uint64_t n, uint32_t numofchars, uint32_t prefixlength,
+              uint32_t demand, esa_result *out, esa_stats *stats, char *errbuf, size_t errlen);
+void esa_free(esa_ctx *ctx, esa_result *out);
+
+/* ---- the same work in three stages, so that the device-resident part can be timed alone ---- */
+int esa_upload(esa_ctx *ctx, const uint8_t *tis, uint64_t n, uint32_t numofchars, char *errbuf, size_t errlen);
+int esa_construct(esa_ctx *ctx, uint32_t prefixlength, uint32_t demand, esa_stats *stats, char *errbuf,
+                  size_t errlen);
+int esa_download(esa_ctx *ctx, esa_result *out, char *errbuf, size_t errlen);
+
+/* ---- suffix-to-text checks on the device (reference DEBUG checks: bese.c:355-528, cprsuf.c:66-95,
+ * mkvprocess.c:672-763).  Runs on the tables left resident by the last esa_construct.  Returns 0 when
+ * consistent, ESA_ERR_CHECK with a message naming the violated property otherwise. ---- */
+int esa_check(esa_ctx *ctx, char *errbuf, size_t errlen);
+
+/* ---- host-side scalar math that must match the reference bit for bit ---- */
+/* vm_determinenumofcodes, src/kurtz-basic/detnumofcodes.c:8-11 */
+uint64_t esa_numofcodes(uint32_t numofchars, uint32_t prefixlength);
+/* vm_recommendedprefixlength, src/kurtz/detpfxlen.c:52-61 (sizeofbckentry = 16, mkvtree.c:652-658) */
+uint32_t esa_recommended_prefixlength(uint32_t numofchars, uint64_t totallength);
+/* vm_whatisthemaximalprefixlength, src/kurtz/detpfxlen.c:63-89 (PREFIXLENBITS 4, mkvaux.h:27) */
+uint32_t esa_maximal_prefixlength(uint32_t numofchars, uint64_t totallength);
+
+/* ---- testing hook: the LSD radix sort the suffix sorter is built on, on host arrays (in place).
+ * key_bytes is 4 or 8; vals may be NULL.  Sorts by key bits [begin_bit, end_bit), stable. ---- */
+int esa_debug_radix_sort(esa_ctx *ctx, int key_bytes, void *keys, uint32_t *vals, uint64_t n, uint32_t begin_bit,
+                         uint32_t end_bit, char *errbuf, size_t errlen);
+
+/* Library identification: "vstree_b200 <version> sm_100a". */
+const char *esa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle (C restatement, committed goldens
+made by the reference binary, and the reference binary itself when oracle/_ref travelled to the box)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+from golden_inputs import CASES, make_input
+from vstree_b200 import Esa, EsaError, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden.json")
+ALL = ("suf", "lcp", "bwt", "bck", "sti1")
+TABLES = ("suf", "lcp", "llv", "bwt", "bck", "sti1")
+SCALARS = ("longest", "maxbranchdepth", "largelcpvalues")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def esa():
+    e = Esa(0)
+    yield e
+    e.close()
+
+
+def golden():
+    with open(GOLDEN) as f:
+        return {c["name"]: c for c in json.load(f)["cases"]}
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    d = np.flatnonzero(a[:n] != b[:n])
+    if len(d):
+        i = int(d[0])
+        return f"first difference at {i}: got {a[max(0, i - 2):i + 3].tolist()} want {b[max(0, i - 2):i + 3].tolist()} ({len(d)} differ)"
+    return f"lengths differ: {len(a)} vs {len(b)}"
+
+
+def assert_tables_equal(got, want, what=""):
+    for name in TABLES:
+        if want.get(name) is None:
+            continue
+        g, w = got[name], np.asarray(want[name])
+        assert g is not None, f"{what}: {name} missing"
+        assert len(g) == len(w) and np.array_equal(g, w), f"{what}: {name}: {first_diff(g, w)}"
+    for name in SCALARS:
+        if name in want:
+            assert got[name] == want[name], f"{what}: {name}: got {got[name]} want {want[name]}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,bits,n", [(np.uint32, (0, 32), 1), (np.uint32, (0, 32), 1000), (np.uint32, (0, 31), 8192),
+                                          (np.uint32, (0, 32), 8193), (np.uint32, (3, 17), 300001),
+                                          (np.uint32, (0, 8), 70000), (np.uint32, (0, 32), 3000000),
+                                          (np.uint64, (0, 64), 6144), (np.uint64, (0, 54), 500000),
+                                          (np.uint64, (5, 50), 6145), (np.uint64, (0, 64), 2500000)])
+def test_radix_sort_matches_numpy_stable_sort(esa, dtype, bits, n):
+    rng = np.random.default_rng(n)
+    hi = np.iinfo(dtype).max
+    keys = rng.integers(0, hi, size=n, dtype=dtype, endpoint=True)
+    if n > 5000:  # plant heavy duplicates and a constant digit
+        keys[: n // 3] &= dtype(0xFF00FF)
+    vals = np.arange(n, dtype=np.uint32)
+    b, e = bits
+    mask = ((1 << (e - b)) - 1) << b
+    order = np.argsort((keys & dtype(mask)), kind="stable")
+    k2, v2 = keys.copy(), vals.copy()
+    esa.debug_radix_sort(k2, v2, b, e)
+    assert np.array_equal(v2, order.astype(np.uint32)), first_diff(v2, order.astype(np.uint32))
+    assert np.array_equal(k2, keys[order])
+    k3 = keys.copy()
+    esa.debug_radix_sort(k3, None, b, e)
+    assert np.array_equal(k3 & dtype(mask), (keys & dtype(mask))[order])
+
+
+def test_radix_sort_skewed(esa):
+    n = 1 << 20
+    keys = np.zeros(n, np.uint32)
+    keys[::7] = 1
+    keys[5::1001] = 0xFFFFFFFF
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    esa.debug_radix_sort(keys, vals, 0, 32)
+    assert np.array_equal(vals, order.astype(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES.keys()))
+def test_golden_cases(esa, name):
+    """Byte parity with the committed goldens (made by the reference binary) and with the C restatement."""
+    g = golden()[name]
+    tis, sigma = make_input(name)
+    k = g["prefixlength"]
+    got, stats = esa.build(tis, sigma, k, tables=ALL)
+    want = ou.oracle_build(tis, sigma, k)
+    assert_tables_equal(got, want, name)
+    for t in TABLES:
+        assert sha(got[t]) == g["sha"][t], f"{name}: {t} hash differs from the reference golden"
+    for sname in SCALARS:
+        assert got[sname] == g[sname]
+    if "tables" in g:
+        for t in TABLES:
+            assert got[t].tolist() == g["tables"][t], f"{name}: {t}"
+    esa.check()
+
+
+def test_kat_survey(esa):
+    tis = np.array([0, 1, 2, 3, 254, 0, 1, 2, 255, 0, 1, 2, 3, 255, 254, 254, 0, 1], np.uint8)
+    got, _ = esa.build(tis, 4, 1, tables=ALL)
+    assert got["suf"].tolist() == [0, 9, 5, 16, 1, 10, 6, 17, 2, 11, 7, 3, 12, 4, 8, 13, 14, 15, 18]
+    assert got["lcp"].tolist() == [0, 4, 3, 2, 0, 3, 2, 1, 0, 2, 1, 0, 1, 0, 0, 0, 0, 0, 0]
+    assert got["bwt"].tolist() == [253, 255, 254, 254, 0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 2, 3, 255, 254, 1]
+    assert got["bck"].tolist() == [0, 4, 4, 8, 8, 11, 11, 13]
+    assert got["sti1"].tolist() == [0, 0, 0, 0, 0, 2, 2, 2, 0, 1, 1, 1, 1, 0, 0, 0, 3, 3, 0]
+    assert got["longest"] == 0 and got["maxbranchdepth"] == 4 and got["largelcpvalues"] == 0
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_inputs_against_oracle(esa, seed):
+    """Ragged sizes around tile borders, every alphabet, dense specials."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([0, 1, 2, 3, 15, 16, 17, 255, 256, 4095, 4096, 4097, 8191, 8192, 8200, 20000, 65537]))
+    sigma = int(rng.choice([1, 2, 3, 4, 5, 20, 31, 200]))
+    if n == 0:
+        tis = np.zeros(0, np.uint8)
+    else:
+        tis = rng.integers(0, sigma, size=n, dtype=np.uint8)
+        sp = rng.random(n) < rng.choice([0.0, 0.01, 0.3])
+        tis[sp] = rng.choice([254, 255], size=int(sp.sum()))
+        if rng.random() < 0.5 and n > 40:  # long repeats
+            tis[n // 2:n // 2 + n // 3] = tis[:n // 3]
+    lib = ou.oracle_lib()
+    kmax = lib.oracle_maximalprefixlength(sigma, n) if sigma > 1 and n > 0 else 1
+    k = int(rng.integers(1, max(1, kmax) + 1)) if sigma > 1 else 1
+    if sigma == 1:
+        k = 1
+    got, _ = esa.build(tis, sigma, k, tables=ALL)
+    want = ou.oracle_build(tis, sigma, k)
+    assert_tables_equal(got, want, f"seed {seed} n={n} sigma={sigma} k={k}")
+    esa.check()
+
+
+def test_no_prefixlength_global_sort(esa):
+    """-pl absent: one global sort, no bck/sti1 (bese.c:1048-1075)."""
+    tis = synth.dna_with_specials(30000, seed=77, nfrac=0.01, mean_run=4, records=9)
+    got, _ = esa.build(tis, 4, 0, tables=("suf", "lcp", "bwt"))
+    want = ou.oracle_build(tis, 4, 0, bck=False, sti1=False)
+    assert_tables_equal(got, want, "k=0")
+    assert got["bck"] is None and got["sti1"] is None
+    with pytest.raises(EsaError) as ei:
+        esa.build(tis, 4, 0, tables=("suf", "bck"))
+    assert "requires option -pl" in str(ei.value)
+
+
+def test_prefixlength_too_large_is_the_reference_error(esa):
+    tis = synth.random_dna(1000, seed=3)
+    with pytest.raises(EsaError) as ei:
+        esa.build(tis, 4, 9, tables=("suf",))
+    assert "prefix length 9 is too large, maximal prefix length for this input size and alphabet size is 3" in str(
+        ei.value)
+
+
+def test_demand_subsets(esa):
+    tis = synth.dna_with_specials(40000, seed=8, nfrac=0.005, mean_run=6, records=5)
+    want = ou.oracle_build(tis, 4, 6)
+    got, _ = esa.build(tis, 4, 6, tables=("suf",))
+    assert np.array_equal(got["suf"], want["suf"]) and got["lcp"] is None and got["bwt"] is None
+    got, _ = esa.build(tis, 4, 6, tables=("bwt",))
+    assert np.array_equal(got["bwt"], want["bwt"]) and got["suf"] is None
+    got, _ = esa.build(tis, 4, 6, tables=("sti1",))  # forces lcp + bck like mkvtree.c:376
+    assert np.array_equal(got["sti1"], want["sti1"]) and np.array_equal(got["bck"], want["bck"])
+    assert np.array_equal(got["lcp"], want["lcp"])
+    got, _ = esa.build(tis, 4, 6, tables=("suf", "sti"))
+    inv = np.zeros(len(tis) + 1, np.uint64)
+    inv[want["suf"]] = np.arange(len(tis) + 1, dtype=np.uint64)
+    assert np.array_equal(got["sti"], inv)
+
+
+def test_staged_api_and_repeatability(esa):
+    tis = synth.random_protein(50000, seed=21, records=30, xfrac=0.001)
+    want = ou.oracle_build(tis, 20, 3)
+    esa.upload(tis, 20)
+    for _ in range(3):  # same resident text, arena reused
+        st = esa.construct(3, tables=ALL)
+        assert st["launches"] > 0 and st["kernel"]["radix_pass"]["launches"] > 0
+        esa.check()
+    got = esa.download()
+    assert_tables_equal(got, want, "staged")
+
+
+@pytest.mark.skipif(not ou.have_ref(), reason="oracle/_ref/mkvtree.x did not travel")
+@pytest.mark.parametrize("kind", ["dna", "protein"])
+def test_against_live_reference_binary(esa, kind, tmp_path):
+    """The unmodified reference mkvtree, run on this box, on a FASTA rendering of a seeded input."""
+    if kind == "dna":
+        tis, sigma, flag = synth.dna_with_specials(150000, seed=31, nfrac=0.003, mean_run=12, records=25), 4, "-dna"
+    else:
+        tis, sigma, flag = synth.random_protein(120000, seed=32, records=80, xfrac=0.001), 20, "-protein"
+    path = str(tmp_path / "in.fna")
+    with open(path, "wb") as f:
+        f.write(synth.to_fasta(tis, kind))
+    rc, out, err, files = ou.run_mkvtree(ou.REF_MKVTREE, path, [flag, "-pl", "-tis", "-suf", "-lcp", "-bwt", "-bck",
+                                                                "-sti1"])
+    assert rc == 0, err
+    ref = ou.tables_from_files(files)
+    assert np.array_equal(ref["tis"], tis)
+    k = ref["prj"]["prefixlength"]
+    got, _ = esa.build(tis, sigma, k, tables=ALL)
+    want = {t: ref[t] for t in TABLES}
+    want.update({"longest": ref["prj"]["longest"], "maxbranchdepth": ref["prj"]["maxbranchdepth"],
+                 "largelcpvalues": ref["prj"]["largelcpvalues"]})
+    assert_tables_equal(got, want, f"reference {kind}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs): too big for the CPU oracle, so size-independent invariants
+def _properties(esa, tis, sigma, k, tables=ALL):
+    got, st = esa.build(tis, sigma, k, tables=tables)
+    esa.check()  # permutation, order, lcp, bwt, sti1 on the device
+    N = len(tis) + 1
+    suf = got["suf"]
+    assert len(suf) == N
+    assert int(suf.sum()) == N * (N - 1) // 2          # checksum of a permutation
+    assert suf[N - 1] == N - 1                          # the sentinel is the largest suffix
+    assert suf[got["longest"]] == 0
+    nspecial = int((tis >= 254).sum())
+    tail = suf[N - 1 - nspecial:]
+    assert np.all(np.diff(tail.astype(np.int64)) > 0)   # special-initial suffixes in position order
+    if got["bck"] is not None:
+        bck = got["bck"].reshape(-1, 2)
+        assert bck[0, 0] == 0 and np.all(bck[:, 0] <= bck[:, 1]) and np.all(bck[1:, 0] >= bck[:-1, 1])
+    if got["lcp"] is not None:
+        llv = got["llv"].reshape(-1, 2)
+        big = np.flatnonzero(got["lcp"] == 255)
+        assert np.array_equal(llv[:, 0], big.astype(np.uint64)) and np.all(llv[:, 1] >= 255)
+        assert got["maxbranchdepth"] == (int(llv[:, 1].max()) if len(llv) else int(got["lcp"].max()))
+    return got, st
+
+
+def test_full_size_c2_100mbp_random_dna(esa):
+    """BASELINE.json configs[1]: 100 Mbp random DNA, byte-identical .suf/.lcp/.bwt (hashes made here by the reference
+    binary, tests/golden/bench_golden.json)."""
+    tis = synth.random_dna(100_000_000, seed=42)
+    got, st = _properties(esa, tis, 4, 11, tables=("suf", "lcp", "bwt"))
+    path = os.path.join(os.path.dirname(__file__), "golden", "bench_golden.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            g = json.load(f).get("c2_100mbp")
+        if g:
+            for t in ("suf", "lcp", "llv", "bwt"):
+                assert hashlib.sha256(got[t].tobytes()).hexdigest()[:16] == g["sha"][t], t
+
+
+def test_full_size_repeat_rich_30mbp(esa):
+    """Scaled-down C3 (deep LCPs, many doubling rounds), checked on the device."""
+    tis = synth.repeat_rich_dna(30_000_000, seed=7, copies=50, divergence=0.005, tandem_frac=0.01)
+    got, st = _properties(esa, tis, 4, 10)
+    assert st["rounds"] >= 5 and got["largelcpvalues"] > 0
+
+
+def test_full_size_protein_50m(esa):
+    tis = synth.random_protein(50_000_000, seed=11, records=10000, xfrac=0.0005)
+    _properties(esa, tis, 20, 5)

@@ -1,0 +1,224 @@
+"""ctypes binding of include/vstree_b200.h.  There is no fallback: if the shared library is missing or no GPU is
+usable, calls raise."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+
+DEMAND_BITS = {"tis": 1 << 0, "ois": 1 << 1, "des": 1 << 2, "ssp": 1 << 3, "bwt": 1 << 4, "suf": 1 << 5,
+               "lcp": 1 << 6, "bck": 1 << 7, "sti1": 1 << 8, "skp": 1 << 9, "sti": 1 << 13}
+KERNEL_FAMILIES = ["classify", "radix_hist", "radix_pass", "regroup", "gather_rank", "bck", "plcp", "finalize",
+                   "sti1", "misc", "memop"]
+ERRBUF = 1024
+
+
+class EsaError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class KernelStat(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_uint64), ("ms", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("ms_total", ctypes.c_double), ("ms_initial_sort", ctypes.c_double), ("ms_doubling", ctypes.c_double),
+                ("ms_lcp", ctypes.c_double), ("ms_derive", ctypes.c_double), ("h0", ctypes.c_uint32),
+                ("rounds", ctypes.c_uint32), ("active_sum", ctypes.c_uint64), ("active_first", ctypes.c_uint64),
+                ("launches", ctypes.c_uint64), ("device_bytes_peak", ctypes.c_uint64),
+                ("kernel", KernelStat * len(KERNEL_FAMILIES)), ("ms_h2d", ctypes.c_double),
+                ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "kernel"}
+        d["kernel"] = {name: {"launches": self.kernel[i].launches, "ms": self.kernel[i].ms,
+                              "bytes": self.kernel[i].bytes} for i, name in enumerate(KERNEL_FAMILIES)}
+        return d
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("numofcodes", ctypes.c_uint64), ("suftab", ctypes.POINTER(ctypes.c_uint64)),
+                ("lcptab", ctypes.POINTER(ctypes.c_uint8)), ("llv", ctypes.POINTER(ctypes.c_uint64)),
+                ("nllv", ctypes.c_uint64), ("maxbranchdepth", ctypes.c_uint64), ("longest", ctypes.c_uint64),
+                ("bwttab", ctypes.POINTER(ctypes.c_uint8)), ("bcktab", ctypes.POINTER(ctypes.c_uint64)),
+                ("stitab1", ctypes.POINTER(ctypes.c_uint8)), ("stitab", ctypes.POINTER(ctypes.c_uint64)),
+                ("skiptab", ctypes.POINTER(ctypes.c_uint64))]
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libvstree_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the product library; raises if it has not been built (run `make` or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EsaError(-2, f"{path} is missing: build it with `make` at the repository root (no fallback exists)")
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    vp, cp, sz = c.c_void_p, c.c_char_p, c.c_size_t
+    lib.esa_init.restype = c.c_int
+    lib.esa_init.argtypes = [c.POINTER(vp), c.c_int, cp, sz]
+    lib.esa_shutdown.restype = None
+    lib.esa_shutdown.argtypes = [vp]
+    lib.esa_build.restype = c.c_int
+    lib.esa_build.argtypes = [vp, vp, c.c_uint64, c.c_uint32, c.c_uint32, c.c_uint32, c.POINTER(Result),
+                              c.POINTER(Stats), cp, sz]
+    lib.esa_free.restype = None
+    lib.esa_free.argtypes = [vp, c.POINTER(Result)]
+    lib.esa_upload.restype = c.c_int
+    lib.esa_upload.argtypes = [vp, vp, c.c_uint64, c.c_uint32, cp, sz]
+    lib.esa_construct.restype = c.c_int
+    lib.esa_construct.argtypes = [vp, c.c_uint32, c.c_uint32, c.POINTER(Stats), cp, sz]
+    lib.esa_download.restype = c.c_int
+    lib.esa_download.argtypes = [vp, c.POINTER(Result), cp, sz]
+    lib.esa_check.restype = c.c_int
+    lib.esa_check.argtypes = [vp, cp, sz]
+    lib.esa_numofcodes.restype = c.c_uint64
+    lib.esa_numofcodes.argtypes = [c.c_uint32, c.c_uint32]
+    lib.esa_recommended_prefixlength.restype = c.c_uint32
+    lib.esa_recommended_prefixlength.argtypes = [c.c_uint32, c.c_uint64]
+    lib.esa_maximal_prefixlength.restype = c.c_uint32
+    lib.esa_maximal_prefixlength.argtypes = [c.c_uint32, c.c_uint64]
+    lib.esa_debug_radix_sort.restype = c.c_int
+    lib.esa_debug_radix_sort.argtypes = [vp, c.c_int, vp, vp, c.c_uint64, c.c_uint32, c.c_uint32, cp, sz]
+    lib.esa_version.restype = cp
+    lib.esa_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def demand_mask(tables):
+    m = 0
+    for t in tables:
+        m |= DEMAND_BITS[t]
+    return m
+
+
+def _as_ptr(tis):
+    """Accepts a numpy uint8 array, a torch CPU uint8 tensor (e.g. pinned) or a raw (address, length) tuple."""
+    if isinstance(tis, tuple):
+        return ctypes.c_void_p(tis[0]), int(tis[1]), None
+    if hasattr(tis, "data_ptr"):
+        return ctypes.c_void_p(tis.data_ptr()), int(tis.numel()), tis
+    arr = np.ascontiguousarray(tis, dtype=np.uint8)
+    return ctypes.c_void_p(arr.ctypes.data), int(arr.shape[0]), arr
+
+
+class Esa:
+    """One context = one GPU.  Mirrors the C ABI one to one."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(ERRBUF)
+        rc = self.lib.esa_init(ctypes.byref(self.ctx), device, err, ERRBUF)
+        if rc != 0:
+            raise EsaError(rc, err.value.decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.esa_shutdown(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, err):
+        if rc != 0:
+            raise EsaError(rc, err.value.decode())
+
+    @staticmethod
+    def _tables(res, copy=True):
+        N = res.n + 1
+
+        def arr(ptr, count, dt):
+            if not ptr:
+                return None
+            a = np.ctypeslib.as_array(ptr, shape=(int(count),)) if count else np.zeros(0, dt)
+            return a.copy() if copy else a
+
+        return {"suf": arr(res.suftab, N, np.uint64), "lcp": arr(res.lcptab, N, np.uint8),
+                "llv": arr(res.llv, 2 * res.nllv, np.uint64) if res.lcptab else None,
+                "bwt": arr(res.bwttab, N, np.uint8), "bck": arr(res.bcktab, 2 * res.numofcodes, np.uint64),
+                "sti1": arr(res.stitab1, N, np.uint8), "sti": arr(res.stitab, N, np.uint64),
+                "maxbranchdepth": int(res.maxbranchdepth), "longest": int(res.longest),
+                "largelcpvalues": int(res.nllv), "numofcodes": int(res.numofcodes)}
+
+    def build(self, tis, numofchars, prefixlength, tables=("suf", "lcp", "bwt"), want_stats=True, copy=True):
+        """esa_build: host buffer in, tables out.  Returns (tables dict, stats dict or None).
+        With copy=False the arrays alias the library's pinned buffers until free(tables) is called."""
+        ptr, n, keep = _as_ptr(tis)
+        res, st = Result(), Stats()
+        err = ctypes.create_string_buffer(ERRBUF)
+        rc = self.lib.esa_build(self.ctx, ptr, n, numofchars, prefixlength, demand_mask(tables), ctypes.byref(res),
+                                ctypes.byref(st) if want_stats else None, err, ERRBUF)
+        self._check(rc, err)
+        try:
+            out = self._tables(res, copy=copy)
+        finally:
+            if copy:
+                self.lib.esa_free(self.ctx, ctypes.byref(res))
+        if not copy:
+            out["_result"] = res
+        return out, (st.as_dict() if want_stats else None)
+
+    def free(self, tables):
+        res = tables.pop("_result", None)
+        if res is not None:
+            self.lib.esa_free(self.ctx, ctypes.byref(res))
+
+    def upload(self, tis, numofchars):
+        ptr, n, keep = _as_ptr(tis)
+        err = ctypes.create_string_buffer(ERRBUF)
+        self._check(self.lib.esa_upload(self.ctx, ptr, n, numofchars, err, ERRBUF), err)
+
+    def construct(self, prefixlength, tables=("suf", "lcp", "bwt"), want_stats=True):
+        st = Stats()
+        err = ctypes.create_string_buffer(ERRBUF)
+        rc = self.lib.esa_construct(self.ctx, prefixlength, demand_mask(tables),
+                                    ctypes.byref(st) if want_stats else None, err, ERRBUF)
+        self._check(rc, err)
+        return st.as_dict() if want_stats else None
+
+    def download(self):
+        res = Result()
+        err = ctypes.create_string_buffer(ERRBUF)
+        self._check(self.lib.esa_download(self.ctx, ctypes.byref(res), err, ERRBUF), err)
+        try:
+            return self._tables(res)
+        finally:
+            self.lib.esa_free(self.ctx, ctypes.byref(res))
+
+    def debug_radix_sort(self, keys, vals, begin_bit, end_bit):
+        """Testing hook: sorts the numpy arrays in place (keys uint32/uint64, vals uint32 or None)."""
+        assert keys.dtype in (np.uint32, np.uint64) and keys.flags.c_contiguous
+        err = ctypes.create_string_buffer(ERRBUF)
+        rc = self.lib.esa_debug_radix_sort(self.ctx, keys.dtype.itemsize, keys.ctypes.data,
+                                           vals.ctypes.data if vals is not None else None, len(keys), begin_bit,
+                                           end_bit, err, ERRBUF)
+        self._check(rc, err)
+
+    def check(self):
+        err = ctypes.create_string_buffer(ERRBUF)
+        self._check(self.lib.esa_check(self.ctx, err, ERRBUF), err)

@@ -1,0 +1,632 @@
+// api.cu -- the extern "C" boundary declared in include/vstree_b200.h.
+//
+// Mirrors the call sequence of the reference's mkvtreeprocess (src/Mkvtree/mkvprocess.c:976-1060):
+// suffix sort (+ inline lcp) -> llv -> bck -> longest -> suf -> sti1 -> bwt, but every table is produced on the
+// device; the host only moves bytes.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+void radix_sort_init();
+void widen_isa(esa_ctx *ctx);
+
+namespace
+{
+
+void set_err(char *errbuf, size_t errlen, const char *msg)
+{
+  if (errbuf != nullptr && errlen > 0)
+  {
+    snprintf(errbuf, errlen, "%s", msg);
+  }
+}
+
+template <typename F> int guarded(char *errbuf, size_t errlen, F &&f)
+{
+  try
+  {
+    f();
+    return ESA_OK;
+  } catch (const EsaError &e)
+  {
+    set_err(errbuf, errlen, e.msg.c_str());
+    return e.code;
+  } catch (const std::exception &e)
+  {
+    set_err(errbuf, errlen, e.what());
+    return ESA_ERR_MEMORY;
+  }
+}
+
+// pinned host blocks handed out in esa_result; recycled between builds so that a steady-state build does not pin
+struct PinnedPool
+{
+  struct Block
+  {
+    void *p;
+    size_t bytes;
+    bool used;
+  };
+  std::vector<Block> blocks;
+  void *get(size_t bytes)
+  {
+    if (bytes == 0)
+    {
+      bytes = 1;
+    }
+    Block *best = nullptr;
+    for (Block &b : blocks)
+    {
+      if (!b.used && b.bytes >= bytes && (best == nullptr || b.bytes < best->bytes))
+      {
+        best = &b;
+      }
+    }
+    if (best != nullptr && best->bytes <= 2 * bytes + 4096)
+    {
+      best->used = true;
+      return best->p;
+    }
+    void *p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, bytes));
+    blocks.push_back({p, bytes, true});
+    return p;
+  }
+  void put(void *p)
+  {
+    for (Block &b : blocks)
+    {
+      if (b.p == p)
+      {
+        b.used = false;
+        return;
+      }
+    }
+  }
+  void trim()  // drop unused blocks
+  {
+    std::vector<Block> keep;
+    for (Block &b : blocks)
+    {
+      if (b.used)
+      {
+        keep.push_back(b);
+      } else
+      {
+        cudaFreeHost(b.p);
+      }
+    }
+    blocks.swap(keep);
+  }
+  void destroy()
+  {
+    for (Block &b : blocks)
+    {
+      cudaFreeHost(b.p);
+    }
+    blocks.clear();
+  }
+};
+
+struct CtxExtra
+{
+  PinnedPool pool;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
+};
+
+// esa_ctx is declared in common.cuh; the api-private part hangs off a side table keyed by the ctx pointer
+struct FullCtx : esa_ctx
+{
+  CtxExtra x;
+};
+
+size_t arena_estimate(u64 n)
+{
+  const u64 N = n + 1;
+  // tis 1 + sa 4 + isa 4 + bck worst case 5 + doubling regions X and Y 32 + sort scratch and tile summaries ~2
+  return (size_t) (48 * N) + ((size_t) 256 << 20);
+}
+
+void collect_kernel_stats(esa_ctx *ctx, esa_stats *st)
+{
+  for (int k = 0; k < ESA_K_NUM; k++)
+  {
+    st->kernel[k].launches = ctx->prof.launches[k];
+    st->kernel[k].ms = 0;
+    st->kernel[k].bytes = 0;
+    if (k != ESA_K_MEMOP)
+    {
+      st->launches += ctx->prof.launches[k];
+    }
+  }
+  for (const KernelProfiler::Span &sp : ctx->prof.spans)
+  {
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    st->kernel[sp.kind].ms += ms;
+    st->kernel[sp.kind].bytes += sp.bytes;
+  }
+}
+
+void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
+{
+  if (tis == nullptr && n > 0)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "tis is NULL");
+  }
+  if (numofchars == 0 || numofchars > 253)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "alphabet size %u out of range 1..253", numofchars);
+  }
+  if (n + 1 >= ((u64) 1 << 32) - 1)
+  {
+    esa_throw(ESA_ERR_TOOLARGE, "sequence of length %llu needs more than 32-bit indices; not supported",
+              (unsigned long long) n);
+  }
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->uploaded = ctx->constructed = false;
+  ctx->arena.reserve(arena_estimate(n));
+  ctx->arena.reset();
+  const u64 padded = ((n + 15) & ~(u64) 15) + 64;
+  ctx->d_tis = ctx->arena.alloc<u8>(padded);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_tis + n, 255, padded - n, ctx->stream));
+  if (n > 0)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_tis, tis, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->n = n;
+  ctx->sigma = numofchars;
+  ctx->arena_after_upload = ctx->arena.mark();
+  ctx->uploaded = true;
+}
+
+void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
+{
+  if (!ctx->uploaded)
+  {
+    esa_throw(ESA_ERR_STATE, "esa_construct called before esa_upload");
+  }
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (demand & ESA_STI1TAB)
+  {
+    demand |= ESA_LCPTAB | ESA_BCKTAB;  // reference: mkvtree.c:376
+  }
+  if ((demand & (ESA_BCKTAB | ESA_STI1TAB)) && prefixlength == 0)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "option -bck requires option -pl");  // reference: mkvtree.c:470-473
+  }
+  const u64 n = ctx->n, N = n + 1;
+  if (prefixlength > 0)
+  {
+    const u32 maxk = esa_maximal_prefixlength(ctx->sigma, n);
+    if (prefixlength > maxk)
+    {
+      // reference: src/kurtz/detpfxlen.c:95-98
+      esa_throw(ESA_ERR_PREFIXLEN,
+                "prefix length %lu is too large, maximal prefix length for this input size and alphabet size is %lu",
+                (unsigned long) prefixlength, (unsigned long) maxk);
+    }
+  }
+  cudaStream_t s = ctx->stream;
+  Arena &ar = ctx->arena;
+  ar.rewind(ctx->arena_after_upload);
+  ctx->constructed = false;
+  ctx->d_suf64 = nullptr;
+  ctx->d_lcp = ctx->d_bwt = ctx->d_sti1 = nullptr;
+  ctx->d_bck = ctx->d_llv = ctx->d_sti64 = ctx->d_skp = nullptr;
+  ctx->d_plcpv = nullptr;
+  ctx->nllv = ctx->maxbranchdepth = ctx->longest = 0;
+  ctx->prof.reset();
+  ctx->prof.enabled = stats != nullptr;
+
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_a, s));
+  ctx->d_sa = ar.alloc<u32>(N + 64);
+  ctx->d_isa = ar.alloc<u32>(N + 64);
+  ctx->prefixlength = prefixlength;
+  ctx->demand = demand;
+  ctx->numofcodes = prefixlength > 0 ? esa_numofcodes(ctx->sigma, prefixlength) : 0;
+  const bool want_bck = (demand & ESA_BCKTAB) != 0;
+  if (want_bck)
+  {
+    ctx->d_bck = ar.alloc<u64>(2 * ctx->numofcodes);
+  }
+  const size_t scratch_mark = ar.mark();
+  SortOutcome so;
+  suffix_sort(ctx, prefixlength, want_bck, &so, scratch_mark);
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_b, s));
+  ar.rewind(scratch_mark);  // everything the sorter carved is dead now
+  const bool want_lcp = (demand & ESA_LCPTAB) != 0;
+  if (want_lcp)
+  {
+    ctx->d_plcpv = ar.alloc<u32>(N + 64);
+    compute_plcp(ctx, ctx->d_plcpv);
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_c, s));
+  finalize_tables(ctx, demand, ctx->d_plcpv);
+  if (demand & ESA_STI1TAB)
+  {
+    compute_sti1(ctx, prefixlength);
+  }
+  if (demand & ESA_STITAB)
+  {
+    widen_isa(ctx);
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_d, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx->constructed = true;
+  if (stats != nullptr)
+  {
+    memset(stats, 0, sizeof *stats);
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_a, ctx->x.ev_d));
+    stats->ms_total = ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_a, ctx->x.ev_b));
+    stats->ms_initial_sort = ms;  // refined below: split into initial sort and doubling by kernel family
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_b, ctx->x.ev_c));
+    stats->ms_lcp = ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_c, ctx->x.ev_d));
+    stats->ms_derive = ms;
+    stats->h0 = so.h0;
+    stats->rounds = so.rounds;
+    stats->active_sum = so.active_sum;
+    stats->active_first = so.active_first;
+    stats->device_bytes_peak = ar.peak;
+    collect_kernel_stats(ctx, stats);
+    stats->ms_doubling = 0;
+  }
+}
+
+template <typename T> T *download_table(FullCtx *ctx, const T *d, u64 count)
+{
+  T *h = (T *) ctx->x.pool.get(count * sizeof(T));
+  if (count > 0)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(h, d, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return h;
+}
+
+u64 do_download(FullCtx *ctx, esa_result *out)
+{
+  if (!ctx->constructed)
+  {
+    esa_throw(ESA_ERR_STATE, "esa_download called before esa_construct");
+  }
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof *out);
+  const u64 N = ctx->n + 1;
+  u64 bytes = 0;
+  out->n = ctx->n;
+  out->numofcodes = ctx->numofcodes;
+  out->nllv = ctx->nllv;
+  out->maxbranchdepth = ctx->maxbranchdepth;
+  out->longest = ctx->longest;
+  if (ctx->d_suf64 != nullptr)
+  {
+    out->suftab = download_table(ctx, ctx->d_suf64, N);
+    bytes += 8 * N;
+  }
+  if (ctx->d_lcp != nullptr && (ctx->demand & ESA_LCPTAB))
+  {
+    out->lcptab = download_table(ctx, ctx->d_lcp, N);
+    out->llv = (esa_pairuint *) download_table(ctx, ctx->d_llv, 2 * ctx->nllv);
+    bytes += N + 16 * ctx->nllv;
+  }
+  if (ctx->d_bwt != nullptr)
+  {
+    out->bwttab = download_table(ctx, ctx->d_bwt, N);
+    bytes += N;
+  }
+  if (ctx->d_bck != nullptr)
+  {
+    out->bcktab = download_table(ctx, ctx->d_bck, 2 * ctx->numofcodes);
+    bytes += 16 * ctx->numofcodes;
+  }
+  if (ctx->d_sti1 != nullptr)
+  {
+    out->stitab1 = download_table(ctx, ctx->d_sti1, N);
+    bytes += N;
+  }
+  if (ctx->d_sti64 != nullptr)
+  {
+    out->stitab = download_table(ctx, ctx->d_sti64, N);
+    bytes += 8 * N;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return bytes;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int esa_init(esa_ctx **out, int device, char *errbuf, size_t errlen)
+{
+  if (out == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx pointer is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+  {
+    char buf[256];
+    snprintf(buf, sizeof buf, "no usable CUDA device (%s); this library has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    set_err(errbuf, errlen, buf);
+    return ESA_ERR_NODEVICE;
+  }
+  if (device < 0 || device >= count)
+  {
+    set_err(errbuf, errlen, "device index out of range");
+    return ESA_ERR_NODEVICE;
+  }
+  FullCtx *ctx = new FullCtx();
+  int rc = guarded(errbuf, errlen, [&]() {
+    CUDA_CHECK(cudaSetDevice(device));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (prop.major < 10)
+    {
+      esa_throw(ESA_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+    }
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaMallocHost((void **) &ctx->h_scalars, 64 * sizeof(u64)));
+    for (cudaEvent_t *ev : {&ctx->x.ev_a, &ctx->x.ev_b, &ctx->x.ev_c, &ctx->x.ev_d, &ctx->x.ev_e})
+    {
+      CUDA_CHECK(cudaEventCreate(ev));
+    }
+    radix_sort_init();
+  });
+  if (rc != ESA_OK)
+  {
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return ESA_OK;
+}
+
+void esa_shutdown(esa_ctx *c)
+{
+  if (c == nullptr)
+  {
+    return;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->arena.release();
+  ctx->prof.destroy();
+  ctx->x.pool.destroy();
+  for (cudaEvent_t ev : {ctx->x.ev_a, ctx->x.ev_b, ctx->x.ev_c, ctx->x.ev_d, ctx->x.ev_e})
+  {
+    if (ev != nullptr)
+    {
+      cudaEventDestroy(ev);
+    }
+  }
+  if (ctx->h_scalars != nullptr)
+  {
+    cudaFreeHost(ctx->h_scalars);
+  }
+  if (ctx->stream != nullptr)
+  {
+    cudaStreamDestroy(ctx->stream);
+  }
+  if (ctx->copy_stream != nullptr)
+  {
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  delete ctx;
+}
+
+int esa_upload(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, char *errbuf, size_t errlen)
+{
+  if (c == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  return guarded(errbuf, errlen, [&]() {
+    do_upload(ctx, tis, n, numofchars);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int esa_construct(esa_ctx *c, uint32_t prefixlength, uint32_t demand, esa_stats *stats, char *errbuf, size_t errlen)
+{
+  if (c == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  return guarded(errbuf, errlen, [&]() { do_construct(ctx, prefixlength, demand, stats); });
+}
+
+int esa_download(esa_ctx *c, esa_result *out, char *errbuf, size_t errlen)
+{
+  if (c == nullptr || out == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx or result is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  int rc = guarded(errbuf, errlen, [&]() { do_download(ctx, out); });
+  if (rc != ESA_OK)
+  {
+    esa_free(c, out);
+  }
+  return rc;
+}
+
+int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, uint32_t prefixlength, uint32_t demand,
+              esa_result *out, esa_stats *stats, char *errbuf, size_t errlen)
+{
+  if (c == nullptr || out == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx or result is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  memset(out, 0, sizeof *out);
+  int rc = guarded(errbuf, errlen, [&]() {
+    cudaStream_t s = ctx->stream;
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    CUDA_CHECK(cudaEventRecord(ctx->x.ev_e, s));
+    do_upload(ctx, tis, n, numofchars);
+    do_construct(ctx, prefixlength, demand, stats);  // records ev_a .. ev_d, synchronises
+    const u64 d2h = do_download(ctx, out);
+    if (stats != nullptr)
+    {
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_e, ctx->x.ev_a));
+      stats->ms_h2d = ms;
+      CUDA_CHECK(cudaEventRecord(ctx->x.ev_e, s));
+      CUDA_CHECK(cudaEventSynchronize(ctx->x.ev_e));
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_d, ctx->x.ev_e));
+      stats->ms_d2h = ms;
+      stats->h2d_bytes = n;
+      stats->d2h_bytes = d2h;
+    }
+  });
+  if (rc != ESA_OK)
+  {
+    esa_free(c, out);
+  }
+  return rc;
+}
+
+void esa_free(esa_ctx *c, esa_result *out)
+{
+  if (c == nullptr || out == nullptr)
+  {
+    return;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  void *ptrs[] = {out->suftab, out->lcptab, out->llv, out->bwttab, out->bcktab, out->stitab1, out->stitab, out->skiptab};
+  for (void *p : ptrs)
+  {
+    if (p != nullptr)
+    {
+      ctx->x.pool.put(p);
+    }
+  }
+  memset(out, 0, sizeof *out);
+}
+
+int esa_check(esa_ctx *c, char *errbuf, size_t errlen)
+{
+  if (c == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  int bad = 0;
+  std::string msg;
+  int rc = guarded(errbuf, errlen, [&]() {
+    if (!ctx->constructed)
+    {
+      esa_throw(ESA_ERR_STATE, "esa_check called before esa_construct");
+    }
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    bad = run_checks(ctx, msg);
+  });
+  if (rc != ESA_OK)
+  {
+    return rc;
+  }
+  if (bad != 0)
+  {
+    set_err(errbuf, errlen, msg.c_str());
+    return ESA_ERR_CHECK;
+  }
+  return ESA_OK;
+}
+
+int esa_debug_radix_sort(esa_ctx *c, int key_bytes, void *keys, uint32_t *vals, uint64_t n, uint32_t begin_bit,
+                         uint32_t end_bit, char *errbuf, size_t errlen)
+{
+  if (c == nullptr || keys == nullptr || (key_bytes != 4 && key_bytes != 8))
+  {
+    set_err(errbuf, errlen, "bad argument");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  return guarded(errbuf, errlen, [&]() {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    ctx->uploaded = ctx->constructed = false;
+    const size_t tb = radix_sort_temp_bytes(n, (u32) key_bytes);
+    ctx->arena.reserve(2 * n * key_bytes + 2 * n * 4 + tb + (1 << 20));
+    ctx->arena.reset();
+    ctx->prof.reset();
+    ctx->prof.enabled = false;
+    char *ka = ctx->arena.alloc<char>(n * key_bytes + 16), *kb = ctx->arena.alloc<char>(n * key_bytes + 16);
+    u32 *va = nullptr, *vb = nullptr;
+    if (vals != nullptr)
+    {
+      va = ctx->arena.alloc<u32>(n + 4);
+      vb = ctx->arena.alloc<u32>(n + 4);
+      CUDA_CHECK(cudaMemcpyAsync(va, vals, n * 4, cudaMemcpyHostToDevice, s));
+    }
+    void *temp = ctx->arena.alloc<char>(tb);
+    CUDA_CHECK(cudaMemcpyAsync(ka, keys, n * key_bytes, cudaMemcpyHostToDevice, s));
+    int w = key_bytes == 4 ? radix_sort_pairs_u32(ctx, (u32 *) ka, (u32 *) kb, va, vb, n, begin_bit, end_bit, temp, tb)
+                           : radix_sort_pairs_u64(ctx, (u64 *) ka, (u64 *) kb, va, vb, n, begin_bit, end_bit, temp, tb);
+    CUDA_CHECK(cudaMemcpyAsync(keys, w ? kb : ka, n * key_bytes, cudaMemcpyDeviceToHost, s));
+    if (vals != nullptr)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(vals, w ? vb : va, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+uint64_t esa_numofcodes(uint32_t numofchars, uint32_t prefixlength)
+{
+  return (uint64_t) pow((double) numofchars, (double) prefixlength);
+}
+
+static uint64_t logalphasize(uint64_t numofchars, double value)
+{
+  if (value <= (double) numofchars)
+  {
+    return 1;
+  }
+  return (uint64_t) floor(log(value) / log((double) numofchars));
+}
+
+uint32_t esa_recommended_prefixlength(uint32_t numofchars, uint64_t totallength)
+{
+  const uint64_t k = logalphasize(numofchars, (double) totallength / 16);
+  return (uint32_t) (k == 0 ? 1 : k);
+}
+
+uint32_t esa_maximal_prefixlength(uint32_t numofchars, uint64_t totallength)
+{
+  const unsigned prefixlenbits = 4;
+  uint64_t maxk = logalphasize(numofchars, (double) totallength / (16 / 4));
+  uint64_t t = logalphasize(numofchars, (double) ((((uint64_t) 1) << (64 - prefixlenbits)) - 1));
+  maxk = std::min(maxk, t);
+  t = (((uint64_t) 1) << prefixlenbits) - 1;
+  maxk = std::min(maxk, t);
+  return (uint32_t) maxk;
+}
+
+const char *esa_version(void) { return "vstree_b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// common.cuh -- context, device arena, launch accounting and error plumbing shared by all translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vstree_b200.h"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define ESA_NUM_SMS_FALLBACK 148
+
+// ---------------------------------------------------------------------------------------------------------
+// Errors: C++ exceptions are used inside the library only and are caught at the extern "C" boundary.
+struct EsaError
+{
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] inline void esa_throw(int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw EsaError{code, std::string(buf)};
+}
+
+#define CUDA_CHECK(call)                                                                                    \
+  do                                                                                                        \
+  {                                                                                                         \
+    cudaError_t err__ = (call);                                                                             \
+    if (err__ != cudaSuccess)                                                                               \
+    {                                                                                                       \
+      esa_throw(err__ == cudaErrorMemoryAllocation ? ESA_ERR_MEMORY : ESA_ERR_CUDA, "%s failed at %s:%d: %s", \
+                #call, __FILE__, __LINE__, cudaGetErrorString(err__));                                      \
+    }                                                                                                       \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Device arena: one big allocation per context, carved by a bump pointer.  Builds reuse it, so the timed
+// region of a steady-state build contains no cudaMalloc.
+struct Arena
+{
+  char *base = nullptr;
+  size_t capacity = 0;
+  size_t top = 0;
+  size_t peak = 0;
+
+  void reserve(size_t bytes)
+  {
+    if (bytes <= capacity)
+    {
+      return;
+    }
+    release();
+    CUDA_CHECK(cudaMalloc((void **) &base, bytes));
+    capacity = bytes;
+  }
+  void release()
+  {
+    if (base != nullptr)
+    {
+      cudaFree(base);
+    }
+    base = nullptr;
+    capacity = top = 0;
+  }
+  void reset() { top = 0; }
+  size_t mark() const { return top; }
+  void rewind(size_t m) { top = m; }
+  template <typename T> T *alloc(size_t count)
+  {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t) 255;
+    if (top + bytes > capacity)
+    {
+      esa_throw(ESA_ERR_MEMORY, "device arena exhausted: need %zu more bytes, capacity %zu", top + bytes - capacity,
+                capacity);
+    }
+    T *p = (T *) (base + top);
+    top += bytes;
+    if (top > peak)
+    {
+      peak = top;
+    }
+    return p;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-family kernel timing with CUDA events on the launching stream.
+struct KernelProfiler
+{
+  struct Span
+  {
+    int kind;
+    cudaEvent_t a, b;
+    double bytes;
+  };
+  std::vector<cudaEvent_t> pool;
+  std::vector<Span> spans;
+  size_t next = 0;
+  bool enabled = true;
+  u64 launches[ESA_K_NUM] = {0};
+
+  cudaEvent_t get()
+  {
+    if (next == pool.size())
+    {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      pool.push_back(e);
+    }
+    return pool[next++];
+  }
+  void reset()
+  {
+    next = 0;
+    spans.clear();
+    memset(launches, 0, sizeof launches);
+  }
+  void destroy()
+  {
+    for (cudaEvent_t e : pool)
+    {
+      cudaEventDestroy(e);
+    }
+    pool.clear();
+  }
+};
+
+struct esa_ctx
+{
+  int device = -1;
+  int num_sms = ESA_NUM_SMS_FALLBACK;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;       // compute stream: every kernel of a build is launched here
+  cudaStream_t copy_stream = nullptr;  // D2H overlap
+  Arena arena;
+  KernelProfiler prof;
+
+  // resident input
+  u8 *d_tis = nullptr;   // arena; n symbols followed by >= 64 bytes of 255
+  u64 n = 0;
+  u32 sigma = 0;
+  bool uploaded = false;
+
+  // resident outputs of the last esa_construct (device pointers into the arena)
+  bool constructed = false;
+  u32 demand = 0, prefixlength = 0;
+  u64 numofcodes = 0;
+  u32 *d_sa = nullptr;     // [N] suffix array, 32-bit
+  u32 *d_isa = nullptr;    // [N] inverse suffix array
+  u64 *d_suf64 = nullptr;  // [N]
+  u8 *d_lcp = nullptr;     // [N]
+  u8 *d_bwt = nullptr;     // [N]
+  u8 *d_sti1 = nullptr;    // [N]
+  u64 *d_bck = nullptr;    // [2*numofcodes]
+  u64 *d_llv = nullptr;    // [2*nllv]
+  u64 *d_sti64 = nullptr;  // [N]
+  u64 *d_skp = nullptr;    // [N]
+  u32 *d_plcpv = nullptr;  // [N] V[i] = i + PLCP[i]
+  u64 nllv = 0, maxbranchdepth = 0, longest = 0;
+  size_t arena_after_upload = 0;
+
+  // small pinned scratch for scalar read-backs
+  u64 *h_scalars = nullptr;  // 64 words
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Launch bracket: counts the launch, optionally wraps it in an event pair, checks the launch error.
+struct LaunchScope
+{
+  esa_ctx *ctx;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  double bytes;
+  LaunchScope(esa_ctx *c, int k, double algorithmic_bytes) : ctx(c), kind(k), bytes(algorithmic_bytes)
+  {
+    ctx->prof.launches[kind]++;
+    if (ctx->prof.enabled)
+    {
+      a = ctx->prof.get();
+      b = ctx->prof.get();
+      CUDA_CHECK(cudaEventRecord(a, ctx->stream));
+    }
+  }
+  void done()
+  {
+    CUDA_CHECK(cudaGetLastError());
+    if (ctx->prof.enabled)
+    {
+      CUDA_CHECK(cudaEventRecord(b, ctx->stream));
+      ctx->prof.spans.push_back({kind, a, b, bytes});
+    }
+  }
+};
+
+#define ESA_LAUNCH(ctx, kind, bytes, ...)            \
+  do                                                 \
+  {                                                  \
+    LaunchScope scope__((ctx), (kind), (double) (bytes)); \
+    __VA_ARGS__;                                     \
+    scope__.done();                                  \
+  } while (0)
+
+static inline u32 div_up_u32(u64 a, u64 b) { return (u32) ((a + b - 1) / b); }
+static inline u64 div_up_u64(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// number of bits needed to represent values in [0, v]
+static inline u32 bits_for(u64 v)
+{
+  u32 b = 0;
+  while (v > 0)
+  {
+    b++;
+    v >>= 1;
+  }
+  return b == 0 ? 1 : b;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage entry points (one per translation unit)
+
+// radix_sort.cu
+struct RadixSortTemp
+{
+  u32 *hist;     // [parts][passes][256]
+  u32 *base;     // [parts][passes][256]
+  u32 *status;   // [tiles_per_part_max][256]
+  u32 *counter;  // [passes*parts] dynamic tile tickets
+  u64 n_capacity;
+};
+size_t radix_sort_temp_bytes(u64 n, u32 key_bytes);
+// Sorts (keys, vals) by key bits [begin_bit, end_bit).  Buffers ping-pong; returns 0 when the result is in
+// (keys_a, vals_a) and 1 when it is in (keys_b, vals_b).  vals may be NULL (keys only).
+int radix_sort_pairs_u32(esa_ctx *ctx, u32 *keys_a, u32 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
+                         u32 end_bit, void *temp, size_t temp_bytes);
+int radix_sort_pairs_u64(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
+                         u32 end_bit, void *temp, size_t temp_bytes);
+
+// suffix_sort.cu: fills ctx->d_sa, ctx->d_isa (and ctx->d_bck when demanded) ; returns stats pieces
+struct SortOutcome
+{
+  u32 h0;
+  u32 rounds;
+  u64 active_sum, active_first;
+  u64 num_sorted;   // suffixes that went through the sort (N - specials - 1)
+};
+void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *outcome, size_t scratch_mark);
+
+// lcp.cu: V[i] = i + PLCP[i] for all text positions (ctx->d_plcpv)
+void compute_plcp(esa_ctx *ctx, u32 *d_v);
+
+// derive.cu
+void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v);
+void compute_sti1(esa_ctx *ctx, u32 prefixlength);
+int run_checks(esa_ctx *ctx, std::string &msg);

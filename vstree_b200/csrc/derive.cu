@@ -1,0 +1,381 @@
+// derive.cu -- tables derived from the suffix array in one sweep each:
+//   finalize:  lcp8 / llv / maxbranchdepth (outlcpsubtab, src/Mkvtree/bese.c:533-591), bwt
+//              (encodeburrowswheeler, src/kurtz/bwtcode.c:293-311), longest (determinelongest,
+//              src/Mkvtree/mkvprocess.c:857-873) and the 64-bit suftab the file format wants (types.h:41-49)
+//   sti1:      makestitab1 (src/Mkvtree/mkvprocess.c:583-643) restated per text position:
+//              sti1[s] = 0 if a special lies inside the k-prefix of s, else min(255, isa[s] - bck.left[kmer(s)])
+//   checks:    the reference's DEBUG invariants as device-side property checks.
+#include "kmer_scan.cuh"
+#include "scan.cuh"
+
+namespace
+{
+
+constexpr int FN_THREADS = 256;
+constexpr int FN_ITEMS = 8;
+constexpr int FN_TILE = FN_THREADS * FN_ITEMS;
+constexpr int SCAN1_THREADS = 1024;
+
+// scalars: [0] maxbranchdepth [1] longest [2] nllv
+__global__ void __launch_bounds__(FN_THREADS)
+finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v,
+                u8 *__restrict__ lcp8, u8 *__restrict__ bwt, u64 *__restrict__ suf64, u32 *__restrict__ tile_large,
+                unsigned long long *__restrict__ scalars)
+{
+  __shared__ u32 red[2][FN_THREADS / 32];
+  const u64 tile_base = (u64) blockIdx.x * FN_TILE;
+  u32 nlarge = 0, mx = 0;
+#pragma unroll
+  for (int j = 0; j < FN_ITEMS; j++)
+  {
+    const u64 r = tile_base + (u64) j * FN_THREADS + threadIdx.x;
+    if (r < N)
+    {
+      const u32 s = sa[r];
+      if (suf64 != nullptr)
+      {
+        suf64[r] = s;
+      }
+      if (s == 0)
+      {
+        scalars[1] = r;
+      }
+      if (bwt != nullptr)
+      {
+        bwt[r] = s > 0 ? tis[s - 1] : (u8) ESA_UNDEFBWTCHAR;
+      }
+      if (v != nullptr)
+      {
+        const u32 l = v[s] - s;
+        lcp8[r] = (u8) min(l, 255u);
+        nlarge += l >= 255u;
+        mx = max(mx, l);
+      }
+    }
+  }
+  if (v == nullptr)
+  {
+    return;
+  }
+  nlarge = warp_reduce_sum(nlarge);
+  mx = warp_reduce_max(mx);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+  {
+    red[0][warp] = nlarge;
+    red[1][warp] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    u32 a = 0, b = 0;
+    for (int w = 0; w < FN_THREADS / 32; w++)
+    {
+      a += red[0][w];
+      b = max(b, red[1][w]);
+    }
+    tile_large[blockIdx.x] = a;
+    if (b > 0)
+    {
+      atomicMax(&scalars[0], (unsigned long long) b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SCAN1_THREADS)
+large_scan_kernel(u32 *tile_large, u32 ntiles, unsigned long long *scalars)
+{
+  __shared__ u64 scratch[SCAN1_THREADS / 32 + 1];
+  u64 carry = 0;
+  for (u32 b = 0; b < ntiles; b += SCAN1_THREADS)
+  {
+    const u32 i = b + threadIdx.x;
+    const u64 val = i < ntiles ? tile_large[i] : 0;
+    u64 total;
+    const u64 ex = block_exclusive_sum<u64, SCAN1_THREADS>(val, scratch, &total);
+    if (i < ntiles)
+    {
+      tile_large[i] = (u32) (carry + ex);
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0)
+  {
+    scalars[2] = carry;
+  }
+}
+
+// writes the (index, value) pairs of lcp values >= 255 in increasing index order
+__global__ void __launch_bounds__(FN_THREADS)
+llv_emit_kernel(u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v, const u8 *__restrict__ lcp8,
+                const u32 *__restrict__ tile_offset, u64 nllv, u64 *__restrict__ llv)
+{
+  __shared__ __align__(8) u8 sflag[FN_TILE];
+  __shared__ u32 scratch[FN_THREADS / 32 + 1];
+  const u64 tile_base = (u64) blockIdx.x * FN_TILE;
+  const u64 first = tile_offset[blockIdx.x];
+  const u64 next = blockIdx.x + 1 < gridDim.x ? tile_offset[blockIdx.x + 1] : nllv;
+  if (first == next)
+  {
+    return;  // uniform for the whole CTA
+  }
+#pragma unroll
+  for (int j = 0; j < FN_ITEMS; j++)
+  {
+    const int l = j * FN_THREADS + threadIdx.x;
+    const u64 r = tile_base + l;
+    sflag[l] = (r < N && lcp8[r] == 255) ? 1 : 0;
+  }
+  __syncthreads();
+  const int b0 = threadIdx.x * FN_ITEMS;
+  const u64 f8 = *reinterpret_cast<const u64 *>(sflag + b0);
+  const u32 cnt = (u32) __popcll(f8);
+  u32 o = block_exclusive_sum<u32, FN_THREADS>(cnt, scratch, nullptr);
+#pragma unroll
+  for (int i = 0; i < FN_ITEMS; i++)
+  {
+    if ((f8 >> (8 * i)) & 1)
+    {
+      const u64 r = tile_base + b0 + i;
+      const u32 s = sa[r];
+      llv[2 * (first + o)] = r;
+      llv[2 * (first + o) + 1] = (u64) (v[s] - s);
+      o++;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KS_THREADS)
+sti1_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32 *__restrict__ isa,
+            const u64 *__restrict__ bck, u8 *__restrict__ sti1)
+{
+  __shared__ __align__(16) u8 stext[KS_TILE + KS_HALO];
+  __shared__ __align__(16) u8 sout[KS_TILE];
+  const u64 tile_base = (u64) blockIdx.x * KS_TILE;
+  const u64 N = n + 1;
+  ks_load_tile(tis, n, tile_base, stext);
+  __syncthreads();
+  u32 code[KS_ITEMS], dist[KS_ITEMS];
+  const int lo = threadIdx.x * KS_ITEMS;
+  ks_scan_thread(stext, lo, kp, code, dist);
+#pragma unroll
+  for (int i = 0; i < KS_ITEMS; i++)
+  {
+    const u64 p = tile_base + lo + i;
+    u8 out = 0;
+    if (p < N && dist[i] >= kp.h)
+    {
+      const u64 off = (u64) isa[p] - bck[2 * (u64) code[i]];
+      out = (u8) (off < 255 ? off : 255);
+    }
+    sout[lo + i] = out;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < KS_TILE; l += KS_THREADS)
+  {
+    const u64 p = tile_base + l;
+    if (p < N)
+    {
+      sti1[p] = sout[l];
+    }
+  }
+}
+
+__global__ void widen_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, u64 N)
+{
+  const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N)
+  {
+    out[i] = in[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// checks.  errors: u32[8] counters, one per property.
+__device__ __forceinline__ u64 sym_at(const u8 *tis, u64 n, u64 p)
+{
+  return (p < n && tis[p] < ESA_WILDCARD) ? (u64) tis[p] : p + 256;
+}
+
+__global__ void check_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict__ sa,
+                             const u32 *__restrict__ isa, const u32 *__restrict__ v, const u8 *__restrict__ lcp8,
+                             const u8 *__restrict__ bwt, const u64 *__restrict__ suf64, u32 *__restrict__ errors)
+{
+  const u64 N = n + 1;
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N)
+  {
+    return;
+  }
+  const u64 s = sa[r];
+  // 1: permutation (checksuftab, bese.c:355-451): isa inverts sa
+  if (s > n || isa[s] != r)
+  {
+    atomicAdd(&errors[1], 1u);
+    return;
+  }
+  if (suf64 != nullptr && suf64[r] != s)
+  {
+    atomicAdd(&errors[1], 1u);
+  }
+  // 4: bwt against the text (checksufencoding, cprsuf.c:66-95)
+  if (bwt != nullptr && bwt[r] != (s > 0 ? tis[s - 1] : (u8) ESA_UNDEFBWTCHAR))
+  {
+    atomicAdd(&errors[4], 1u);
+  }
+  if (r == 0)
+  {
+    if (lcp8 != nullptr && lcp8[0] != 0)
+    {
+      atomicAdd(&errors[3], 1u);
+    }
+    return;
+  }
+  // 2 + 3: order of adjacent suffixes and the lcp value, by direct comparison (checklcpsubtab, bese.c:454-528)
+  const u64 p = sa[r - 1];
+  u64 l = 0;
+  while (sym_at(tis, n, p + l) == sym_at(tis, n, s + l))
+  {
+    l++;
+  }
+  if (sym_at(tis, n, p + l) > sym_at(tis, n, s + l))
+  {
+    atomicAdd(&errors[2], 1u);
+  }
+  if (v != nullptr)
+  {
+    if ((u64) (v[s] - (u32) s) != l || lcp8[r] != (u8) (l < 255 ? l : 255))
+    {
+      atomicAdd(&errors[3], 1u);
+    }
+  }
+}
+
+// 5: bck.left + sti1 == isa (saturated) inside [left, mid) (checkstitab1, mkvprocess.c:672-763)
+__global__ void check_sti1_kernel(u64 numofcodes, const u64 *__restrict__ bck, const u32 *__restrict__ sa,
+                                  const u8 *__restrict__ sti1, u64 N, u32 *__restrict__ errors)
+{
+  const u64 c = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= numofcodes)
+  {
+    return;
+  }
+  const u64 left = bck[2 * c], mid = bck[2 * c + 1];
+  if (left > mid || mid > N)
+  {
+    atomicAdd(&errors[5], 1u);
+    return;
+  }
+  for (u64 i = left; i < mid; i++)
+  {
+    const u64 off = i - left;
+    if (sti1[sa[i]] != (u8) (off < 255 ? off : 255))
+    {
+      atomicAdd(&errors[5], 1u);
+      return;
+    }
+  }
+}
+
+}  // namespace
+
+void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
+{
+  const u64 N = ctx->n + 1;
+  cudaStream_t s = ctx->stream;
+  Arena &ar = ctx->arena;
+  const bool want_lcp = d_v != nullptr;
+  unsigned long long *d_scalars = (unsigned long long *) ar.alloc<u64>(8);
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_scalars, 0, 8 * sizeof(u64), s)));
+  if (demand & ESA_SUFTAB)
+  {
+    ctx->d_suf64 = ar.alloc<u64>(N);
+  }
+  if (demand & ESA_BWTTAB)
+  {
+    ctx->d_bwt = ar.alloc<u8>(N);
+  }
+  if (want_lcp)
+  {
+    ctx->d_lcp = ar.alloc<u8>(N);
+  }
+  const u32 tiles = (u32) div_up_u64(N, FN_TILE);
+  u32 *tile_large = ar.alloc<u32>(tiles);
+  const double bytes = (double) N * (4.0 + ((demand & ESA_SUFTAB) ? 8.0 : 0.0) + ((demand & ESA_BWTTAB) ? 2.0 : 0.0)
+                                     + (want_lcp ? 5.0 : 0.0));
+  ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
+             (finalize_kernel<<<tiles, FN_THREADS, 0, s>>>(ctx->d_tis, N, ctx->d_sa, d_v, ctx->d_lcp, ctx->d_bwt,
+                                                            ctx->d_suf64, tile_large, d_scalars)));
+  if (want_lcp)
+  {
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx->maxbranchdepth = ctx->h_scalars[0];
+  ctx->longest = ctx->h_scalars[1];
+  ctx->nllv = want_lcp ? ctx->h_scalars[2] : 0;
+  if (want_lcp && ctx->nllv > 0)
+  {
+    ctx->d_llv = ar.alloc<u64>(2 * ctx->nllv);
+    ESA_LAUNCH(ctx, ESA_K_FINALIZE, (double) N + 24.0 * ctx->nllv,
+               (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, ctx->d_lcp, tile_large, ctx->nllv,
+                                                              ctx->d_llv)));
+  }
+}
+
+void compute_sti1(esa_ctx *ctx, u32 prefixlength)
+{
+  const u64 N = ctx->n + 1;
+  ctx->d_sti1 = ctx->arena.alloc<u8>(N + KS_TILE);
+  const KmerParams kp = make_kmer_params(ctx->sigma, prefixlength);
+  const u32 tiles = (u32) div_up_u64(N, KS_TILE);
+  ESA_LAUNCH(ctx, ESA_K_STI1, 14.0 * N,
+             (sti1_kernel<<<tiles, KS_THREADS, 0, ctx->stream>>>(ctx->d_tis, ctx->n, kp, ctx->d_isa, ctx->d_bck,
+                                                                  ctx->d_sti1)));
+}
+
+void widen_isa(esa_ctx *ctx)
+{
+  const u64 N = ctx->n + 1;
+  ctx->d_sti64 = ctx->arena.alloc<u64>(N);
+  ESA_LAUNCH(ctx, ESA_K_FINALIZE, 12.0 * N,
+             (widen_kernel<<<div_up_u32(N, 256), 256, 0, ctx->stream>>>(ctx->d_isa, ctx->d_sti64, N)));
+}
+
+int run_checks(esa_ctx *ctx, std::string &msg)
+{
+  const u64 N = ctx->n + 1;
+  cudaStream_t s = ctx->stream;
+  const size_t mark = ctx->arena.mark();
+  u32 *d_err = ctx->arena.alloc<u32>(8);
+  CUDA_CHECK(cudaMemsetAsync(d_err, 0, 8 * sizeof(u32), s));
+  check_kernel<<<div_up_u32(N, 256), 256, 0, s>>>(ctx->d_tis, ctx->n, ctx->d_sa, ctx->d_isa, ctx->d_plcpv, ctx->d_lcp,
+                                                   ctx->d_bwt, ctx->d_suf64, d_err);
+  CUDA_CHECK(cudaGetLastError());
+  if (ctx->d_sti1 != nullptr && ctx->d_bck != nullptr)
+  {
+    check_sti1_kernel<<<div_up_u32(ctx->numofcodes, 256), 256, 0, s>>>(ctx->numofcodes, ctx->d_bck, ctx->d_sa,
+                                                                        ctx->d_sti1, N, d_err);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  u32 h_err[8];
+  CUDA_CHECK(cudaMemcpyAsync(h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx->arena.rewind(mark);
+  static const char *names[8] = {"", "suftab is not a permutation / isa does not invert it",
+                                 "adjacent suffixes out of order", "lcp value wrong", "bwt does not match the text",
+                                 "bck.left + sti1 != inverse suftab", "", ""};
+  for (int i = 1; i <= 5; i++)
+  {
+    if (h_err[i] != 0)
+    {
+      char buf[256];
+      snprintf(buf, sizeof buf, "check %d failed (%s): %u violations", i, names[i], h_err[i]);
+      msg = buf;
+      return i;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,413 @@
+// radix_sort.cu -- least-significant-digit radix sort of (key, 32-bit value) pairs, one memory sweep per digit.
+//
+// This is the dominant kernel family of the suffix sorter (north star: "LSD radix passes ... coalesced,
+// vectorised HBM loads, shared-memory histogramming and warp-shuffle scans").  Structure per sort:
+//   1. radix_hist_kernel   one read of the keys -> histograms of EVERY digit (shared-memory bins, one
+//                          warp-aggregated atomic per distinct digit and warp)
+//   2. radix_scan_kernel   exclusive scan of each digit histogram -> global bin bases
+//   3. radix_pass_kernel   per digit ONE read + ONE write of the pairs: each 512-thread CTA takes a tile
+//                          (dynamic ticket), ranks its keys with warp match/ballot, learns the number of equal
+//                          digits in all earlier tiles by decoupled look-back over a status array (single 32-bit
+//                          word = 2 flag bits + 30 value bits), reorders the tile in shared memory and writes
+//                          each digit run coalesced.  Stable.
+// Algorithmic bytes: hist = n*sizeof(key); pass = 2*n*(sizeof(key)+sizeof(value)).
+// Inputs beyond 2^30-1 pairs are cut into parts so that look-back prefixes fit 30 bits; the per-part
+// histograms give every part its own bin bases, so parts are independent launches.
+#include "scan.cuh"
+
+namespace
+{
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_ITEMS = 8;
+constexpr u32 STATUS_AGG = 1u << 30;
+constexpr u32 STATUS_PREFIX = 2u << 30;
+constexpr u32 STATUS_VALUE_MASK = (1u << 30) - 1;
+
+template <typename KeyT> struct SortTraits;
+template <> struct SortTraits<u32>
+{
+  static constexpr int ITEMS = 16;
+};
+template <> struct SortTraits<u64>
+{
+  static constexpr int ITEMS = 12;
+};
+
+template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, u32 shift, u32 mask)
+{
+  return (u32) (k >> shift) & mask;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(HIST_THREADS)
+radix_hist_kernel(const KeyT *__restrict__ keys, u32 count, u32 begin_bit, u32 end_bit, u32 npass,
+                  u32 *__restrict__ hist /* [npass][256] of this part */)
+{
+  __shared__ u32 sh[sizeof(KeyT) * RADIX];
+  for (u32 i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS)
+  {
+    sh[i] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr u32 STEP = HIST_THREADS * HIST_ITEMS;
+  for (u64 base = (u64) blockIdx.x * STEP; base < count; base += (u64) gridDim.x * STEP)
+  {
+    KeyT k[HIST_ITEMS];
+    bool valid[HIST_ITEMS];
+#pragma unroll
+    for (int i = 0; i < HIST_ITEMS; i++)
+    {
+      u64 idx = base + (u64) i * HIST_THREADS + threadIdx.x;
+      valid[i] = idx < count;
+      k[i] = valid[i] ? keys[idx] : (KeyT) 0;
+    }
+#pragma unroll
+    for (int i = 0; i < HIST_ITEMS; i++)
+    {
+      const u32 vmask = __ballot_sync(FULL_MASK, valid[i]);
+      if (valid[i])
+      {
+        for (u32 p = 0; p < npass; p++)
+        {
+          const u32 shift = begin_bit + p * RADIX_BITS;
+          const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
+          const u32 d = digit_of(k[i], shift, (1u << bits) - 1);
+          const u32 peers = __match_any_sync(vmask, d);
+          if (lane == __ffs(peers) - 1)
+          {
+            atomicAdd(&sh[p * RADIX + d], (u32) __popc(peers));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS)
+  {
+    const u32 v = sh[i];
+    if (v != 0)
+    {
+      atomicAdd(&hist[i], v);
+    }
+  }
+}
+
+// one block per pass, one thread per digit
+__global__ void __launch_bounds__(RADIX)
+radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npass, u32 parts)
+{
+  __shared__ u32 scratch[RADIX / 32 + 1];
+  const u32 p = blockIdx.x, d = threadIdx.x;
+  u32 total = 0;
+  for (u32 part = 0; part < parts; part++)
+  {
+    total += hist[((u64) part * npass + p) * RADIX + d];
+  }
+  u32 run = block_exclusive_sum<u32, RADIX>(total, scratch, nullptr);
+  for (u32 part = 0; part < parts; part++)
+  {
+    const u64 o = ((u64) part * npass + p) * RADIX + d;
+    base[o] = run;
+    run += hist[o];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename KeyT, bool HAS_VALS, int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, 2)
+radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin,
+                  u32 *__restrict__ vout, u32 count, u32 shift, u32 mask, const u32 *__restrict__ base,
+                  volatile u32 *status, u32 *ticket)
+{
+  constexpr int TILE = SORT_THREADS * ITEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT *skeys = (KeyT *) smem_raw;
+  u32 *svals = (u32 *) (skeys + TILE);
+  u32 *wc = svals + (HAS_VALS ? TILE : 0);     // [SORT_WARPS][RADIX] per-warp digit counters, then offsets
+  u32 *digit_start = wc + SORT_WARPS * RADIX;  // [RADIX] first slot of the digit in the reordered tile
+  u32 *gbase = digit_start + RADIX;            // [RADIX] global index of slot 0 of the digit, minus digit_start
+  u32 *misc = gbase + RADIX;                   // [0] tile ticket, [1..] scan scratch
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+  {
+    misc[0] = atomicAdd(ticket, 1u);
+  }
+  u32 *mywc = wc + warp * RADIX;
+#pragma unroll
+  for (int d = lane; d < RADIX; d += 32)
+  {
+    mywc[d] = 0;
+  }
+  __syncthreads();
+  const u32 tile = misc[0];
+  const u32 tile_base = tile * (u32) TILE;                 // count < 2^30, so this cannot overflow
+  const u32 tile_count = min((u32) TILE, count - tile_base);
+
+  // ---- load, warp-striped: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile
+  KeyT keys[ITEMS];
+  u32 ranks[ITEMS];
+  const u32 wbase = warp * (32 * ITEMS);
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 idx = wbase + i * 32 + lane;
+    keys[i] = idx < tile_count ? kin[tile_base + idx] : (KeyT) ~(KeyT) 0;  // padding sorts last
+  }
+  // ---- rank inside the warp: stable in (item, lane) order = memory order
+  const u32 lt_mask = (1u << lane) - 1;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 peers = __match_any_sync(FULL_MASK, d);
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if (lane == leader)
+    {
+      old = mywc[d];
+      mywc[d] = old + __popc(peers);
+    }
+    old = __shfl_sync(FULL_MASK, old, leader);
+    ranks[i] = old + __popc(peers & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- per digit: exclusive offsets of the warps, tile count
+  u32 bcount = 0;
+  if (tid < RADIX)
+  {
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+    {
+      const u32 c = wc[w * RADIX + tid];
+      wc[w * RADIX + tid] = run;
+      run += c;
+    }
+    bcount = run;
+  }
+  const u32 dstart = block_exclusive_sum<u32, RADIX>(bcount, misc + 1, nullptr);
+  // ---- decoupled look-back: how many keys with my digit precede this tile (within the part)
+  if (tid < RADIX)
+  {
+    u32 valid_count = bcount;
+    if ((u32) tid == mask)
+    {
+      valid_count -= (u32) TILE - tile_count;  // padding keys carry the largest digit
+    }
+    u32 excl = 0;
+    if (tile == 0)
+    {
+      status[tid] = STATUS_PREFIX | valid_count;
+    } else
+    {
+      status[(u64) tile * RADIX + tid] = STATUS_AGG | valid_count;
+      u32 t = tile - 1;
+      while (true)
+      {
+        const u32 s = status[(u64) t * RADIX + tid];
+        if ((s >> 30) == 0)
+        {
+          continue;  // predecessor has not published yet
+        }
+        excl += s & STATUS_VALUE_MASK;
+        if ((s >> 30) == 2)
+        {
+          break;
+        }
+        t--;
+      }
+      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (excl + valid_count);
+    }
+    digit_start[tid] = dstart;
+    gbase[tid] = base[tid] + excl - dstart;  // wraps modulo 2^32 by design
+  }
+  __syncthreads();
+  // ---- reorder the tile in shared memory
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 pos = digit_start[d] + mywc[d] + ranks[i];
+    skeys[pos] = keys[i];
+    if (HAS_VALS)
+    {
+      const u32 idx = wbase + i * 32 + lane;
+      svals[pos] = idx < tile_count ? vin[tile_base + idx] : 0u;
+    }
+  }
+  __syncthreads();
+  // ---- write every digit run coalesced
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++)
+  {
+    const u32 p = j * SORT_THREADS + tid;
+    if (p < tile_count)
+    {
+      const KeyT k = skeys[p];
+      const u32 g = gbase[digit_of(k, shift, mask)] + p;
+      kout[g] = k;
+      if (HAS_VALS)
+      {
+        vout[g] = svals[p];
+      }
+    }
+  }
+}
+
+template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
+{
+  constexpr int TILE = SORT_THREADS * SortTraits<KeyT>::ITEMS;
+  return (size_t) TILE * sizeof(KeyT) + (has_vals ? (size_t) TILE * 4 : 0) + (size_t) SORT_WARPS * RADIX * 4
+         + 2 * RADIX * 4 + (1 + RADIX / 32 + 1 + 6) * 4;
+}
+
+template <typename KeyT> u64 part_items_max()
+{
+  constexpr u64 TILE = (u64) SORT_THREADS * SortTraits<KeyT>::ITEMS;
+  return (((u64) 1 << 30) - 1) / TILE * TILE;
+}
+
+struct TempLayout
+{
+  u32 parts, npass_max;
+  size_t hist_off, base_off, status_off, ticket_off, total;
+};
+
+template <typename KeyT> TempLayout temp_layout(u64 n)
+{
+  constexpr u64 TILE = (u64) SORT_THREADS * SortTraits<KeyT>::ITEMS;
+  TempLayout L;
+  const u64 pim = part_items_max<KeyT>();
+  L.parts = (u32) (n == 0 ? 1 : div_up_u64(n, pim));
+  L.npass_max = (u32) sizeof(KeyT);
+  const u64 tiles_per_part = div_up_u64(n < pim ? (n == 0 ? 1 : n) : pim, TILE);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t) 255;
+    return o;
+  };
+  L.hist_off = take((size_t) L.parts * L.npass_max * RADIX * 4);
+  L.ticket_off = take((size_t) L.parts * L.npass_max * 4);
+  L.base_off = take((size_t) L.parts * L.npass_max * RADIX * 4);
+  L.status_off = take((size_t) tiles_per_part * RADIX * 4);
+  L.total = off;
+  return L;
+}
+
+template <typename KeyT>
+int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u32 begin_bit, u32 end_bit, void *temp,
+                    size_t temp_bytes)
+{
+  constexpr int ITEMS = SortTraits<KeyT>::ITEMS;
+  constexpr u64 TILE = (u64) SORT_THREADS * ITEMS;
+  if (n <= 1 || end_bit <= begin_bit)
+  {
+    return 0;
+  }
+  const bool has_vals = va != nullptr;
+  const u32 npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  const TempLayout L = temp_layout<KeyT>(n);
+  if (temp_bytes < L.total)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "radix sort scratch too small: %zu < %zu", temp_bytes, L.total);
+  }
+  char *t = (char *) temp;
+  u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off),
+      *status = (u32 *) (t + L.status_off);
+  const u64 pim = part_items_max<KeyT>();
+  cudaStream_t s = ctx->stream;
+
+  // hist and tickets are adjacent: one memset clears both
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
+  for (u32 part = 0; part < L.parts; part++)
+  {
+    const u64 off = (u64) part * pim;
+    const u32 cnt = (u32) (n - off < pim ? n - off : pim);
+    const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(cnt, (u64) HIST_THREADS * HIST_ITEMS));
+    ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, (double) cnt * sizeof(KeyT),
+               (radix_hist_kernel<KeyT><<<grid, HIST_THREADS, 0, s>>>(ka + off, cnt, begin_bit, end_bit, npass,
+                                                                        hist + (u64) part * npass * RADIX)));
+  }
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<npass, RADIX, 0, s>>>(hist, base, npass, L.parts)));
+
+  const size_t smem = pass_smem_bytes<KeyT>(has_vals);
+  KeyT *ksrc = ka, *kdst = kb;
+  u32 *vsrc = va, *vdst = vb;
+  for (u32 p = 0; p < npass; p++)
+  {
+    const u32 shift = begin_bit + p * RADIX_BITS;
+    const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
+    const u32 mask = (1u << bits) - 1;
+    for (u32 part = 0; part < L.parts; part++)
+    {
+      const u64 off = (u64) part * pim;
+      const u32 cnt = (u32) (n - off < pim ? n - off : pim);
+      const u32 tiles = (u32) div_up_u64(cnt, TILE);
+      ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 4, s)));
+      const u32 *pbase = base + ((u64) part * npass + p) * RADIX;
+      u32 *ticket = tickets + (u64) part * npass + p;
+      const double bytes = 2.0 * cnt * (sizeof(KeyT) + (has_vals ? 4 : 0));
+      if (has_vals)
+      {
+        ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, bytes,
+                   (radix_pass_kernel<KeyT, true, ITEMS><<<tiles, SORT_THREADS, smem, s>>>(
+                       ksrc + off, kdst, vsrc + off, vdst, cnt, shift, mask, pbase, status, ticket)));
+      } else
+      {
+        ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, bytes,
+                   (radix_pass_kernel<KeyT, false, ITEMS><<<tiles, SORT_THREADS, smem, s>>>(
+                       ksrc + off, kdst, nullptr, nullptr, cnt, shift, mask, pbase, status, ticket)));
+      }
+    }
+    KeyT *kt = ksrc;
+    ksrc = kdst;
+    kdst = kt;
+    u32 *vt = vsrc;
+    vsrc = vdst;
+    vdst = vt;
+  }
+  return (int) (npass & 1);
+}
+
+template <typename KeyT> void set_smem_attr()
+{
+  CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, SortTraits<KeyT>::ITEMS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem_bytes<KeyT>(true)));
+  CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, SortTraits<KeyT>::ITEMS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem_bytes<KeyT>(false)));
+}
+
+}  // namespace
+
+void radix_sort_init()
+{
+  set_smem_attr<u32>();
+  set_smem_attr<u64>();
+}
+
+size_t radix_sort_temp_bytes(u64 n, u32 key_bytes)
+{
+  return key_bytes == 8 ? temp_layout<u64>(n).total : temp_layout<u32>(n).total;
+}
+
+int radix_sort_pairs_u32(esa_ctx *ctx, u32 *keys_a, u32 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
+                         u32 end_bit, void *temp, size_t temp_bytes)
+{
+  return radix_sort_impl<u32>(ctx, keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes);
+}
+
+int radix_sort_pairs_u64(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
+                         u32 end_bit, void *temp, size_t temp_bytes)
+{
+  return radix_sort_impl<u64>(ctx, keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes);
+}
