@@ -4,6 +4,7 @@
 // suffix sort (+ inline lcp) -> llv -> bck -> longest -> suf -> sti1 -> bwt, but every table is produced on the
 // device; the host only moves bytes.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -232,19 +233,46 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   {
     ctx->d_bck = ar.alloc<u64>(2 * ctx->numofcodes);
   }
+  const bool want_lcp = (demand & ESA_LCPTAB) != 0;
+  ctx->d_pk = nullptr;
+  ctx->d_spm = nullptr;
+  ctx->d_hround = nullptr;
+  ctx->lcp_work_estimate = 0;
+  if (ctx->sigma <= 4 && (demand & (ESA_LCPTAB | ESA_BWTTAB)))
+  {
+    pack_text(ctx);  // 2-bit text + special mask for the random suffix-start accesses of lcp and bwt
+  }
+  if (want_lcp && ctx->lcp_mode != 2)
+  {
+    ctx->d_hround = ar.alloc<u8>(N + 64);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, (double) N, CUDA_CHECK(cudaMemsetAsync(ctx->d_hround, 0, N + 64, s)));
+  }
   const size_t scratch_mark = ar.mark();
   SortOutcome so;
   suffix_sort(ctx, prefixlength, want_bck, &so, scratch_mark);
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_b, s));
   ar.rewind(scratch_mark);  // everything the sorter carved is dead now
-  const bool want_lcp = (demand & ESA_LCPTAB) != 0;
+  // lcp path: direct comparison in suffix-array order unless the deep groups are so large that the work bound
+  // sum(active * depth / 32) explodes (long exact tandem arrays); then the text-order plcp path, whose cost does
+  // not depend on the lcp values
+  bool use_plcp = false;
   if (want_lcp)
+  {
+    use_plcp = ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N);
+  }
+  if (use_plcp)
   {
     ctx->d_plcpv = ar.alloc<u32>(N + 64);
     compute_plcp(ctx, ctx->d_plcpv);
   }
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_c, s));
-  finalize_tables(ctx, demand, ctx->d_plcpv);
+  if (use_plcp)
+  {
+    finalize_tables(ctx, demand, ctx->d_plcpv);
+  } else
+  {
+    finalize_tables_direct(ctx, demand, so.h0);
+  }
   if (demand & ESA_STI1TAB)
   {
     compute_sti1(ctx, prefixlength);
@@ -270,6 +298,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     stats->ms_derive = ms;
     stats->h0 = so.h0;
     stats->rounds = so.rounds;
+    stats->lcp_path = want_lcp ? (use_plcp ? 2 : 1) : 0;
     stats->active_sum = so.active_sum;
     stats->active_first = so.active_first;
     stats->device_bytes_peak = ar.peak;
@@ -387,6 +416,14 @@ int esa_init(esa_ctx **out, int device, char *errbuf, size_t errlen)
       CUDA_CHECK(cudaEventCreate(ev));
     }
     radix_sort_init();
+    if (const char *m = getenv("ESA_LCP_MODE"))
+    {
+      ctx->lcp_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "plcp") == 0 ? 2 : 0;
+    }
+    // the scatter/gather kernels (inverse suffix array, phi, plcp-to-lcp) touch 4 bytes per 32-byte sector:
+    // keep L2 from fetching 64/128-byte neighbourhoods for them (ncu: 99 B of DRAM reads per gathered word)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();  // a refused hint is not an error
   });
   if (rc != ESA_OK)
   {

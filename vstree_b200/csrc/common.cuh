@@ -151,6 +151,11 @@ struct esa_ctx
 
   // resident input
   u8 *d_tis = nullptr;   // arena; n symbols followed by >= 64 bytes of 255
+  u64 *d_pk = nullptr;   // 2-bit packed text (sigma <= 4 only), see textcmp.cuh
+  u32 *d_spm = nullptr;  // special mask of the packed text
+  u8 *d_hround = nullptr;  // [N] doubling round in which slot r became a group head (lcp lower bound), 0 = initial sort
+  u64 lcp_work_estimate = 0;  // sum over rounds of active * depth / 32 (window compares of the direct lcp path)
+  int lcp_mode = 0;           // 0 auto, 1 direct (suffix-array order), 2 plcp (text order)
   u64 n = 0;
   u32 sigma = 0;
   bool uploaded = false;
@@ -263,6 +268,8 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 void compute_plcp(esa_ctx *ctx, u32 *d_v);
 
 // derive.cu
+void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v);
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 int run_checks(esa_ctx *ctx, std::string &msg);

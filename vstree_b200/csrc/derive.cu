@@ -6,15 +6,12 @@
 //              sti1[s] = 0 if a special lies inside the k-prefix of s, else min(255, isa[s] - bck.left[kmer(s)])
 //   checks:    the reference's DEBUG invariants as device-side property checks.
 #include "kmer_scan.cuh"
+#include "llv.cuh"
 #include "scan.cuh"
 
 namespace
 {
 
-constexpr int FN_THREADS = 256;
-constexpr int FN_ITEMS = 8;
-constexpr int FN_TILE = FN_THREADS * FN_ITEMS;
-constexpr int SCAN1_THREADS = 1024;
 
 // scalars: [0] maxbranchdepth [1] longest [2] nllv
 __global__ void __launch_bounds__(FN_THREADS)
@@ -25,31 +22,86 @@ finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, c
   __shared__ u32 red[2][FN_THREADS / 32];
   const u64 tile_base = (u64) blockIdx.x * FN_TILE;
   u32 nlarge = 0, mx = 0;
+  // four consecutive ranks per thread and step: 16-byte loads of sa, four independent gathers in flight,
+  // 4-byte stores of lcp8/bwt and 32-byte stores of the widened suftab
 #pragma unroll
-  for (int j = 0; j < FN_ITEMS; j++)
+  for (int j = 0; j < FN_ITEMS / 4; j++)
   {
-    const u64 r = tile_base + (u64) j * FN_THREADS + threadIdx.x;
-    if (r < N)
+    const u64 r0 = tile_base + ((u64) j * FN_THREADS + threadIdx.x) * 4;
+    if (r0 + 4 <= N)
     {
-      const u32 s = sa[r];
-      if (suf64 != nullptr)
+      const uint4 s4 = *reinterpret_cast<const uint4 *>(sa + r0);
+      const u32 s[4] = {s4.x, s4.y, s4.z, s4.w};
+      u32 vv[4] = {0, 0, 0, 0};
+      u8 bb[4] = {0, 0, 0, 0};
+      if (v != nullptr)
       {
-        suf64[r] = s;
-      }
-      if (s == 0)
-      {
-        scalars[1] = r;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+          vv[q] = v[s[q]];
+        }
       }
       if (bwt != nullptr)
       {
-        bwt[r] = s > 0 ? tis[s - 1] : (u8) ESA_UNDEFBWTCHAR;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+          bb[q] = s[q] > 0 ? tis[s[q] - 1] : (u8) ESA_UNDEFBWTCHAR;
+        }
+        *reinterpret_cast<uchar4 *>(bwt + r0) = make_uchar4(bb[0], bb[1], bb[2], bb[3]);
+      }
+      if (suf64 != nullptr)
+      {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(suf64 + r0);
+        o[0] = make_ulonglong2(s[0], s[1]);
+        o[1] = make_ulonglong2(s[2], s[3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+      {
+        if (s[q] == 0)
+        {
+          scalars[1] = r0 + q;
+        }
       }
       if (v != nullptr)
       {
-        const u32 l = v[s] - s;
-        lcp8[r] = (u8) min(l, 255u);
-        nlarge += l >= 255u;
-        mx = max(mx, l);
+        u8 l8[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+          const u32 l = vv[q] - s[q];
+          l8[q] = (u8) min(l, 255u);
+          nlarge += l >= 255u;
+          mx = max(mx, l);
+        }
+        *reinterpret_cast<uchar4 *>(lcp8 + r0) = make_uchar4(l8[0], l8[1], l8[2], l8[3]);
+      }
+    } else
+    {
+      for (u64 r = r0; r < N; r++)
+      {
+        const u32 s = sa[r];
+        if (suf64 != nullptr)
+        {
+          suf64[r] = s;
+        }
+        if (s == 0)
+        {
+          scalars[1] = r;
+        }
+        if (bwt != nullptr)
+        {
+          bwt[r] = s > 0 ? tis[s - 1] : (u8) ESA_UNDEFBWTCHAR;
+        }
+        if (v != nullptr)
+        {
+          const u32 l = v[s] - s;
+          lcp8[r] = (u8) min(l, 255u);
+          nlarge += l >= 255u;
+          mx = max(mx, l);
+        }
       }
     }
   }
@@ -78,69 +130,6 @@ finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, c
     if (b > 0)
     {
       atomicMax(&scalars[0], (unsigned long long) b);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(SCAN1_THREADS)
-large_scan_kernel(u32 *tile_large, u32 ntiles, unsigned long long *scalars)
-{
-  __shared__ u64 scratch[SCAN1_THREADS / 32 + 1];
-  u64 carry = 0;
-  for (u32 b = 0; b < ntiles; b += SCAN1_THREADS)
-  {
-    const u32 i = b + threadIdx.x;
-    const u64 val = i < ntiles ? tile_large[i] : 0;
-    u64 total;
-    const u64 ex = block_exclusive_sum<u64, SCAN1_THREADS>(val, scratch, &total);
-    if (i < ntiles)
-    {
-      tile_large[i] = (u32) (carry + ex);
-    }
-    carry += total;
-  }
-  if (threadIdx.x == 0)
-  {
-    scalars[2] = carry;
-  }
-}
-
-// writes the (index, value) pairs of lcp values >= 255 in increasing index order
-__global__ void __launch_bounds__(FN_THREADS)
-llv_emit_kernel(u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v, const u8 *__restrict__ lcp8,
-                const u32 *__restrict__ tile_offset, u64 nllv, u64 *__restrict__ llv)
-{
-  __shared__ __align__(8) u8 sflag[FN_TILE];
-  __shared__ u32 scratch[FN_THREADS / 32 + 1];
-  const u64 tile_base = (u64) blockIdx.x * FN_TILE;
-  const u64 first = tile_offset[blockIdx.x];
-  const u64 next = blockIdx.x + 1 < gridDim.x ? tile_offset[blockIdx.x + 1] : nllv;
-  if (first == next)
-  {
-    return;  // uniform for the whole CTA
-  }
-#pragma unroll
-  for (int j = 0; j < FN_ITEMS; j++)
-  {
-    const int l = j * FN_THREADS + threadIdx.x;
-    const u64 r = tile_base + l;
-    sflag[l] = (r < N && lcp8[r] == 255) ? 1 : 0;
-  }
-  __syncthreads();
-  const int b0 = threadIdx.x * FN_ITEMS;
-  const u64 f8 = *reinterpret_cast<const u64 *>(sflag + b0);
-  const u32 cnt = (u32) __popcll(f8);
-  u32 o = block_exclusive_sum<u32, FN_THREADS>(cnt, scratch, nullptr);
-#pragma unroll
-  for (int i = 0; i < FN_ITEMS; i++)
-  {
-    if ((f8 >> (8 * i)) & 1)
-    {
-      const u64 r = tile_base + b0 + i;
-      const u32 s = sa[r];
-      llv[2 * (first + o)] = r;
-      llv[2 * (first + o) + 1] = (u64) (v[s] - s);
-      o++;
     }
   }
 }
@@ -243,12 +232,13 @@ __global__ void check_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__res
   {
     atomicAdd(&errors[2], 1u);
   }
-  if (v != nullptr)
+  if (lcp8 != nullptr && lcp8[r] != (u8) (l < 255 ? l : 255))
   {
-    if ((u64) (v[s] - (u32) s) != l || lcp8[r] != (u8) (l < 255 ? l : 255))
-    {
-      atomicAdd(&errors[3], 1u);
-    }
+    atomicAdd(&errors[3], 1u);
+  }
+  if (v != nullptr && (u64) (v[s] - (u32) s) != l)
+  {
+    atomicAdd(&errors[3], 1u);
   }
 }
 
@@ -309,7 +299,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
                                                             ctx->d_suf64, tile_large, d_scalars)));
   if (want_lcp)
   {
-    ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, LLV_SCAN_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
   }
   CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -320,8 +310,8 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
   {
     ctx->d_llv = ar.alloc<u64>(2 * ctx->nllv);
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, (double) N + 24.0 * ctx->nllv,
-               (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, ctx->d_lcp, tile_large, ctx->nllv,
-                                                              ctx->d_llv)));
+               (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, nullptr, ctx->d_lcp, tile_large,
+                                                              ctx->nllv, ctx->d_llv)));
   }
 }
 

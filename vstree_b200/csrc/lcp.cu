@@ -9,6 +9,7 @@
 // Specials never match (bese.c:26-55), so a comparison stops at the first special on either side; the text
 // buffer is padded with 255 behind position n, which doubles as the sentinel.
 #include "scan.cuh"
+#include "textcmp.cuh"
 
 namespace
 {
@@ -19,42 +20,9 @@ constexpr int PL_ITEMS = 8;
 constexpr int PL_TILE = PL_THREADS * PL_ITEMS;
 constexpr int SCAN1_THREADS = 1024;
 
-__device__ __forceinline__ u64 load_window8(const u8 *__restrict__ tis, u64 p)
-{
-  const u64 *w = reinterpret_cast<const u64 *>(tis + (p & ~(u64) 7));
-  const u32 sh = (u32) (p & 7) * 8;
-  const u64 lo = w[0];
-  if (sh == 0)
-  {
-    return lo;
-  }
-  return (lo >> sh) | (w[1] << (64 - sh));
-}
-
-// number of equal leading letters of the suffixes at i and j (i != j)
-__device__ __forceinline__ u32 lcp_direct(const u8 *__restrict__ tis, u64 i, u64 j)
-{
-  u32 l = 0;
-  while (true)
-  {
-    const u64 a = load_window8(tis, i + l), b = load_window8(tis, j + l);
-    const u64 x = a ^ b;
-    // bytes of a that are special (254/255): zero bytes of y; equal specials do not match either
-    const u64 y = ~(a | 0x0101010101010101ull);
-    const u64 z = (y - 0x0101010101010101ull) & ~y & 0x8080808080808080ull;
-    const u32 stop_mis = x ? (u32) (__ffsll((long long) x) - 1) >> 3 : 8u;
-    const u32 stop_sp = z ? (u32) (__ffsll((long long) z) - 1) >> 3 : 8u;
-    const u32 stop = min(stop_mis, stop_sp);
-    l += stop;
-    if (stop < 8)
-    {
-      return l;
-    }
-  }
-}
-
+template <typename Text>
 __global__ void __launch_bounds__(PL_THREADS)
-plcp_irreducible_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict__ sa, const u32 *__restrict__ isa,
+plcp_irreducible_kernel(Text text, u64 n, const u32 *__restrict__ sa, const u32 *__restrict__ isa,
                         u32 *__restrict__ v, u32 *__restrict__ tile_last)
 {
   __shared__ u32 red_idx[PL_THREADS / 32];
@@ -62,6 +30,27 @@ plcp_irreducible_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict
   const u64 N = n + 1;
   const u64 tile_base = (u64) blockIdx.x * PL_TILE;
   u32 last_idx = 0, last_val = MARK;  // last valid (irreducible) item of this thread: local index + 1, its value
+  // the dependent gathers are issued loop by loop so that PL_ITEMS of them are in flight per thread
+  u32 rr[PL_ITEMS], jj[PL_ITEMS], cc[PL_ITEMS];
+#pragma unroll
+  for (int j = 0; j < PL_ITEMS; j++)
+  {
+    const u64 i = tile_base + j * PL_THREADS + threadIdx.x;
+    rr[j] = i < N ? isa[i] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < PL_ITEMS; j++)
+  {
+    jj[j] = rr[j] > 0 ? sa[rr[j] - 1] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < PL_ITEMS; j++)
+  {
+    const u64 i = tile_base + j * PL_THREADS + threadIdx.x;
+    const u32 ci = i < N ? text.before(i) : 255u;
+    const u32 cj = rr[j] > 0 ? text.before(jj[j]) : 255u;
+    cc[j] = (ci == cj && ci < ESA_WILDCARD) ? 1u : 0u;  // reducible
+  }
 #pragma unroll
   for (int j = 0; j < PL_ITEMS; j++)
   {
@@ -69,23 +58,16 @@ plcp_irreducible_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict
     const u64 i = tile_base + l;
     if (i < N)
     {
-      const u32 r = isa[i];
       u32 val;
-      if (r == 0)
+      if (rr[j] == 0)
       {
         val = (u32) i;  // lcp of the first suffix is 0 (bese.c:639)
+      } else if (cc[j])
+      {
+        val = MARK;
       } else
       {
-        const u64 jpos = sa[r - 1];
-        const u32 ci = i > 0 ? tis[i - 1] : 255u;
-        const u32 cj = jpos > 0 ? tis[jpos - 1] : 255u;
-        if (ci == cj && ci < ESA_WILDCARD)
-        {
-          val = MARK;
-        } else
-        {
-          val = (u32) i + lcp_direct(tis, i, jpos);
-        }
+        val = (u32) i + text.lcp(i, jj[j], 0);
       }
       v[i] = val;
       if (val != MARK)
@@ -223,8 +205,19 @@ void compute_plcp(esa_ctx *ctx, u32 *d_v)
   const u32 tiles = (u32) div_up_u64(N, PL_TILE);
   u32 *tile_last = ctx->arena.alloc<u32>(tiles);
   // algorithmic bytes: isa 4 + sa gather 4 + two symbols 2 + V write 4, plus the compared windows (data dependent)
-  ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * N,
-             (plcp_irreducible_kernel<<<tiles, PL_THREADS, 0, s>>>(ctx->d_tis, n, ctx->d_sa, ctx->d_isa, d_v, tile_last)));
+  if (ctx->d_pk != nullptr)
+  {
+    TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
+    ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * N,
+               (plcp_irreducible_kernel<TextPacked2><<<tiles, PL_THREADS, 0, s>>>(text, n, ctx->d_sa, ctx->d_isa, d_v,
+                                                                                   tile_last)));
+  } else
+  {
+    TextBytes text{ctx->d_tis};
+    ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * N,
+               (plcp_irreducible_kernel<TextBytes><<<tiles, PL_THREADS, 0, s>>>(text, n, ctx->d_sa, ctx->d_isa, d_v,
+                                                                                 tile_last)));
+  }
   ESA_LAUNCH(ctx, ESA_K_MISC, 0, (last_valid_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_last, tiles)));
   ESA_LAUNCH(ctx, ESA_K_PLCP, 8.0 * N, (plcp_fill_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last)));
 }

@@ -74,15 +74,23 @@ radix_hist_kernel(const KeyT *__restrict__ keys, u32 count, u32 begin_bit, u32 e
       const u32 vmask = __ballot_sync(FULL_MASK, valid[i]);
       if (valid[i])
       {
+        const int first = __ffs(vmask) - 1;
         for (u32 p = 0; p < npass; p++)
         {
           const u32 shift = begin_bit + p * RADIX_BITS;
           const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
           const u32 d = digit_of(k[i], shift, (1u << bits) - 1);
-          const u32 peers = __match_any_sync(vmask, d);
-          if (lane == __ffs(peers) - 1)
+          // a digit that is the same in the whole warp (constant high bits, runs of equal keys) would
+          // serialise 32 ways on one bin: count it once
+          if (__all_sync(vmask, d == __shfl_sync(vmask, d, first)))
           {
-            atomicAdd(&sh[p * RADIX + d], (u32) __popc(peers));
+            if (lane == first)
+            {
+              atomicAdd(&sh[p * RADIX + d], (u32) __popc(vmask));
+            }
+          } else
+          {
+            atomicAdd(&sh[p * RADIX + d], 1u);
           }
         }
       }
@@ -163,11 +171,29 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   }
   // ---- rank inside the warp: stable in (item, lane) order = memory order
   const u32 lt_mask = (1u << lane) - 1;
+  // lanes holding the same digit, found with one ballot per digit bit.  MATCH.ANY does the same in one
+  // instruction but its cost grows with the number of distinct values in the warp (ncu, round 1: the instruction
+  // behind it held 35 % of all stall samples and splitting it from its use changed nothing).
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
     const u32 d = digit_of(keys[i], shift, mask);
-    const u32 peers = __match_any_sync(FULL_MASK, d);
+    u32 peers = FULL_MASK;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++)
+    {
+      const bool bit = (d >> b) & 1;
+      const u32 bal = __ballot_sync(FULL_MASK, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    ranks[i] = peers;
+  }
+  // then the short serial chain through the warp's shared counters
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 peers = ranks[i];
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
     if (lane == leader)
@@ -180,21 +206,28 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     __syncwarp();
   }
   __syncthreads();
-  // ---- per digit: exclusive offsets of the warps, tile count
+  // ---- per digit: tile count, then (after the scan over digits) the first slot of every warp's run
   u32 bcount = 0;
   if (tid < RADIX)
   {
-    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+    {
+      bcount += wc[w * RADIX + tid];
+    }
+  }
+  const u32 dstart = block_exclusive_sum<u32, RADIX>(bcount, misc + 1, nullptr);
+  if (tid < RADIX)
+  {
+    u32 run = dstart;
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; w++)
     {
       const u32 c = wc[w * RADIX + tid];
-      wc[w * RADIX + tid] = run;
+      wc[w * RADIX + tid] = run;  // slot of the warp's first key with this digit in the reordered tile
       run += c;
     }
-    bcount = run;
   }
-  const u32 dstart = block_exclusive_sum<u32, RADIX>(bcount, misc + 1, nullptr);
   // ---- decoupled look-back: how many keys with my digit precede this tile (within the part)
   if (tid < RADIX)
   {
@@ -236,7 +269,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   for (int i = 0; i < ITEMS; i++)
   {
     const u32 d = digit_of(keys[i], shift, mask);
-    const u32 pos = digit_start[d] + mywc[d] + ranks[i];
+    const u32 pos = mywc[d] + ranks[i];
     skeys[pos] = keys[i];
     if (HAS_VALS)
     {

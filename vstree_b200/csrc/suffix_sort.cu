@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(RG_THREADS)
 regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slots, u64 m,
                      const u32 *__restrict__ tile_maxrank, const u32 *__restrict__ tile_active, u32 *__restrict__ sa,
                      u32 *__restrict__ rank, u64 *__restrict__ next_key, u32 *__restrict__ next_pos,
-                     u32 *__restrict__ next_slots, u32 rank_shift)
+                     u32 *__restrict__ next_slots, u32 rank_shift, u8 *__restrict__ hround, u32 round)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
@@ -474,6 +474,15 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
         next_key[d] = (u64) r << rank_shift;
         next_pos[d] = p;
         next_slots[d] = slot;
+      }
+      if (!FIRST && hround != nullptr && t > 0 && (sflag[l] & 1))
+      {
+        // a head whose predecessor belongs to the same old group was split off in this round: the two
+        // suffixes agree on the depth of the round (lcp lower bound for the direct lcp kernel)
+        if ((u64) (skey[l + 1] >> rank_shift) == (u64) (skey[l] >> rank_shift))
+        {
+          hround[slot] = (u8) round;
+        }
       }
     }
   }
@@ -646,7 +655,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
              (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
                                                                               tile_active, sa, rank, dk_in, dp_in,
-                                                                              slots_cur, rank_shift)));
+                                                                              slots_cur, rank_shift, nullptr, 0u)));
   if (m == 0)
   {
     return;
@@ -662,6 +671,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   {
     outcome->rounds++;
     outcome->active_sum += m;
+    ctx->lcp_work_estimate += m * (h / 32 + 1);
     ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
                (gather_rank_kernel<<<div_up_u32(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, rank)));
     u64 *ks = dk_in, *ko = dk_out;
@@ -683,7 +693,8 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                  tile_active, sa, rank, ko, po,
-                                                                                 slots_next, rank_shift)));
+                                                                                 slots_next, rank_shift,
+                                                                                 ctx->d_hround, outcome->rounds)));
     dk_in = ko;
     dp_in = po;
     dk_out = ks;
