@@ -18,5 +18,6 @@ with Esa(0) as esa:
     esa.upload(tis, sigma)
     for i in range(reps):
         st = esa.construct(k, tables)
-        print("rep", i, "ms_total %.3f" % st["ms_total"], "launches", st["launches"], "rounds", st["rounds"])
+        print("rep", i, "ms_total %.3f" % st["ms_total"], "launches", st["launches"], "rounds", st["rounds"],
+              " ".join("%s=%.3f" % (k, v["ms"]) for k, v in st["kernel"].items() if v["launches"]))
     esa.check()

@@ -51,7 +51,8 @@ class Result(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libvstree_b200.so")
+    """The product library; VSTREE_B200_LIB overrides the path (tuning experiments with alternative builds)."""
+    return os.environ.get("VSTREE_B200_LIB") or os.path.join(_HERE, "lib", "libvstree_b200.so")
 
 
 _lib = None

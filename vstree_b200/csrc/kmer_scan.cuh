@@ -55,24 +55,39 @@ __device__ __forceinline__ void ks_load_tile(const u8 *__restrict__ tis, u64 n, 
 __device__ __forceinline__ void ks_scan_thread(const u8 *stext, int lo, const KmerParams &kp, u32 *code, u32 *dist)
 {
   u32 c = kp.all_pad, d = 0;
-  // warm-up over the h-1 symbols behind the thread's last position
-  for (int q = lo + KS_ITEMS - 1 + (int) kp.h - 1; q >= lo + KS_ITEMS; q--)
+  // the thread's 16 symbols and the 32 behind them as three 16-byte shared-memory loads (conflict free; byte loads
+  // at a 16-byte stride were 4-way bank conflicts: 1.1e8 conflicts per 100 Mbp in the round-1 profile)
+  u32 w[12];
   {
-    const u32 a = stext[q];
-    if (a >= ESA_WILDCARD)
+    const uint4 *src = reinterpret_cast<const uint4 *>(stext + lo);
+    const uint4 x0 = src[0], x1 = src[1], x2 = src[2];
+    w[0] = x0.x, w[1] = x0.y, w[2] = x0.z, w[3] = x0.w;
+    w[4] = x1.x, w[5] = x1.y, w[6] = x1.z, w[7] = x1.w;
+    w[8] = x2.x, w[9] = x2.y, w[10] = x2.z, w[11] = x2.w;
+  }
+  // warm-up over the h-1 symbols behind the thread's last position
+#pragma unroll
+  for (int j = KS_HALO - 2; j >= 0; j--)
+  {
+    if (j < (int) kp.h - 1)
     {
-      c = kp.all_pad;
-      d = 0;
-    } else
-    {
-      c = (kp.sigma_shift ? (c >> kp.sigma_shift) : (c / kp.sigma)) + a * kp.top_power;
-      d = min(d + 1, kp.h);
+      const int q = KS_ITEMS + j;
+      const u32 a = (w[q >> 2] >> ((q & 3) * 8)) & 0xffu;
+      if (a >= ESA_WILDCARD)
+      {
+        c = kp.all_pad;
+        d = 0;
+      } else
+      {
+        c = (kp.sigma_shift ? (c >> kp.sigma_shift) : (c / kp.sigma)) + a * kp.top_power;
+        d = min(d + 1, kp.h);
+      }
     }
   }
 #pragma unroll
   for (int i = KS_ITEMS - 1; i >= 0; i--)
   {
-    const u32 a = stext[lo + i];
+    const u32 a = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
     if (a >= ESA_WILDCARD)
     {
       c = kp.all_pad;

@@ -99,28 +99,34 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
       }
     }
     u32 l[4] = {0, 0, 0, 0};
-    if (want_lcp)
-    {
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-      {
-        if (q < cnt && r0 + q > 0)
-        {
-          const u32 lb = hr[q] ? (h0 << (hr[q] - 1)) : 0u;
-          l[q] = text.lcp(s[q], s[q + 1], lb);
-        }
-      }
-    }
     u8 bb[4] = {0, 0, 0, 0};
-    if (bwt != nullptr)
+    if (want_lcp || bwt != nullptr)
     {
+      // every suffix start is probed once (first window, special mask, preceding symbol): five independent
+      // probes per thread serve four comparisons and four bwt symbols
+      typename Text::Probe pr[5];
+#pragma unroll
+      for (int q = 0; q < 5; q++)
+      {
+        pr[q] = text.probe(s[q]);
+      }
 #pragma unroll
       for (int q = 0; q < 4; q++)
       {
         if (q < cnt)
         {
-          const u32 c = text.before(s[q + 1]);
-          bb[q] = s[q + 1] > 0 ? (u8) c : (u8) ESA_UNDEFBWTCHAR;
+          bb[q] = s[q + 1] > 0 ? (u8) pr[q + 1].before : (u8) ESA_UNDEFBWTCHAR;
+        }
+        if (want_lcp && q < cnt && r0 + q > 0)
+        {
+          const u32 lb = hr[q] ? (h0 << (hr[q] - 1)) : 0u;
+          // pairs split by a doubling round agree on lb symbols: start there (at most lb/WINDOW + 1 steps)
+          const u32 stop = lb == 0 ? Text::probe_stop(pr[q], pr[q + 1]) : text.step((u64) s[q] + lb, (u64) s[q + 1] + lb);
+          l[q] = lb + stop;
+          if (stop == Text::WINDOW)
+          {
+            l[q] = text.lcp(s[q], s[q + 1], l[q]);
+          }
         }
       }
     }

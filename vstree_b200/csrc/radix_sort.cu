@@ -20,7 +20,22 @@ namespace
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 512;
+#ifndef ESA_SORT_THREADS
+#define ESA_SORT_THREADS 512
+#endif
+#ifndef ESA_SORT_ITEMS32
+#define ESA_SORT_ITEMS32 16
+#endif
+#ifndef ESA_SORT_ITEMS64
+#define ESA_SORT_ITEMS64 12
+#endif
+#ifndef ESA_SORT_MINBLOCKS
+#define ESA_SORT_MINBLOCKS 2
+#endif
+#ifndef ESA_SORT_MATCH
+#define ESA_SORT_MATCH 0  // 0: eight ballots per key, 1: shared-memory atomicOr lane masks
+#endif
+constexpr int SORT_THREADS = ESA_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_ITEMS = 8;
@@ -31,11 +46,11 @@ constexpr u32 STATUS_VALUE_MASK = (1u << 30) - 1;
 template <typename KeyT> struct SortTraits;
 template <> struct SortTraits<u32>
 {
-  static constexpr int ITEMS = 16;
+  static constexpr int ITEMS = ESA_SORT_ITEMS32;
 };
 template <> struct SortTraits<u64>
 {
-  static constexpr int ITEMS = 12;
+  static constexpr int ITEMS = ESA_SORT_ITEMS64;
 };
 
 template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, u32 shift, u32 mask)
@@ -129,7 +144,7 @@ radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npas
 
 // ---------------------------------------------------------------------------------------------------------
 template <typename KeyT, bool HAS_VALS, int ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS, 2)
+__global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
 radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin,
                   u32 *__restrict__ vout, u32 count, u32 shift, u32 mask, const u32 *__restrict__ base,
                   volatile u32 *status, u32 *ticket)
@@ -153,6 +168,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   for (int d = lane; d < RADIX; d += 32)
   {
     mywc[d] = 0;
+#if ESA_SORT_MATCH == 1
+    misc[16 + warp * RADIX + d] = 0;
+#endif
   }
   __syncthreads();
   const u32 tile = misc[0];
@@ -174,6 +192,31 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   // lanes holding the same digit, found with one ballot per digit bit.  MATCH.ANY does the same in one
   // instruction but its cost grows with the number of distinct values in the warp (ncu, round 1: the instruction
   // behind it held 35 % of all stall samples and splitting it from its use changed nothing).
+#if ESA_SORT_MATCH == 1
+  // Variant: peers through a per-warp, per-digit lane mask in shared memory (one atomicOr per key, read back after
+  // a warp barrier) instead of eight ballots: far fewer instructions, three shared-memory round trips per step.
+  u32 *mymm = misc + 16 + warp * RADIX;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 d = digit_of(keys[i], shift, mask);
+    atomicOr(&mymm[d], 1u << lane);
+    __syncwarp();
+    const u32 peers = mymm[d];
+    __syncwarp();  // every lane has read the mask before its leader clears it
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if (lane == leader)
+    {
+      old = mywc[d];
+      mywc[d] = old + __popc(peers);
+      mymm[d] = 0;
+    }
+    old = __shfl_sync(FULL_MASK, old, leader);
+    ranks[i] = old + __popc(peers & lt_mask);
+    __syncwarp();
+  }
+#else
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
@@ -205,6 +248,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     ranks[i] = old + __popc(peers & lt_mask);
     __syncwarp();
   }
+#endif
   __syncthreads();
   // ---- per digit: tile count, then (after the scan over digits) the first slot of every warp's run
   u32 bcount = 0;
@@ -300,7 +344,7 @@ template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
 {
   constexpr int TILE = SORT_THREADS * SortTraits<KeyT>::ITEMS;
   return (size_t) TILE * sizeof(KeyT) + (has_vals ? (size_t) TILE * 4 : 0) + (size_t) SORT_WARPS * RADIX * 4
-         + 2 * RADIX * 4 + (1 + RADIX / 32 + 1 + 6) * 4;
+         + 2 * RADIX * 4 + (1 + RADIX / 32 + 1 + 6) * 4 + (ESA_SORT_MATCH == 1 ? (size_t) SORT_WARPS * RADIX * 4 : 0);
 }
 
 template <typename KeyT> u64 part_items_max()

@@ -129,8 +129,10 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32
                      u32 *__restrict__ sa, u32 *__restrict__ rank)
 {
   __shared__ __align__(16) u8 stext[KS_TILE + KS_HALO];
-  __shared__ u32 skey[KS_TILE];
-  __shared__ u32 spos[KS_TILE];
+  // staging for coalesced output; index e is stored at e + e/32 so that the 16-strided per-thread writes hit
+  // 32 different banks
+  __shared__ u32 skey[KS_TILE + KS_TILE / 32];
+  __shared__ u32 spos[KS_TILE + KS_TILE / 32];
   __shared__ u32 scratch[KS_THREADS / 32 + 1];
   const u64 tile_base = (u64) blockIdx.x * KS_TILE;
   const u64 N = n + 1;
@@ -187,8 +189,8 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32
         rs++;
       } else
       {
-        skey[rf] = code[i] << 1;
-        spos[rf] = (u32) p;
+        skey[rf + (rf >> 5)] = code[i] << 1;
+        spos[rf + (rf >> 5)] = (u32) p;
         rf++;
       }
     }
@@ -196,8 +198,8 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32
   __syncthreads();
   for (u32 r = threadIdx.x; r < tfull; r += KS_THREADS)
   {
-    main_key[off_full + r] = skey[r];
-    main_pos[off_full + r] = spos[r];
+    main_key[off_full + r] = skey[r + (r >> 5)];
+    main_pos[off_full + r] = spos[r + (r >> 5)];
   }
 }
 
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(RG_THREADS)
 regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slots, u64 m,
                      const u32 *__restrict__ tile_maxrank, const u32 *__restrict__ tile_active, u32 *__restrict__ sa,
                      u32 *__restrict__ rank, u64 *__restrict__ next_key, u32 *__restrict__ next_pos,
-                     u32 *__restrict__ next_slots, u32 rank_shift, u8 *__restrict__ hround, u32 round)
+                     u32 *__restrict__ next_slots, u32 rank_shift, u8 *__restrict__ hround, u32 round,
+                     u32 *__restrict__ rank_out /* if set: rank_out[t] = rank instead of the scatter rank[pos] */)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
@@ -468,7 +471,13 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
       {
         sa[slot] = p;  // FIRST: the sorted position buffer already is sa[0..m)
       }
-      rank[p] = r;
+      if (rank_out != nullptr)
+      {
+        rank_out[t] = r;
+      } else
+      {
+        rank[p] = r;
+      }
       if (d != NONE32)
       {
         next_key[d] = (u64) r << rank_shift;
@@ -497,6 +506,51 @@ __global__ void gather_rank_kernel(u64 *__restrict__ key, const u32 *__restrict_
   {
     key[t] |= (u64) rank[(u64) pos[t] + h];
   }
+}
+
+// second half of the two-level rank scatter: (pos, rank) pairs arrive partitioned by the top bits of pos, so
+// the writes of one stretch of the input fall into one L2-sized window of the rank array
+__global__ void scatter_rank_kernel(const u32 *__restrict__ pos, const u32 *__restrict__ val, u64 m,
+                                    u32 *__restrict__ rank)
+{
+  const u64 t = ((u64) blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t + 4 <= m)
+  {
+    const uint4 p = *reinterpret_cast<const uint4 *>(pos + t), v = *reinterpret_cast<const uint4 *>(val + t);
+    rank[p.x] = v.x;
+    rank[p.y] = v.y;
+    rank[p.z] = v.z;
+    rank[p.w] = v.w;
+  } else
+  {
+    for (u64 q = t; q < m; q++)
+    {
+      rank[pos[q]] = val[q];
+    }
+  }
+}
+
+// Writing rank[pos[t]] = val[t] for m pairs in suffix-array order is a random 4-byte scatter over 4N bytes:
+// every write costs a 32-byte sector fetch plus a 32-byte write-back (measured 3.7 ms per 100 M on B200).
+// Two levels instead: one radix pass partitions the pairs by the top bits of pos (sequential traffic), then
+// the scatter runs window by window inside L2.  Worth it only for large m.
+constexpr u64 PARTITIONED_SCATTER_MIN = (u64) 1 << 22;
+constexpr u32 SCATTER_WINDOW_BITS = 23;  // 2^23 positions = 32 MB of the rank array per window
+
+bool scatter_ranks_partitioned(esa_ctx *ctx, u32 *pos, u32 *val, u64 m, u32 pos_bits, u32 *rank, u32 *tmp_pos,
+                               u32 *tmp_val, void *sort_temp, size_t temp_bytes)
+{
+  if (m < PARTITIONED_SCATTER_MIN || pos_bits <= SCATTER_WINDOW_BITS)
+  {
+    return false;
+  }
+  const u32 pbits = min(8u, pos_bits - SCATTER_WINDOW_BITS);
+  const int w = radix_sort_pairs_u32(ctx, pos, tmp_pos, val, tmp_val, m, pos_bits - pbits, pos_bits, sort_temp,
+                                     temp_bytes);
+  const u32 *p = w ? tmp_pos : pos, *v = w ? tmp_val : val;
+  ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
+             (scatter_rank_kernel<<<div_up_u32(div_up_u64(m, 4), 256), 256, 0, ctx->stream>>>(p, v, m, rank)));
+  return true;
 }
 
 u64 read_scalar(esa_ctx *ctx, const u64 *d_scalars, int idx)
@@ -652,10 +706,24 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   const u64 mal = m + 64;
   u64 *dk_in = ar.alloc<u64>(mal);
   u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
+  // scratch of the two-level rank scatter (rank in suffix-array order + the partitioned copy of (pos, rank));
+  // skipped when the arena is too tight, then ranks are scattered directly
+  u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
+  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS && ar.capacity - ar.top > 12 * (M + 64) + (1 << 20))
+  {
+    part_rank = ar.alloc<u32>(M + 64);
+    part_tp = ar.alloc<u32>(M + 64);
+    part_tv = ar.alloc<u32>(M + 64);
+  }
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
              (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
                                                                               tile_active, sa, rank, dk_in, dp_in,
-                                                                              slots_cur, rank_shift, nullptr, 0u)));
+                                                                              slots_cur, rank_shift, nullptr, 0u,
+                                                                              part_rank)));
+  if (part_rank != nullptr)
+  {
+    scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+  }
   if (m == 0)
   {
     return;
@@ -690,11 +758,17 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
     const u64 m_next = read_scalar(ctx, d_scalars, 4);
+    const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                  tile_active, sa, rank, ko, po,
                                                                                  slots_next, rank_shift,
-                                                                                 ctx->d_hround, outcome->rounds)));
+                                                                                 ctx->d_hround, outcome->rounds,
+                                                                                 two_level ? part_rank : nullptr)));
+    if (two_level)
+    {
+      scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+    }
     dk_in = ko;
     dp_in = po;
     dk_out = ks;
