@@ -10,7 +10,13 @@ CU := $(wildcard $(CSRC)/*.cu)
 OBJ := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU))
 HDR := $(wildcard $(CSRC)/*.cuh) include/vstree_b200.h
 
-all: $(LIBDIR)/libvstree_b200.so
+all: $(LIBDIR)/libvstree_b200.so $(BINDIR)/mkvtree
+
+# the drop-in host driver: plain C, links the C ABI only
+$(BINDIR)/mkvtree: vstree_b200/host/mkvtree.c include/vstree_b200.h $(LIBDIR)/libvstree_b200.so
+	@mkdir -p $(BINDIR)
+	gcc -O2 -std=gnu99 -Wall -Wextra -Iinclude -o $@ vstree_b200/host/mkvtree.c -L$(LIBDIR) -lvstree_b200 -lz \
+	    -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)

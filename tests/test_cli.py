@@ -1,0 +1,229 @@
+"""The mkvtree host driver (vstree_b200/bin/mkvtree) against the UNMODIFIED reference binary (oracle/_ref/mkvtree.x):
+same command line, same files byte for byte, same -v transcript, same error messages and exit codes.
+Cases that only write host-side tables (-tis/-ois) run on the CPU; the others need the GPU."""
+import gzip
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+from golden_inputs import CASES, make_input
+from vstree_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "vstree_b200", "bin", "mkvtree")
+
+needs_ref = pytest.mark.skipif(not ou.have_ref(), reason="oracle/_ref/mkvtree.x not built")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(OURS):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def run(binary, args, cwd):
+    pr = subprocess.run([binary] + args, cwd=cwd, capture_output=True)
+    files = {}
+    for fn in sorted(os.listdir(cwd)):
+        if "." in fn and fn.split(".")[-1] in ("prj", "al1", "al2", "tis", "ois", "des", "sds", "ssp", "suf", "lcp",
+                                                "llv", "bwt", "bck", "sti1", "skp"):
+            with open(os.path.join(cwd, fn), "rb") as f:
+                files[fn] = f.read()
+    return pr.returncode, pr.stdout.decode(errors="replace"), pr.stderr.decode(errors="replace"), files
+
+
+def transcript(out):
+    """-v output without the space-peak line (its numbers are build specific)."""
+    return [l for l in out.splitlines() if not l.startswith("overall space peak:")]
+
+
+def compare(tmp_path, inputs, args, expect_rc=0):
+    """Runs both binaries in twin directories holding the same input files; compares everything."""
+    da, db = tmp_path / "ref", tmp_path / "ours"
+    for d in (da, db):
+        d.mkdir()
+        for name, content in inputs.items():
+            (d / name).write_bytes(content)
+    ra = run(ou.REF_MKVTREE, args, str(da))
+    rb = run(OURS, args, str(db))
+    for d in (da, db):  # inputs are not part of the comparison
+        pass
+    assert rb[0] == ra[0], f"exit code {rb[0]} vs reference {ra[0]}: {rb[2]} | {ra[2]}"
+    if expect_rc is not None:
+        assert ra[0] == expect_rc, ra[2]
+    assert transcript(rb[1]) == transcript(ra[1])
+    if ra[0] != 0:
+        strip = lambda s, b: s.replace(b, "PROG")
+        assert strip(rb[2], OURS) == strip(ra[2], ou.REF_MKVTREE)
+    fa = {k: v for k, v in ra[3].items() if k not in inputs}
+    fb = {k: v for k, v in rb[3].items() if k not in inputs}
+    assert sorted(fa) == sorted(fb), f"files differ: {sorted(fb)} vs reference {sorted(fa)}"
+    for k in fa:
+        assert fa[k] == fb[k], f"{k} differs from the reference ({len(fb[k])} vs {len(fa[k])} bytes)"
+    return ra, rb
+
+
+DNA = (b">seq1 first\nACGTNACGTTTGACCA\nacgtnnacg\n>seq2\nGGGACGTRYACGT\n>s3 third one\nNNACGATCGATCGAT\n"
+       + b">s4 long\n" + b"\n".join(bytes(np.random.default_rng(5).choice(list(b"ACGTacgtN"), size=60).tolist())
+                                     for _ in range(12)) + b"\n>s5\nACGTACGTACGTACGTACGTTTTTTTTTTTTTTTTTTTTTTTTT\n")
+PROT = b">p1 alpha\nLVIFKREDAGSTNQYWPHMC\nXUBZLLV\n>p2\nMKVLAAGIVGLLLA*\n"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side only: no GPU involved
+@needs_ref
+@pytest.mark.parametrize("args", [
+    ["-db", "in.fna", "-dna", "-tis", "-ois", "-v"],
+    ["-db", "in.fna", "-dna", "-tis", "-indexname", "myidx"],
+    ["-db", "in.fna", "-dna", "-ois", "-pl", "2", "-v"],
+    ["-db", "in.fna", "-dna", "-pl", "-tis", "-v"],
+    ["-dna", "-v", "-tis", "-db", "in.fna"],
+])
+def test_host_tables_dna(tmp_path, args):
+    compare(tmp_path, {"in.fna": DNA}, args)
+
+
+@needs_ref
+def test_host_tables_protein(tmp_path):
+    compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-pl", "1", "-v"])
+
+
+@needs_ref
+def test_crlf_and_leading_whitespace(tmp_path):
+    data = b"\n  \n" + DNA.replace(b"\n", b"\r\n")
+    compare(tmp_path, {"in.fna": data}, ["-db", "in.fna", "-dna", "-tis", "-ois", "-v"])
+
+
+@needs_ref
+def test_gzipped_input(tmp_path):
+    compare(tmp_path, {"in.fna.gz": gzip.compress(DNA)}, ["-db", "in.fna.gz", "-dna", "-tis", "-ois", "-v"])
+
+
+@needs_ref
+def test_multiple_files_and_plain_member(tmp_path):
+    compare(tmp_path, {"a.fna": DNA, "b.fna": b">only\nTTTTGGGGCCCCAAAA\n", "c.txt": b"ACGTACGTNNACGT"},
+            ["-db", "a.fna", "b.fna", "c.txt", "-dna", "-tis", "-ois", "-indexname", "all", "-v"])
+
+
+@needs_ref
+def test_plain_input(tmp_path):
+    compare(tmp_path, {"p.txt": b"ACGTNACGTACCA"}, ["-db", "p.txt", "-dna", "-tis", "-ois", "-v"])
+
+
+@needs_ref
+def test_symbol_map(tmp_path, monkeypatch):
+    smap = b"# comment\naA\ncC\ngG\ntTuU\nnsywrkvbdhmNSYWRKVBDHM x\n"
+    compare(tmp_path, {"in.fna": DNA, "MyMap": smap}, ["-db", "in.fna", "-smap", "MyMap", "-tis", "-ois", "-pl", "1",
+                                                       "-v"])
+
+
+@needs_ref
+def test_existing_index_is_removed(tmp_path):
+    compare(tmp_path, {"in.fna": DNA, "in.fna.suf": b"stale", "in.fna.prj": b"stale", "in.fna.llv": b"x"},
+            ["-db", "in.fna", "-dna", "-tis", "-v"])
+
+
+@needs_ref
+@pytest.mark.parametrize("args,inputs", [
+    ([], {}),
+    (["-db"], {}),
+    (["-dna", "-tis"], {}),
+    (["-db", "in.fna", "-dna", "-tis", "-foo"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "-tis"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-bck"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-sti1"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-protein", "-tis"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-smap", "x", "-tis"], {"in.fna": DNA}),
+    (["-db", "in.fna", "in.fna", "-dna", "-tis"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-indexname", "x"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "-indexname"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "-pl", "0"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "-pl", "1024"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "-pl", "9"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-tis", "stray"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-protein", "-tis"], {"in.fna": DNA}),                      # lower-case letters are illegal
+    (["-db", "in.fna", "-dna", "-tis"], {"in.fna": b">a\nACGT\n>b\n\n>c\nAC\n"}),  # empty sequence
+    (["-db", "in.fna", "-dna", "-tis"], {"in.fna": b">a\nAC>GT\n"}),               # '>' inside a line
+    (["-db", "in.fna", "-dna", "-tis"], {"in.fna": b">a\nACGT\n>b\n"}),            # last sequence empty
+    (["-db", "p.txt", "-dna", "-tis"], {"p.txt": b"ACGT\n"}),                      # plain input, illegal newline
+    (["-db", "p.txt", "-dna", "-tis"], {"p.txt": b"ACXGT"}),
+])
+def test_error_behaviour(tmp_path, args, inputs):
+    ra, rb = compare(tmp_path, inputs, args, expect_rc=None)
+    assert ra[0] != 0
+
+
+def test_missing_file_message(tmp_path):
+    rc, out, err, files = run(OURS, ["-db", "nonexist", "-dna", "-tis"], str(tmp_path))
+    assert rc == 1 and 'cannot read file "nonexist": open failed: No such file or directory' in err
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["kat_survey", "dna_specials_50k", "protein_30k", "human_like_400k"])
+def test_host_tables_on_golden_inputs(tmp_path, name):
+    tis, sigma = make_input(name)
+    kind = "dna" if CASES[name][2] == "-dna" else "protein"
+    compare(tmp_path, {"g.fa": synth.to_fasta(tis, kind)}, ["-db", "g.fa", CASES[name][2], "-tis", "-ois", "-v"])
+
+
+@needs_ref
+def test_host_tables_on_reference_fixtures(tmp_path, refdata):
+    for rel, flag in (("testdata/at100K1", "-dna"), ("testdata/swiss10K", "-protein"),
+                      ("testdata/Grumbach/Wildcards.fna", "-dna")):
+        d = tmp_path / os.path.basename(rel)
+        d.mkdir()
+        with open(os.path.join(refdata, rel), "rb") as f:
+            compare(d, {"in": f.read()}, ["-db", "in", flag, "-tis", "-ois", "-pl", "-v"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the whole path: needs the GPU
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,data", [
+    (["-db", "in.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-v"], DNA),
+    (["-db", "in.fna", "-dna", "-pl", "2", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-v"], DNA),
+    (["-db", "in.fna", "-dna", "-pl", "1", "-sti1", "-v"], DNA),                   # writes lcp llv bck sti1, no suf
+    (["-db", "in.fna", "-dna", "-suf", "-lcp", "-v"], DNA),                        # no -pl: one global sort
+    (["-db", "in.fna", "-dna", "-v"], DNA),                                        # sorts, writes nothing
+    (["-db", "in.fna", "-dna", "-pl", "-bwt", "-indexname", "x"], DNA),
+    (["-db", "in.fna", "-protein", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-v"], PROT),
+])
+def test_full_cli_small(tmp_path, args, data):
+    compare(tmp_path, {"in.fna": data}, args)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["dna_specials_50k", "dna_repeat_200k", "dna_twocopies_60k", "protein_200k",
+                                  "human_like_400k", "poly_a_5000"])
+def test_full_cli_golden_inputs(tmp_path, name):
+    tis, sigma = make_input(name)
+    flag = CASES[name][2]
+    kind = "dna" if flag == "-dna" else "protein"
+    compare(tmp_path, {"g.fa": synth.to_fasta(tis, kind)},
+            ["-db", "g.fa", flag, "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-v"])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_full_cli_multifile_gz(tmp_path):
+    compare(tmp_path, {"a.fna.gz": gzip.compress(DNA), "b.fna": b">only\nTTTTGGGGCCCCAAAANNNNACGT\n"},
+            ["-db", "a.fna.gz", "b.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-tis", "-indexname", "two",
+             "-v"])
+
+
+@pytest.mark.gpu
+def test_at1mb_scale_cli_against_reference(tmp_path):
+    """Config 1 of BASELINE.json at its real size: a 1 Mbp multi-FASTA with ~2000 records and ~2 % specials."""
+    if not ou.have_ref():
+        pytest.skip("oracle/_ref/mkvtree.x did not travel")
+    tis = synth.dna_with_specials(800000, seed=17, nfrac=0.02, mean_run=8, records=1900)
+    compare(tmp_path, {"at.fna": synth.to_fasta(tis, "dna")},
+            ["-db", "at.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-bck", "-sti1", "-v"])

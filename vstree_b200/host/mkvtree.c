@@ -1,0 +1,1330 @@
+/*
+ * mkvtree.c -- host driver of the B200-native mkvtree: the reference's command line and on-disk index layout,
+ * with the enhanced-suffix-array construction done by libvstree_b200 (CUDA, sm_100a) through its C ABI.
+ *
+ * Written from scratch; it restates the BEHAVIOUR of
+ *   option parsing        src/Mkvtree/mkvtree.c:169-551 (mkvparseoptions), src/kurtz-basic/procopt.c:103-129
+ *   input and alphabets   src/Mkvtree/mkvinput.c, src/kurtz-basic/multiseq-adv.c:1036-1291,1360-1453,
+ *                         src/kurtz-basic/alphabet.c:180-410, src/kurtz-basic/parsemultiform.c:352-389
+ *   table writers         src/Mkvtree/mkvprocess.c:38-211,403-580,875-1089
+ *   main                  src/Mkvtree/mkvfile.c:37-79
+ * The host keeps alphabet transformation and file I/O; there is no CPU implementation of the sort behind it:
+ * without a GPU the program fails.
+ *
+ * Not supported (reported as errors): -q, -rev, -cpl, -maxdepth, -skp/-allout, GenBank/EMBL/SwissProt input,
+ * input without one of -dna/-protein/-smap.
+ */
+#define _GNU_SOURCE
+#include <ctype.h>
+#include <errno.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include "vstree_b200.h"
+
+#define AUTOPREFIXLENGTH 1024u          /* src/Mkvtree/mkvtree.c (AUTOPREFIXLENGTH) */
+#define MAXNUMBEROFFILES 256u
+#define UNDEFCHAR 253u                  /* src/include/chardef.h */
+#define WILDCARD ESA_WILDCARD
+#define SEPARATOR ESA_SEPARATOR
+#define ISSPECIAL(c) ((c) >= WILDCARD)
+#define OUTPUTTABS (ESA_TISTAB | ESA_OISTAB | ESA_BWTTAB | ESA_SUFTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB)
+
+static char message[4096 + 2 * PATH_MAX];
+
+static int fail(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(message, sizeof message, fmt, ap);
+  va_end(ap);
+  return -1;
+}
+
+static int verbose = 0;
+static void say(const char *fmt, ...)
+{
+  if (verbose)
+  {
+    va_list ap;
+    va_start(ap, fmt);
+    vprintf(fmt, ap);
+    va_end(ap);
+    printf("\n");
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* options */
+
+enum
+{
+  OPTDB, OPTQ, OPTSMAP, OPTDNA, OPTPROTEIN, OPTTRANSNUM, OPTPL, OPTREV, OPTCPL, OPTINDEXNAME, OPTTIS, OPTOIS, OPTSUF,
+  OPTSTI1, OPTBWT, OPTBCK, OPTLCP, OPTSKP, OPTALLOUT, OPTMAXDEPTH, OPTV, OPTVERSION, OPTHELP, NUMOFOPTIONS
+};
+
+static const char *optname[NUMOFOPTIONS] = {
+  "-db", "-q", "-smap", "-dna", "-protein", "-transnum", "-pl", "-rev", "-cpl", "-indexname", "-tis", "-ois", "-suf",
+  "-sti1", "-bwt", "-bck", "-lcp", "-skp", "-allout", "-maxdepth", "-v", "-version", "-help"
+};
+
+static const char *optdesc[NUMOFOPTIONS] = {
+  "specify database files (mandatory)", "specify query files", "specify file containing a symbol mapping",
+  "input is DNA sequence", "input is Protein sequence", "(only for mkdna6idx)",
+  "specify prefix length for bucket sort\nrecommendation: use without argument;\nthen a reasonable prefix length is "
+  "automatically determined",
+  "use reverse input sequence", "use reverse complement of the input sequence",
+  "specify name for index to be generated", "output transformed input sequences (tistab) to file",
+  "output original input sequences (oistab) to file", "output suffix array (suftab) to file",
+  "output reduced inverse suffix array (sti1tab) to file", "output Burrows-Wheeler Transformation (bwttab) to file",
+  "output bucket boundaries (bcktab) to file", "output longest common prefix lengths (lcptab) to file",
+  "output skip values (skptab) to file", "output all index tables to files",
+  "restrict the sorting to prefixes of the given length", "verbose mode", "show the version of the program",
+  "this option"
+};
+
+typedef struct
+{
+  int isset[NUMOFOPTIONS];
+  uint32_t demand;
+  uint32_t prefixlength;
+  const char *smapfile;
+  const char *files[MAXNUMBEROFFILES];
+  unsigned numoffiles;
+  char indexname[PATH_MAX + 1];
+} Options;
+
+static int isoption(const char *s) { return s[0] == '-' && isalpha((unsigned char) s[1]); }
+
+static int imply(const Options *o, int a, int b)
+{
+  if (o->isset[a] && !o->isset[b])
+  {
+    return fail("option %s requires option %s", optname[a], optname[b]);
+  }
+  return 0;
+}
+
+static int exclude(const Options *o, int a, int b)
+{
+  if (o->isset[a] && o->isset[b])
+  {
+    return fail("option %s and option %s exclude each other", optname[a], optname[b]);
+  }
+  return 0;
+}
+
+static void showhelp(const char *prog)
+{
+  printf("%s: options\n", prog);
+  for (int i = 0; i < NUMOFOPTIONS; i++)
+  {
+    if (i == OPTTRANSNUM)
+    {
+      continue;
+    }
+    const char *d = optdesc[i];
+    printf("%-11s", optname[i]);
+    for (; *d; d++)
+    {
+      putchar(*d);
+      if (*d == '\n')
+      {
+        printf("%-11s", "");
+      }
+    }
+    putchar('\n');
+  }
+}
+
+/* returns 0 ok, 1 help/version shown, -1 usage, -2 other error */
+static int parseoptions(Options *o, int argc, char **argv)
+{
+  int argnum;
+  memset(o, 0, sizeof *o);
+  if (argc == 1)
+  {
+    fail("Usage: %s options indexname\n%s -help shows possible options", argv[0], argv[0]);
+    return -1;
+  }
+  for (argnum = 1; argnum < argc && isoption(argv[argnum]); argnum++)
+  {
+    int opt = -1;
+    long readint;
+    if (strcmp("-prefix", argv[argnum]) == 0)
+    {
+      fprintf(stderr, "%s: option -prefix has been renamed to %s", argv[0], optname[OPTINDEXNAME]);
+      exit(EXIT_FAILURE);
+    }
+    for (int i = 0; i < NUMOFOPTIONS; i++)
+    {
+      if (strcmp(argv[argnum], optname[i]) == 0)
+      {
+        opt = i;
+        break;
+      }
+    }
+    if (opt < 0)
+    {
+      fail("illegal option \"%s\"", argv[argnum]);
+      return -2;
+    }
+    if (o->isset[opt])
+    {
+      fail("option \"%s\" already set", argv[argnum]);
+      return -2;
+    }
+    o->isset[opt] = 1;
+    switch (opt)
+    {
+      case OPTHELP:
+        showhelp(argv[0]);
+        return 1;
+      case OPTVERSION:
+        printf("mkvtree (Vmatch-compatible index construction) %s\n", esa_version());
+        return 1;
+      case OPTSMAP:
+      case OPTINDEXNAME:
+        argnum++;
+        if (argnum >= argc || isoption(argv[argnum]))
+        {
+          fail("missing argument to option %s", optname[opt]);
+          return -2;
+        }
+        if (opt == OPTSMAP)
+        {
+          o->smapfile = argv[argnum];
+        } else
+        {
+          if (strlen(argv[argnum]) > PATH_MAX)
+          {
+            fail("string \"%s\" is too long, cannot copy", argv[argnum]);
+            return -2;
+          }
+          strcpy(o->indexname, argv[argnum]);
+        }
+        break;
+      case OPTTRANSNUM:
+        fail("illegal option \"%s\"", optname[OPTTRANSNUM]);
+        return -2;
+      case OPTPL:
+        if (argnum + 1 < argc && !isoption(argv[argnum + 1]))
+        {
+          argnum++;
+          if (sscanf(argv[argnum], "%ld", &readint) != 1 || readint <= 0)
+          {
+            fail("argument \"%s\" of option %s must be positive number", argv[argnum], optname[OPTPL]);
+            return -2;
+          }
+          o->prefixlength = (uint32_t) readint;
+          if (o->prefixlength == AUTOPREFIXLENGTH)
+          {
+            fail("Illegal value %lu as argument to option %s", (unsigned long) o->prefixlength, optname[OPTPL]);
+            return -2;
+          }
+        } else
+        {
+          o->prefixlength = AUTOPREFIXLENGTH;
+        }
+        break;
+      case OPTTIS: o->demand |= ESA_TISTAB; break;
+      case OPTOIS: o->demand |= ESA_OISTAB; break;
+      case OPTSUF: o->demand |= ESA_SUFTAB; break;
+      case OPTSTI1: o->demand |= ESA_STI1TAB | ESA_LCPTAB | ESA_BCKTAB; break;
+      case OPTBWT: o->demand |= ESA_BWTTAB; break;
+      case OPTBCK: o->demand |= ESA_BCKTAB; break;
+      case OPTLCP: o->demand |= ESA_LCPTAB; break;
+      case OPTSKP: o->demand |= ESA_SKPTAB; break;
+      case OPTV: verbose = 1; break;
+      case OPTMAXDEPTH:
+        if (!(argnum == argc - 1 || isoption(argv[argnum + 1])))
+        {
+          argnum++;
+          if (sscanf(argv[argnum], "%ld", &readint) != 1 || readint <= 0)
+          {
+            fail("argument \"%s\" of option %s must be positive number", argv[argnum], optname[OPTMAXDEPTH]);
+            return -2;
+          }
+        }
+        break;
+      case OPTDB:
+      case OPTQ:
+        argnum++;
+        while (argnum < argc)
+        {
+          if (isoption(argv[argnum]))
+          {
+            argnum--;
+            break;
+          }
+          if (opt == OPTDB && o->numoffiles < MAXNUMBEROFFILES)
+          {
+            o->files[o->numoffiles] = argv[argnum];
+          }
+          if (opt == OPTDB)
+          {
+            o->numoffiles++;
+          }
+          argnum++;
+        }
+        break;
+      default:
+        break;
+    }
+  }
+  if (argc > argnum)
+  {
+    fail("illegal additional argument \"%s\"", argv[argc - 1]);
+    return -2;
+  }
+  if (imply(o, OPTALLOUT, OPTPL) || imply(o, OPTSTI1, OPTPL) || imply(o, OPTBCK, OPTPL) || imply(o, OPTSKP, OPTLCP)
+      || imply(o, OPTSKP, OPTSUF) || exclude(o, OPTDNA, OPTSMAP) || exclude(o, OPTPROTEIN, OPTSMAP)
+      || exclude(o, OPTDNA, OPTPROTEIN))
+  {
+    return -2;
+  }
+  if (o->isset[OPTALLOUT])
+  {
+    if (o->demand & OUTPUTTABS)
+    {
+      fail("option %s cannot be combined with any other output option", optname[OPTALLOUT]);
+      return -2;
+    }
+    o->demand = OUTPUTTABS;
+  }
+  if (o->numoffiles == 0)
+  {
+    fail("option %s is mandatory", optname[OPTDB]);
+    return -2;
+  }
+  if (o->numoffiles >= MAXNUMBEROFFILES)
+  {
+    fail("too many input files, maximum is %lu", (unsigned long) MAXNUMBEROFFILES);
+    return -2;
+  }
+  /* what this build does not do (see the header comment) */
+  {
+    static const int unsupported[] = {OPTQ, OPTREV, OPTCPL, OPTMAXDEPTH, OPTSKP, OPTALLOUT};
+    for (size_t i = 0; i < sizeof unsupported / sizeof unsupported[0]; i++)
+    {
+      if (o->isset[unsupported[i]])
+      {
+        fail("option %s is not supported by the GPU build of mkvtree", optname[unsupported[i]]);
+        return -2;
+      }
+    }
+  }
+  if (o->isset[OPTINDEXNAME])
+  {
+    if (!(o->demand & OUTPUTTABS))
+    {
+      fail("option %s only allowed in connection with output option", optname[OPTINDEXNAME]);
+      return -2;
+    }
+  } else if (o->demand & OUTPUTTABS)
+  {
+    const char *base, *slash;
+    if (o->numoffiles > 1)
+    {
+      fail("option %s required for multiple input files", optname[OPTINDEXNAME]);
+      return -2;
+    }
+    slash = strrchr(o->files[0], '/');
+    base = slash != NULL && slash[1] != '\0' ? slash + 1 : o->files[0];
+    if (strlen(base) > PATH_MAX)
+    {
+      fail("string \"%s\" is too long, cannot copy", base);
+      return -2;
+    }
+    strcpy(o->indexname, base);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* alphabets */
+
+typedef struct
+{
+  unsigned symbolmap[UCHAR_MAX + 1];  /* UNDEFCHAR = not in the alphabet */
+  unsigned char mapdomain[UCHAR_MAX + 1];
+  unsigned char characters[UCHAR_MAX + 1];
+  unsigned domainsize, mapsize;
+} Alphabet;
+
+static void assign_builtin(Alphabet *a, const char *letters, int pairs, const char *wildcards, const char *domain)
+{
+  for (unsigned i = 0; i <= UCHAR_MAX; i++)
+  {
+    a->symbolmap[i] = UNDEFCHAR;
+  }
+  unsigned code = 0;
+  for (const char *p = letters; *p; code++)
+  {
+    /* DNA: "aA","cC","gG","tTuU" groups are given explicitly by the caller through `pairs` */
+    if (pairs)
+    {
+      while (*p && *p != ' ')
+      {
+        a->symbolmap[(unsigned char) *p++] = code;
+      }
+      if (*p == ' ')
+      {
+        p++;
+      }
+    } else
+    {
+      a->symbolmap[(unsigned char) *p++] = code;
+    }
+  }
+  for (const char *p = wildcards; *p; p++)
+  {
+    a->symbolmap[(unsigned char) *p] = WILDCARD;
+  }
+  a->domainsize = (unsigned) strlen(domain);
+  memcpy(a->mapdomain, domain, a->domainsize);
+  a->mapsize = code + 1;
+}
+
+static FILE *scanpathsforfile(const char *envname, const char *filename)
+{
+  FILE *fp = fopen(filename, "rb");
+  const char *env;
+  if (fp != NULL)
+  {
+    return fp;
+  }
+  if (strchr(filename, '/') != NULL)
+  {
+    fail("filename \"%s\" contains illegal symbol '%c': the path list specified by environment variable \"%s\" "
+         "cannot be searched for it", filename, '/', envname);
+    return NULL;
+  }
+  env = getenv(envname);
+  if (env != NULL)
+  {
+    char *copy = strdup(env), *save = NULL;
+    for (char *dir = strtok_r(copy, ":", &save); dir != NULL; dir = strtok_r(NULL, ":", &save))
+    {
+      char path[2 * PATH_MAX + 2];
+      snprintf(path, sizeof path, "%s/%s", dir, filename);
+      fp = fopen(path, "rb");
+      if (fp != NULL)
+      {
+        free(copy);
+        return fp;
+      }
+    }
+    free(copy);
+  }
+  fail("cannot find file \"%s\"", filename);
+  return NULL;
+}
+
+/* symbol map file: one line per code, the last line holds the wildcards; "xyz c" shows the class as c
+   (src/kurtz-basic/alphabet.c:180-290) */
+static int read_symbolmap(Alphabet *a, const char *mapfile)
+{
+  FILE *fp = scanpathsforfile("MKVTREESMAPDIR", mapfile);
+  char *line = NULL;
+  size_t cap = 0;
+  ssize_t len;
+  unsigned long linecount = 0;
+  int preamble = 1;
+  if (fp == NULL)
+  {
+    return -1;
+  }
+  a->domainsize = a->mapsize = 0;
+  for (unsigned i = 0; i <= UCHAR_MAX; i++)
+  {
+    a->symbolmap[i] = UNDEFCHAR;
+  }
+  while ((len = getline(&line, &cap, fp)) != -1)
+  {
+    ssize_t i;
+    int blankfound = 0;
+    if (len > 0 && line[len - 1] == '\n')
+    {
+      line[--len] = '\0';
+    }
+    linecount++;
+    if (len == 0)
+    {
+      continue;
+    }
+    if (preamble)
+    {
+      if (line[0] == '#')
+      {
+        continue;
+      }
+      preamble = 0;
+    }
+    for (i = 0; i < len; i++)
+    {
+      unsigned char cc = (unsigned char) line[i];
+      if (ispunct(cc) || isalnum(cc))
+      {
+        if (a->symbolmap[cc] != UNDEFCHAR)
+        {
+          fclose(fp);
+          free(line);
+          return fail("cannot map symbol '%c' to %lu: it is already mapped to %lu", cc, (unsigned long) a->mapsize,
+                      (unsigned long) a->symbolmap[cc]);
+        }
+        a->symbolmap[cc] = a->mapsize;
+        a->mapdomain[a->domainsize++] = cc;
+      } else if (cc == ' ')
+      {
+        blankfound = 1;
+        break;
+      } else
+      {
+        fclose(fp);
+        free(line);
+        return fail("illegal character '%c' in line %lu of mapfile %s", cc, linecount, mapfile);
+      }
+    }
+    if (blankfound)
+    {
+      if (isspace((unsigned char) line[i + 1]) || line[i + 1] == '\0')
+      {
+        fclose(fp);
+        free(line);
+        return fail("illegal character '%c' at the end of line %lu in mapfile %s", line[i + 1], linecount, mapfile);
+      }
+      a->characters[a->mapsize++] = (unsigned char) line[i + 1];
+    } else
+    {
+      a->characters[a->mapsize++] = (unsigned char) line[0];
+    }
+  }
+  free(line);
+  fclose(fp);
+  if (a->mapsize == 0)
+  {
+    return fail("symbol map file \"%s\" defines no symbols", mapfile);
+  }
+  for (unsigned i = 0; i <= UCHAR_MAX; i++)
+  {
+    if (a->symbolmap[i] == a->mapsize - 1)
+    {
+      a->symbolmap[i] = WILDCARD;
+    }
+  }
+  a->characters[WILDCARD] = a->characters[a->mapsize - 1];
+  return 0;
+}
+
+static int make_alphabet(Alphabet *a, const Options *o)
+{
+  memset(a, 0, sizeof *a);
+  if (o->isset[OPTDNA])
+  {
+    assign_builtin(a, "aA cC gG tTuU", 1, "nsywrkvbdhmNSYWRKVBDHM", "aAcCgGtTuUnsywrkvbdhmNSYWRKVBDHM");
+    memcpy(a->characters, "acgtn", 5);
+    a->characters[WILDCARD] = 'n';
+    return 0;
+  }
+  if (o->isset[OPTPROTEIN])
+  {
+    assign_builtin(a, "LVIFKREDAGSTNQYWPHMC", 0, "XUBZJO*-", "LVIFKREDAGSTNQYWPHMCXUBZJO*-");
+    memcpy(a->characters, "LVIFKREDAGSTNQYWPHMCX", 21);
+    a->characters[WILDCARD] = 'X';
+    return 0;
+  }
+  if (o->isset[OPTSMAP])
+  {
+    return read_symbolmap(a, o->smapfile);
+  }
+  return fail("input requires one of the options -smap, -dna, or -protein");
+}
+
+static void verbosealphabet(const Alphabet *a)
+{
+  if (!verbose)
+  {
+    return;
+  }
+  printf("alphabet \"");
+  for (unsigned i = 0; i < a->domainsize; i++)
+  {
+    unsigned char c = a->mapdomain[i];
+    if (isprint(c))
+    {
+      putchar(c);
+    } else
+    {
+      printf("\\%lu", (unsigned long) c);
+    }
+  }
+  printf("\" (size %lu) mapped to \"", (unsigned long) a->domainsize);
+  for (unsigned i = 0; i < a->mapsize; i++)
+  {
+    unsigned char c = a->characters[i];
+    if (isprint(c))
+    {
+      putchar(c);
+    } else
+    {
+      printf("\\%lu", (unsigned long) c);
+    }
+  }
+  printf("\" (size %lu)\n", (unsigned long) a->mapsize);
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* input */
+
+typedef struct
+{
+  uint8_t *tis, *ois;            /* transformed / original sequence, totallength bytes */
+  uint64_t totallength;
+  uint8_t *desc;                 /* descriptions, each ending in '\n' */
+  uint64_t desclen;
+  uint64_t *startdesc;           /* numofsequences + 1 offsets into desc */
+  uint64_t *markpos;             /* numofsequences - 1 separator positions */
+  uint64_t numofsequences;
+  uint64_t specialcharacters, specialranges, lengthofspecialprefix, lengthofspecialsuffix;
+  uint64_t filelength[MAXNUMBEROFFILES];
+  uint64_t filesep[MAXNUMBEROFFILES];   /* separator position in tis between file i and i+1 */
+} Multiseq;
+
+static int hasgzsuffix(const char *name)
+{
+  size_t l = strlen(name);
+  return l > 3 && strcmp(name + l - 3, ".gz") == 0;
+}
+
+static uint8_t *readwholefile(const char *name, uint64_t *len)
+{
+  uint8_t *buf = NULL;
+  uint64_t cap = 0, used = 0;
+  if (hasgzsuffix(name))
+  {
+    gzFile gz = gzopen(name, "rb");
+    if (gz == NULL)
+    {
+      fail("cannot read file \"%s\": open failed: %s", name, strerror(errno));
+      return NULL;
+    }
+    for (;;)
+    {
+      int got;
+      if (cap - used < (1u << 20))
+      {
+        cap = cap ? 2 * cap : (1u << 22);
+        buf = realloc(buf, cap + 1);
+        if (buf == NULL)
+        {
+          fail("not enough memory to read \"%s\"", name);
+          return NULL;
+        }
+      }
+      got = gzread(gz, buf + used, (unsigned) (cap - used > (1u << 30) ? (1u << 30) : cap - used));
+      if (got < 0)
+      {
+        fail("cannot read gzipped file \"%s\"", name);
+        free(buf);
+        gzclose(gz);
+        return NULL;
+      }
+      if (got == 0)
+      {
+        break;
+      }
+      used += (uint64_t) got;
+    }
+    gzclose(gz);
+  } else
+  {
+    FILE *fp = fopen(name, "rb");
+    struct stat st;
+    if (fp == NULL || fstat(fileno(fp), &st) != 0)
+    {
+      fail("cannot read file \"%s\": open failed: %s", name, strerror(errno));
+      if (fp != NULL)
+      {
+        fclose(fp);
+      }
+      return NULL;
+    }
+    cap = (uint64_t) st.st_size;
+    buf = malloc(cap + 1);
+    if (buf == NULL)
+    {
+      fclose(fp);
+      fail("not enough memory to read \"%s\"", name);
+      return NULL;
+    }
+    used = fread(buf, 1, cap, fp);
+    fclose(fp);
+    if (used != cap)
+    {
+      free(buf);
+      fail("cannot read file \"%s\": short read", name);
+      return NULL;
+    }
+  }
+  buf[used] = 0;
+  *len = used;
+  return buf;
+}
+
+/* several files -> one buffer; a file that does not start with '>' gets a ">filename" line
+   (src/kurtz-basic/multiseq-adv.c:1360-1453) */
+static uint8_t *concatfiles(const Options *o, Multiseq *ms, uint64_t *concatfilesep, uint64_t *totalbytes)
+{
+  uint8_t *concat = NULL;
+  uint64_t used = 0, cap = 0;
+  for (unsigned f = 0; f < o->numoffiles; f++)
+  {
+    uint64_t len, skip = 0, namelen = strlen(o->files[f]);
+    uint8_t *buf = readwholefile(o->files[f], &len);
+    int isfasta = 0;
+    if (buf == NULL)
+    {
+      free(concat);
+      return NULL;
+    }
+    ms->filelength[f] = len;
+    for (uint64_t i = 0; i < len; i++)
+    {
+      if (isspace(buf[i]))
+      {
+        skip++;
+      } else
+      {
+        isfasta = buf[i] == '>';
+        break;
+      }
+    }
+    if (used + len + namelen + 8 > cap)
+    {
+      cap = 2 * (used + len + namelen + 8);
+      concat = realloc(concat, cap);
+      if (concat == NULL)
+      {
+        free(buf);
+        fail("not enough memory for the concatenated input");
+        return NULL;
+      }
+    }
+    if (f > 0)
+    {
+      concatfilesep[f - 1] = used;
+    }
+    if (!isfasta)
+    {
+      uint64_t show = hasgzsuffix(o->files[f]) ? namelen - 3 : namelen;
+      printf(">%.*s\n", (int) show, o->files[f]);  /* the reference prints this line, verbose or not */
+      used += (uint64_t) sprintf((char *) concat + used, ">%.*s\n", (int) show, o->files[f]);
+    }
+    say("reading file \"%s\"", o->files[f]);
+    memcpy(concat + used, buf + skip, len - skip);
+    used += len - skip;
+    if (!isfasta)
+    {
+      concat[used++] = '\n';
+    }
+    free(buf);
+  }
+  *totalbytes = used;
+  return concat;
+}
+
+#define PUSH(ARR, CNT, CAP, VAL)                                   \
+  do                                                               \
+  {                                                                \
+    if ((CNT) == (CAP))                                            \
+    {                                                              \
+      (CAP) = (CAP) ? 2 * (CAP) : 1024;                            \
+      (ARR) = realloc((ARR), (CAP) * sizeof *(ARR));               \
+      if ((ARR) == NULL)                                           \
+      {                                                            \
+        return fail("not enough memory while parsing the input");  \
+      }                                                            \
+    }                                                              \
+    (ARR)[(CNT)++] = (VAL);                                        \
+  } while (0)
+
+/* multiple FASTA -> tis, ois, descriptions, separator positions, special statistics
+   (src/kurtz-basic/multiseq-adv.c:1036-1250 readmultiplefastafilesep, :1260-1291 readmultiplefastafileagain) */
+static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, const uint8_t *input, uint64_t inputlen,
+                      uint64_t *concatfilesep, int wantois)
+{
+  uint64_t out = 0, linenum = 1, desccap = 0, sdcap = 0, sdcnt = 0, mpcap = 0, mpcnt = 0;
+  unsigned sepnum = 0;
+  int indesc = 0, lastwasspecial = 0;
+  ms->tis = malloc(inputlen + 1);
+  if (ms->tis == NULL)
+  {
+    return fail("not enough memory for the sequence");
+  }
+  for (uint64_t i = 0; i < inputlen; i++)
+  {
+    const uint8_t current = input[i];
+    if (indesc)
+    {
+      PUSH(ms->desc, ms->desclen, desccap, current);
+      if (current == '\n')
+      {
+        linenum++;
+        indesc = 0;
+      }
+    } else if (current == '>')
+    {
+      if (i > 0 && input[i - 1] != '\n')
+      {
+        return fail("Illegal character '%c' in file \"%s\" line %lu", current, o->files[sepnum],
+                    (unsigned long) linenum);
+      }
+      PUSH(ms->startdesc, sdcnt, sdcap, ms->desclen);
+      if (ms->numofsequences > 0)
+      {
+        if (sepnum + 1 < o->numoffiles && concatfilesep[sepnum] == i)
+        {
+          ms->filesep[sepnum++] = out;
+          linenum = 0;
+        }
+        PUSH(ms->markpos, mpcnt, mpcap, out);
+        if (!lastwasspecial)
+        {
+          ms->specialranges++;
+        }
+        ms->specialcharacters++;
+        lastwasspecial = 1;
+        ms->tis[out++] = SEPARATOR;
+      }
+      ms->numofsequences++;
+      indesc = 1;
+    } else if (isspace(current))
+    {
+      if (current == '\n')
+      {
+        linenum++;
+      }
+    } else
+    {
+      const unsigned acode = alpha->symbolmap[current];
+      if (acode == UNDEFCHAR)
+      {
+        return fail("Illegal character '%c' in file \"%s\" line %lu", current, o->files[sepnum],
+                    (unsigned long) linenum);
+      }
+      if (ISSPECIAL(acode))
+      {
+        if (!lastwasspecial)
+        {
+          ms->specialranges++;
+        }
+        ms->specialcharacters++;
+        lastwasspecial = 1;
+      } else
+      {
+        lastwasspecial = 0;
+      }
+      ms->tis[out++] = (uint8_t) acode;
+    }
+  }
+  PUSH(ms->startdesc, sdcnt, sdcap, ms->desclen);
+  if (ms->numofsequences == 0)
+  {
+    return fail("no sequences in multiple fasta file");
+  }
+  ms->totallength = out;
+  for (uint64_t p = 0; p < out && ISSPECIAL(ms->tis[p]); p++)
+  {
+    ms->lengthofspecialprefix++;
+  }
+  if (out > 0)
+  {
+    for (uint64_t p = out - 1; ISSPECIAL(ms->tis[p]); p--)
+    {
+      ms->lengthofspecialsuffix++;
+      if (p == 0)
+      {
+        break;
+      }
+    }
+  }
+  if (ms->numofsequences >= 2)
+  {
+    for (uint64_t m = 1; m < ms->numofsequences - 1; m++)
+    {
+      if (ms->markpos[m - 1] + 1 == ms->markpos[m])
+      {
+        return fail("sequence %lu is empty", (unsigned long) (m - 1));
+      }
+    }
+    if (ms->markpos[0] == 0)
+    {
+      return fail("sequence 0 is empty");
+    }
+    if (ms->markpos[ms->numofsequences - 2] == out - 1)
+    {
+      return fail("sequence %lu is empty", (unsigned long) (ms->numofsequences - 1));
+    }
+  }
+  if (wantois)
+  {
+    uint64_t q = 0;
+    int d = 0;
+    ms->ois = malloc(out + 1);
+    if (ms->ois == NULL)
+    {
+      return fail("not enough memory for the original sequence");
+    }
+    for (uint64_t i = 0; i < inputlen && q < out; i++)
+    {
+      if (d)
+      {
+        d = input[i] != '\n';
+      } else if (input[i] == '>')
+      {
+        if (i > 0)
+        {
+          ms->ois[q++] = SEPARATOR;
+        }
+        d = 1;
+      } else if (!isspace(input[i]))
+      {
+        ms->ois[q++] = input[i];
+      }
+    }
+  }
+  return 0;
+}
+
+/* a file that is not FASTA is taken verbatim as one sequence (src/Mkvtree/mkvinput.c:78-128) */
+static int parseplain(Multiseq *ms, const Alphabet *alpha, const uint8_t *input, uint64_t inputlen, int wantois)
+{
+  static const char dummy[] = "sequence 1\n";
+  ms->tis = malloc(inputlen + 1);
+  ms->desc = malloc(sizeof dummy);
+  ms->startdesc = malloc(2 * sizeof *ms->startdesc);
+  if (ms->tis == NULL || ms->desc == NULL || ms->startdesc == NULL)
+  {
+    return fail("not enough memory for the sequence");
+  }
+  memcpy(ms->desc, dummy, sizeof dummy - 1);
+  ms->desclen = sizeof dummy - 1;
+  ms->startdesc[0] = 0;
+  ms->startdesc[1] = ms->desclen;
+  ms->numofsequences = 1;
+  ms->totallength = inputlen;
+  if (wantois)
+  {
+    uint64_t q = 0;
+    ms->ois = malloc(inputlen + 1);
+    if (ms->ois == NULL)
+    {
+      return fail("not enough memory for the original sequence");
+    }
+    for (uint64_t i = 0; i < inputlen; i++)
+    {
+      if (!isspace(input[i]))
+      {
+        ms->ois[q++] = input[i];
+      }
+    }
+  }
+  for (uint64_t i = 0; i < inputlen; i++)
+  {
+    const unsigned acode = alpha->symbolmap[input[i]];
+    if (acode == UNDEFCHAR)
+    {
+      switch (input[i])
+      {
+        case '\n': return fail("Illegal newline");
+        case '\t': return fail("Illegal tabulator");
+        case ' ': return fail("Illegal blank");
+        default:
+          return isprint(input[i]) ? fail("Illegal character '%c'", input[i])
+                                   : fail("Illegal character '\\%lu'", (unsigned long) input[i]);
+      }
+    }
+    ms->tis[i] = (uint8_t) acode;
+  }
+  return 0;  /* the reference leaves the special statistics of plain input at zero */
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* output */
+
+static const char *tabsuffixes[] = {"tis", "ois", "des", "ssp", "bwt", "suf", "lcp", "bck", "sti1", "skp", "cld", "cld1",
+                                    "iso", "sti", "cfr", "crf", "lsf", "sds", "llv", "al1", "al2", "prj"};
+
+static int removeexistingindex(const char *indexname)
+{
+  for (size_t i = 0; i < sizeof tabsuffixes / sizeof tabsuffixes[0]; i++)
+  {
+    char name[PATH_MAX + 16];
+    struct stat st;
+    snprintf(name, sizeof name, "%s.%s", indexname, tabsuffixes[i]);
+    if (stat(name, &st) == 0)
+    {
+      if (unlink(name) == -1)
+      {
+        return fail("cannot remove file \"%s\"", name);
+      }
+      say("remove file \"%s\"", name);
+    }
+  }
+  return 0;
+}
+
+static FILE *openthefile(const char *indexname, const char *suffix, int announce)
+{
+  char name[PATH_MAX + 16];
+  struct stat st;
+  FILE *fp;
+  snprintf(name, sizeof name, "%s.%s", indexname, suffix);
+  if (stat(name, &st) == 0)
+  {
+    fail("cannot create file \"%s\": it already exists", name);
+    return NULL;
+  }
+  fp = fopen(name, "wb");
+  if (fp == NULL)
+  {
+    fail("cannot open file \"%s\": %s", name, strerror(errno));
+    return NULL;
+  }
+  if (announce)
+  {
+    say("create file \"%s\"", name);
+  }
+  return fp;
+}
+
+static int writetable(const char *indexname, const char *suffix, const void *data, size_t size, uint64_t count,
+                      int announce)
+{
+  FILE *fp = openthefile(indexname, suffix, announce);
+  if (fp == NULL)
+  {
+    return -1;
+  }
+  if (count > 0 && fwrite(data, size, count, fp) != count)
+  {
+    fclose(fp);
+    return fail("cannot write %lu items of size %lu: errormsg=\"%s\"", (unsigned long) count, (unsigned long) size,
+                strerror(errno));
+  }
+  if (fclose(fp) != 0)
+  {
+    return fail("cannot close file \"%s.%s\"", indexname, suffix);
+  }
+  return 0;
+}
+
+int main(int argc, char **argv)
+{
+  Options opt;
+  Alphabet alpha;
+  Multiseq ms;
+  esa_ctx *ctx = NULL;
+  esa_result res;
+  esa_stats stats;
+  char err[1024];
+  uint8_t *raw;
+  uint64_t rawlen, concatfilesep[MAXNUMBEROFFILES], skip;
+  uint32_t numofchars, k, builddemand;
+  int rc, dosort, somethingout;
+  FILE *lcpfp = NULL;
+
+  rc = parseoptions(&opt, argc, argv);
+  if (rc == 1)
+  {
+    return EXIT_SUCCESS;
+  }
+  if (rc == -1)
+  {
+    fprintf(stderr, "%s\n", message);
+    return EXIT_FAILURE;
+  }
+  if (rc < 0)
+  {
+    goto failure;
+  }
+  if (make_alphabet(&alpha, &opt) != 0)
+  {
+    goto failure;
+  }
+  memset(&ms, 0, sizeof ms);
+  memset(concatfilesep, 0, sizeof concatfilesep);
+  if (opt.numoffiles == 1)
+  {
+    raw = readwholefile(opt.files[0], &rawlen);
+    if (raw == NULL)
+    {
+      goto failure;
+    }
+    ms.filelength[0] = rawlen;
+    say("reading%sfile \"%s\"", hasgzsuffix(opt.files[0]) ? " gzipped " : " ", opt.files[0]);
+  } else
+  {
+    raw = concatfiles(&opt, &ms, concatfilesep, &rawlen);
+    if (raw == NULL)
+    {
+      goto failure;
+    }
+  }
+  for (skip = 0; skip < rawlen && isspace(raw[skip]); skip++)
+  {
+  }
+  if (skip < rawlen && raw[skip] == '>')
+  {
+    /* the separator offsets of concatenated files refer to the unskipped buffer, but a concatenation never
+       starts with white space */
+    if (parsefasta(&ms, &alpha, &opt, raw + skip, rawlen - skip, concatfilesep, (opt.demand & ESA_OISTAB) != 0) != 0)
+    {
+      goto failure;
+    }
+  } else if (rawlen - skip >= 5 && (memcmp(raw + skip, "LOCUS", 5) == 0 || memcmp(raw + skip, "ID   ", 5) == 0))
+  {
+    fail("GenBank/EMBL/SwissProt input is not supported by the GPU build of mkvtree; convert it to FASTA");
+    goto failure;
+  } else
+  {
+    if (parseplain(&ms, &alpha, raw, rawlen, (opt.demand & ESA_OISTAB) != 0) != 0)
+    {
+      goto failure;
+    }
+  }
+  free(raw);
+  if (ms.totallength == 0)
+  {
+    fail("input sequences are all empty");
+    goto failure;
+  }
+  numofchars = alpha.mapsize - 1;
+  k = opt.prefixlength;
+  if (k == AUTOPREFIXLENGTH)
+  {
+    k = esa_recommended_prefixlength(numofchars, ms.totallength);
+  }
+  if (k > 0)
+  {
+    const uint32_t maxk = esa_maximal_prefixlength(numofchars, ms.totallength);
+    if (maxk < k)
+    {
+      fail("prefix length %lu is too large, maximal prefix length for this input size and alphabet size is %lu",
+           (unsigned long) k, (unsigned long) maxk);
+      goto failure;
+    }
+    say("for this input size and alphabet size, the maximal prefixlength\n(argument of option -pl) is %lu,\n"
+        "the recommended prefixlength is %lu", (unsigned long) maxk,
+        (unsigned long) esa_recommended_prefixlength(numofchars, ms.totallength));
+  }
+  if (ms.numofsequences > 1)
+  {
+    say("total length of sequences: %lu (including %lu separator%s)", (unsigned long) ms.totallength,
+        (unsigned long) (ms.numofsequences - 1), ms.numofsequences == 2 ? "" : "s");
+  } else
+  {
+    say("total length of sequences: %lu", (unsigned long) ms.totallength);
+  }
+  if (k > 0)
+  {
+    verbosealphabet(&alpha);
+  }
+  somethingout = (opt.demand & OUTPUTTABS) != 0;
+  if (somethingout && removeexistingindex(opt.indexname) != 0)
+  {
+    goto failure;
+  }
+  if (somethingout && ms.numofsequences > 1
+      && writetable(opt.indexname, "ssp", ms.markpos, sizeof(uint64_t), ms.numofsequences - 1, 0) != 0)
+  {
+    goto failure;
+  }
+  if ((opt.demand & ESA_TISTAB) && writetable(opt.indexname, "tis", ms.tis, 1, ms.totallength, 1) != 0)
+  {
+    goto failure;
+  }
+  if ((opt.demand & ESA_OISTAB) && ms.ois != NULL
+      && writetable(opt.indexname, "ois", ms.ois, 1, ms.totallength, 1) != 0)
+  {
+    goto failure;
+  }
+  if (somethingout && ms.desc != NULL)
+  {
+    if (writetable(opt.indexname, "des", ms.desc, 1, ms.desclen, 1) != 0
+        || writetable(opt.indexname, "sds", ms.startdesc, sizeof(uint64_t), ms.numofsequences + 1, 1) != 0)
+    {
+      goto failure;
+    }
+  }
+  dosort = !((opt.demand & (ESA_TISTAB | ESA_OISTAB))
+             && !(opt.demand & (ESA_BWTTAB | ESA_SUFTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB)));
+  memset(&res, 0, sizeof res);
+  memset(&stats, 0, sizeof stats);
+  if (dosort)
+  {
+    if (opt.demand & ESA_LCPTAB)
+    {
+      lcpfp = openthefile(opt.indexname, "lcp", 1);  /* the reference opens .lcp before it sorts */
+      if (lcpfp == NULL)
+      {
+        goto failure;
+      }
+    }
+    say("initializing data structures");
+    if (k > 0)
+    {
+      say("sorting suffixes according to prefix of length %lu", (unsigned long) k);
+      say("sorting all buckets");
+    } else
+    {
+      say("sorting suffixes");
+    }
+    {
+      const char *dev = getenv("MKVTREE_GPU");
+      if (esa_init(&ctx, dev != NULL ? atoi(dev) : 0, err, sizeof err) != 0)
+      {
+        fail("%s", err);
+        goto failure;
+      }
+    }
+    builddemand = ESA_SUFTAB | (opt.demand & (ESA_BWTTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB));
+    if (esa_build(ctx, ms.tis, ms.totallength, numofchars, k, builddemand, &res, &stats, err, sizeof err) != 0)
+    {
+      fail("%s", err);
+      goto failure;
+    }
+    if (lcpfp != NULL)
+    {
+      if (fwrite(res.lcptab, 1, ms.totallength + 1, lcpfp) != ms.totallength + 1 || fclose(lcpfp) != 0)
+      {
+        fail("cannot write %lu items of size 1: errormsg=\"%s\"", (unsigned long) (ms.totallength + 1),
+             strerror(errno));
+        goto failure;
+      }
+      lcpfp = NULL;
+      if (writetable(opt.indexname, "llv", res.llv, sizeof(esa_pairuint), res.nllv, 1) != 0)
+      {
+        goto failure;
+      }
+    }
+    if ((opt.demand & ESA_BCKTAB) && k > 0
+        && writetable(opt.indexname, "bck", res.bcktab, sizeof(uint64_t), 2 * res.numofcodes, 1) != 0)
+    {
+      goto failure;
+    }
+    if ((opt.demand & ESA_SUFTAB)
+        && writetable(opt.indexname, "suf", res.suftab, sizeof(uint64_t), ms.totallength + 1, 1) != 0)
+    {
+      goto failure;
+    }
+    if ((opt.demand & ESA_STI1TAB) && writetable(opt.indexname, "sti1", res.stitab1, 1, ms.totallength + 1, 1) != 0)
+    {
+      goto failure;
+    }
+    if ((opt.demand & ESA_BWTTAB) && writetable(opt.indexname, "bwt", res.bwttab, 1, ms.totallength + 1, 1) != 0)
+    {
+      goto failure;
+    }
+  }
+  if (somethingout)
+  {
+    uint64_t startseq = 0;
+    FILE *fp = openthefile(opt.indexname, "prj", 1);
+    if (fp == NULL)
+    {
+      goto failure;
+    }
+    for (unsigned f = 0; f < opt.numoffiles; f++)
+    {
+      fprintf(fp, "dbfile=%s %lu ", opt.files[f], (unsigned long) ms.filelength[f]);
+      if (f == opt.numoffiles - 1)
+      {
+        fprintf(fp, "%lu\n", (unsigned long) (ms.totallength - startseq));
+      } else
+      {
+        fprintf(fp, "%lu\n", (unsigned long) (ms.filesep[f] - startseq));
+        startseq = ms.filesep[f] + 1;
+      }
+    }
+    fprintf(fp, "totallength=%lu\n", (unsigned long) ms.totallength);
+    fprintf(fp, "specialcharacters=%lu\n", (unsigned long) ms.specialcharacters);
+    fprintf(fp, "specialranges=%lu\n", (unsigned long) ms.specialranges);
+    fprintf(fp, "lengthofspecialprefix=%lu\n", (unsigned long) ms.lengthofspecialprefix);
+    fprintf(fp, "lengthofspecialsuffix=%lu\n", (unsigned long) ms.lengthofspecialsuffix);
+    fprintf(fp, "numofsequences=%lu\n", (unsigned long) ms.numofsequences);
+    fprintf(fp, "numofdbsequences=%lu\n", (unsigned long) ms.numofsequences);
+    fprintf(fp, "numofquerysequences=0\n");
+    if (dosort)
+    {
+      fprintf(fp, "longest=%lu\n", (unsigned long) res.longest);
+    }
+    fprintf(fp, "prefixlength=%lu\n", (unsigned long) k);
+    if (opt.demand & ESA_LCPTAB)
+    {
+      fprintf(fp, "largelcpvalues=%lu\n", (unsigned long) res.nllv);
+      fprintf(fp, "maxbranchdepth=%lu\n", (unsigned long) res.maxbranchdepth);
+    } else
+    {
+      fprintf(fp, "largelcpvalues=0\nmaxbranchdepth=0\n");
+    }
+    fprintf(fp, "integersize=64\nlittleendian=1\n");
+    if (fclose(fp) != 0)
+    {
+      fail("cannot close file \"%s.prj\"", opt.indexname);
+      goto failure;
+    }
+    fp = openthefile(opt.indexname, "al1", 1);
+    if (fp == NULL)
+    {
+      goto failure;
+    }
+    if (opt.isset[OPTSMAP])
+    {
+      FILE *in = scanpathsforfile("MKVTREESMAPDIR", opt.smapfile);
+      int cc;
+      if (in == NULL)
+      {
+        goto failure;
+      }
+      while ((cc = fgetc(in)) != EOF)
+      {
+        putc(cc, fp);
+      }
+      fclose(in);
+    } else if (opt.isset[OPTDNA])
+    {
+      fputs("aA\ncC\ngG\ntTuU\nnsywrkvbdhmNSYWRKVBDHM\n", fp);
+    } else
+    {
+      fputs("L\nV\nI\nF\nK\nR\nE\nD\nA\nG\nS\nT\nN\nQ\nY\nW\nP\nH\nM\nC\nXUBZ*-\n", fp);
+    }
+    fclose(fp);
+  }
+  if (verbose)
+  {
+    /* same line format as src/Mkvtree/mkvfile.c:22-34; the numbers are this build's: host tables, device arena */
+    const double hostbytes = (double) ms.totallength * ((opt.demand & ESA_OISTAB) ? 2.0 : 1.0)
+                             + (double) stats.d2h_bytes;
+    printf("overall space peak: main=%.2f MB (%.2f bytes/symbol), secondary=%.2f MB\n", hostbytes / (1 << 20),
+           hostbytes / (double) ms.totallength, (double) stats.device_bytes_peak / (1 << 20));
+  }
+  if (ctx != NULL)
+  {
+    esa_free(ctx, &res);
+    esa_shutdown(ctx);
+  }
+  return EXIT_SUCCESS;
+
+failure:
+  fprintf(stderr, "%s: %s\n", argv[0], message);
+  return EXIT_FAILURE;
+}
