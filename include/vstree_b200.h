@@ -82,6 +82,10 @@ typedef struct
   uint8_t *stitab1;          /* [N]   min(rank - bucket left, 255), by text position */
   uint64_t *stitab;          /* [N]   full inverse suffix array */
   uint64_t *skiptab;         /* [N]   skip table */
+  /* sharded builds (esa_construct_sharded): suftab/lcptab/bwttab hold only the suffix-array entries
+     [shard_first, shard_first + shard_count) of this rank, llv indices are global; one GPU: 0 and N */
+  uint64_t shard_first;
+  uint64_t shard_count;
 } esa_result;
 
 /* Kernel families, for esa_stats.kernel[]. */
@@ -98,6 +102,8 @@ enum
   ESA_K_STI1,           /* reduced inverse suffix array */
   ESA_K_MISC,           /* scans over tile summaries, small helpers */
   ESA_K_MEMOP,          /* cudaMemsetAsync / device-to-device cudaMemcpyAsync nodes (not kernels of this library) */
+  ESA_K_COMM,           /* sharded builds: collectives (NCCL or in-process peer copies) between the ranks */
+  ESA_K_EXCHANGE,       /* sharded builds: owner tagging, request serving and answer merging around the collectives */
   ESA_K_NUM
 };
 
@@ -127,6 +133,9 @@ typedef struct
   /* end-to-end legs, filled by esa_build (0 otherwise) */
   double ms_h2d, ms_d2h;
   uint64_t h2d_bytes, d2h_bytes;
+  /* sharded builds (0 otherwise) */
+  uint64_t shard_first, shard_count; /* this rank's slice of the suffix array */
+  uint64_t comm_bytes_sent;          /* payload this rank sent to other ranks */
 } esa_stats;
 
 /* ---- lifetime ---- */
@@ -149,6 +158,32 @@ int esa_upload(esa_ctx *ctx, const uint8_t *tis, uint64_t n, uint32_t numofchars
 int esa_construct(esa_ctx *ctx, uint32_t prefixlength, uint32_t demand, esa_stats *stats, char *errbuf,
                   size_t errlen);
 int esa_download(esa_ctx *ctx, esa_result *out, char *errbuf, size_t errlen);
+
+/* ---- sharded builds: several GPUs build ONE index ----
+ * The suffix array is cut into contiguous ranges along first-symbols bins of the initial sort key; rank r of R builds
+ * range r.  Every rank uploads the WHOLE sequence (it is replicated), classifies its slice of text positions, sends each
+ * suffix to the rank that owns its bin (all-to-all), sorts its range (prefix doubling; ranks of foreign suffixes are
+ * fetched from their owners each round) and derives lcp/llv/bwt for its range.  Attach a communicator to a context,
+ * then call esa_upload / esa_construct / esa_download (or esa_build) on EVERY rank: they are collective.  The tables of
+ * esa_result then cover suffix-array entries [shard_first, shard_first + shard_count) only (llv indices are global;
+ * bcktab, maxbranchdepth and longest are complete on every rank); concatenating the ranks' tables in rank order gives
+ * the files the reference writes.  ESA_STI1TAB / ESA_STITAB and esa_check need the whole inverse suffix array on
+ * one device and are refused on a sharded context.
+ *
+ * Transport A, one process per GPU (NCCL over NVLink): rank 0 calls esa_comm_unique_id and distributes the id by any
+ * means (MPI, torch.distributed, a file); every rank calls esa_comm_attach_nccl.  libnccl.so.2 is loaded with dlopen.
+ * Transport B, one thread per rank inside one process: esa_group_create once, esa_comm_attach_group per context. */
+#define ESA_COMM_ID_BYTES 128
+typedef struct esa_group esa_group;
+int esa_comm_unique_id(uint8_t id[ESA_COMM_ID_BYTES], char *errbuf, size_t errlen);
+int esa_comm_attach_nccl(esa_ctx *ctx, const uint8_t id[ESA_COMM_ID_BYTES], int nranks, int rank, char *errbuf,
+                         size_t errlen);
+int esa_group_create(esa_group **group, int nranks, char *errbuf, size_t errlen);
+void esa_group_destroy(esa_group *group);
+void esa_group_abort(esa_group *group);   /* wakes ranks waiting in a collective; they fail with ESA_ERR_COMM */
+void esa_group_reset(esa_group *group);   /* after all ranks returned from a failed call: group usable again */
+int esa_comm_attach_group(esa_ctx *ctx, esa_group *group, int rank, char *errbuf, size_t errlen);
+void esa_comm_detach(esa_ctx *ctx);
 
 /* ---- suffix-to-text checks on the device (reference DEBUG checks: bese.c:355-528, cprsuf.c:66-95,
  * mkvprocess.c:672-763).  Runs on the tables left resident by the last esa_construct.  Returns 0 when

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(_HERE)
 DEMAND_BITS = {"tis": 1 << 0, "ois": 1 << 1, "des": 1 << 2, "ssp": 1 << 3, "bwt": 1 << 4, "suf": 1 << 5,
                "lcp": 1 << 6, "bck": 1 << 7, "sti1": 1 << 8, "skp": 1 << 9, "sti": 1 << 13}
 KERNEL_FAMILIES = ["classify", "radix_hist", "radix_pass", "regroup", "gather_rank", "bck", "plcp", "finalize",
-                   "sti1", "misc", "memop"]
+                   "sti1", "misc", "memop", "comm", "exchange"]
 ERRBUF = 1024
 
 
@@ -32,7 +32,9 @@ class Stats(ctypes.Structure):
                 ("rounds", ctypes.c_uint32), ("lcp_path", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("active_sum", ctypes.c_uint64), ("active_first", ctypes.c_uint64),
                 ("launches", ctypes.c_uint64), ("device_bytes_peak", ctypes.c_uint64),
                 ("kernel", KernelStat * len(KERNEL_FAMILIES)), ("ms_h2d", ctypes.c_double),
-                ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+                ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+                ("shard_first", ctypes.c_uint64), ("shard_count", ctypes.c_uint64),
+                ("comm_bytes_sent", ctypes.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "kernel"}
@@ -47,7 +49,8 @@ class Result(ctypes.Structure):
                 ("nllv", ctypes.c_uint64), ("maxbranchdepth", ctypes.c_uint64), ("longest", ctypes.c_uint64),
                 ("bwttab", ctypes.POINTER(ctypes.c_uint8)), ("bcktab", ctypes.POINTER(ctypes.c_uint64)),
                 ("stitab1", ctypes.POINTER(ctypes.c_uint8)), ("stitab", ctypes.POINTER(ctypes.c_uint64)),
-                ("skiptab", ctypes.POINTER(ctypes.c_uint64))]
+                ("skiptab", ctypes.POINTER(ctypes.c_uint64)), ("shard_first", ctypes.c_uint64),
+                ("shard_count", ctypes.c_uint64)]
 
 
 def library_path():
@@ -96,6 +99,22 @@ def load_library():
     lib.esa_debug_radix_sort.argtypes = [vp, c.c_int, vp, vp, c.c_uint64, c.c_uint32, c.c_uint32, cp, sz]
     lib.esa_version.restype = cp
     lib.esa_version.argtypes = []
+    lib.esa_comm_unique_id.restype = c.c_int
+    lib.esa_comm_unique_id.argtypes = [vp, cp, sz]
+    lib.esa_comm_attach_nccl.restype = c.c_int
+    lib.esa_comm_attach_nccl.argtypes = [vp, vp, c.c_int, c.c_int, cp, sz]
+    lib.esa_group_create.restype = c.c_int
+    lib.esa_group_create.argtypes = [c.POINTER(vp), c.c_int, cp, sz]
+    lib.esa_group_destroy.restype = None
+    lib.esa_group_destroy.argtypes = [vp]
+    lib.esa_group_abort.restype = None
+    lib.esa_group_abort.argtypes = [vp]
+    lib.esa_group_reset.restype = None
+    lib.esa_group_reset.argtypes = [vp]
+    lib.esa_comm_attach_group.restype = c.c_int
+    lib.esa_comm_attach_group.argtypes = [vp, vp, c.c_int, cp, sz]
+    lib.esa_comm_detach.restype = None
+    lib.esa_comm_detach.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -151,7 +170,7 @@ class Esa:
 
     @staticmethod
     def _tables(res, copy=True):
-        N = res.n + 1
+        N = res.shard_count  # n + 1 on one GPU, this rank's range of the suffix array in a sharded build
 
         def arr(ptr, count, dt):
             if not ptr:
@@ -164,7 +183,8 @@ class Esa:
                 "bwt": arr(res.bwttab, N, np.uint8), "bck": arr(res.bcktab, 2 * res.numofcodes, np.uint64),
                 "sti1": arr(res.stitab1, N, np.uint8), "sti": arr(res.stitab, N, np.uint64),
                 "maxbranchdepth": int(res.maxbranchdepth), "longest": int(res.longest),
-                "largelcpvalues": int(res.nllv), "numofcodes": int(res.numofcodes)}
+                "largelcpvalues": int(res.nllv), "numofcodes": int(res.numofcodes),
+                "shard_first": int(res.shard_first), "shard_count": int(res.shard_count)}
 
     def build(self, tis, numofchars, prefixlength, tables=("suf", "lcp", "bwt"), want_stats=True, copy=True):
         """esa_build: host buffer in, tables out.  Returns (tables dict, stats dict or None).
@@ -223,3 +243,119 @@ class Esa:
     def check(self):
         err = ctypes.create_string_buffer(ERRBUF)
         self._check(self.lib.esa_check(self.ctx, err, ERRBUF), err)
+
+    # ---- sharded builds: attach a communicator, then upload/construct/download/build are collective ----
+    def attach_nccl(self, unique_id, nranks, rank):
+        """One process per GPU: `unique_id` comes from comm_unique_id() on rank 0 (distribute it yourself)."""
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        err = ctypes.create_string_buffer(ERRBUF)
+        self._check(self.lib.esa_comm_attach_nccl(self.ctx, buf, nranks, rank, err, ERRBUF), err)
+
+    def detach(self):
+        self.lib.esa_comm_detach(self.ctx)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    err = ctypes.create_string_buffer(ERRBUF)
+    rc = lib.esa_comm_unique_id(buf, err, ERRBUF)
+    if rc != 0:
+        raise EsaError(rc, err.value.decode())
+    return buf.raw
+
+
+def merge_shards(parts):
+    """Concatenates the per-rank tables of a sharded build in rank order: the tables of the whole index."""
+    parts = sorted(parts, key=lambda t: t["shard_first"])
+    pos = 0
+    for t in parts:
+        assert t["shard_first"] == pos, "ranges of the ranks do not tile the suffix array"
+        pos += t["shard_count"]
+    out = dict(parts[0])
+    for name in ("suf", "lcp", "bwt", "llv"):
+        if parts[0].get(name) is not None:
+            out[name] = np.concatenate([t[name] for t in parts])
+    out["largelcpvalues"] = sum(t["largelcpvalues"] for t in parts)
+    out["shard_first"], out["shard_count"] = 0, pos
+    return out
+
+
+class EsaGroup:
+    """Several ranks inside one process, one thread per rank (transport B of include/vstree_b200.h).  `devices` lists
+    the CUDA device of every rank; ranks may share a device (that is how the single-GPU test box exercises the
+    sharded path)."""
+
+    def __init__(self, devices):
+        import threading
+        self._threading = threading
+        self.lib = load_library()
+        self.nranks = len(devices)
+        self.group = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(ERRBUF)
+        rc = self.lib.esa_group_create(ctypes.byref(self.group), self.nranks, err, ERRBUF)
+        if rc != 0:
+            raise EsaError(rc, err.value.decode())
+        self.ranks = [Esa(d) for d in devices]
+        for r, e in enumerate(self.ranks):
+            e._check(self.lib.esa_comm_attach_group(e.ctx, self.group, r, err, ERRBUF), err)
+
+    def close(self):
+        for e in self.ranks:
+            e.close()
+        self.ranks = []
+        if self.group:
+            self.lib.esa_group_destroy(self.group)
+            self.group = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _collective(self, fn):
+        """Runs fn(rank, esa) on one thread per rank (ctypes releases the GIL inside the library)."""
+        results, errors = [None] * self.nranks, [None] * self.nranks
+
+        def work(r):
+            try:
+                results[r] = fn(r, self.ranks[r])
+            except BaseException as exc:  # noqa: BLE001 -- reported below, after waking the other ranks
+                errors[r] = exc
+                self.lib.esa_group_abort(self.group)
+
+        threads = [self._threading.Thread(target=work, args=(r,)) for r in range(self.nranks)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if any(e is not None for e in errors):
+            self.lib.esa_group_reset(self.group)
+        for e in errors:
+            if e is not None and not (isinstance(e, EsaError) and e.code == -9):
+                raise e
+        for e in errors:
+            if e is not None:
+                raise e
+        return results
+
+    def build(self, tis, numofchars, prefixlength, tables=("suf", "lcp", "bwt"), merge=True):
+        """Collective esa_build.  Returns (tables of the whole index or the per-rank list, per-rank stats)."""
+        out = self._collective(lambda r, e: e.build(tis, numofchars, prefixlength, tables))
+        parts, stats = [o[0] for o in out], [o[1] for o in out]
+        return (merge_shards(parts) if merge else parts), stats
+
+    def upload(self, tis, numofchars):
+        self._collective(lambda r, e: e.upload(tis, numofchars))
+
+    def construct(self, prefixlength, tables=("suf", "lcp", "bwt")):
+        return self._collective(lambda r, e: e.construct(prefixlength, tables))
+
+    def download(self, merge=True):
+        parts = self._collective(lambda r, e: e.download())
+        return merge_shards(parts) if merge else parts

@@ -8,7 +8,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "comm.cuh"
 
 void radix_sort_init();
 void widen_isa(esa_ctx *ctx);
@@ -123,12 +123,26 @@ struct FullCtx : esa_ctx
   CtxExtra x;
 };
 
-size_t arena_estimate(u64 n)
+size_t arena_estimate(u64 n, int nranks)
 {
   const u64 N = n + 1;
-  // tis 1 + sa 4 + isa 4 + bck worst case 5 + doubling regions X and Y 32 + sort scratch and tile summaries ~2
-  return (size_t) (48 * N) + ((size_t) 256 << 20);
+  if (nranks <= 1)
+  {
+    // tis 1 + sa 4 + isa 4 + bck worst case 5 + doubling regions X and Y 32 + sort scratch and tile summaries ~2
+    return (size_t) (48 * N) + ((size_t) 256 << 20);
+  }
+  // sharded: replicated text 1 + packed text 0.4 + dense rank array 4 + bck (with all-reduce scratch) 2.5, plus the
+  // per-range share of everything else with head room for uneven ranges (ESA_SHARD_SLACK percent, default 60)
+  u64 slack = 60;
+  if (const char *e = getenv("ESA_SHARD_SLACK"))
+  {
+    slack = (u64) atoi(e);
+  }
+  const u64 share = N / (u64) nranks + 1;
+  return (size_t) (8 * N) + (size_t) (56 * share * (100 + slack) / 100) + ((size_t) 256 << 20);
 }
+
+bool is_sharded(const esa_ctx *ctx) { return ctx->comm != nullptr && ctx->comm->nranks > 1; }
 
 void collect_kernel_stats(esa_ctx *ctx, esa_stats *st)
 {
@@ -168,7 +182,7 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
   }
   CUDA_CHECK(cudaSetDevice(ctx->device));
   ctx->uploaded = ctx->constructed = false;
-  ctx->arena.reserve(arena_estimate(n));
+  ctx->arena.reserve(arena_estimate(n, ctx->comm != nullptr ? ctx->comm->nranks : 1));
   ctx->arena.reset();
   const u64 padded = ((n + 15) & ~(u64) 15) + 64;
   ctx->d_tis = ctx->arena.alloc<u8>(padded);
@@ -221,9 +235,21 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   ctx->nllv = ctx->maxbranchdepth = ctx->longest = 0;
   ctx->prof.reset();
   ctx->prof.enabled = stats != nullptr;
+  if (ctx->comm != nullptr)
+  {
+    ctx->comm->bytes_sent = 0;
+  }
 
+  const bool sharded = is_sharded(ctx);
+  if (sharded && (demand & (ESA_STI1TAB | ESA_STITAB | ESA_SKPTAB)))
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "sti1/sti/skp need the whole inverse suffix array on one device: not available in a "
+                                "sharded build");
+  }
+  ctx->shard_first = 0;
+  ctx->shard_count = N;
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_a, s));
-  ctx->d_sa = ar.alloc<u32>(N + 64);
+  ctx->d_sa = sharded ? nullptr : ar.alloc<u32>(N + 64);
   ctx->d_isa = ar.alloc<u32>(N + 64);
   ctx->prefixlength = prefixlength;
   ctx->demand = demand;
@@ -242,14 +268,21 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   {
     pack_text(ctx);  // 2-bit text + special mask for the random suffix-start accesses of lcp and bwt
   }
-  if (want_lcp && ctx->lcp_mode != 2)
+  if (want_lcp && ctx->lcp_mode != 2 && !sharded)
   {
     ctx->d_hround = ar.alloc<u8>(N + 64);
     ESA_LAUNCH(ctx, ESA_K_MEMOP, (double) N, CUDA_CHECK(cudaMemsetAsync(ctx->d_hround, 0, N + 64, s)));
   }
   const size_t scratch_mark = ar.mark();
   SortOutcome so;
-  suffix_sort(ctx, prefixlength, want_bck, &so, scratch_mark);
+  if (sharded)
+  {
+    ar.high = ar.capacity;
+    suffix_sort_sharded(ctx, ctx->comm, prefixlength, want_bck, want_lcp, &so);
+  } else
+  {
+    suffix_sort(ctx, prefixlength, want_bck, &so, scratch_mark);
+  }
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_b, s));
   ar.rewind(scratch_mark);  // everything the sorter carved is dead now
   // lcp path: direct comparison in suffix-array order unless the deep groups are so large that the work bound
@@ -258,7 +291,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   bool use_plcp = false;
   if (want_lcp)
   {
-    use_plcp = ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N);
+    use_plcp = !sharded && (ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N));
   }
   if (use_plcp)
   {
@@ -269,9 +302,47 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   if (use_plcp)
   {
     finalize_tables(ctx, demand, ctx->d_plcpv);
+  } else if (!sharded)
+  {
+    finalize_tables_direct(ctx, demand, so.h0, N, 0, 0);
   } else
   {
-    finalize_tables_direct(ctx, demand, so.h0);
+    // halo: the suffix in front of my range is the last entry of the nearest non-empty range before mine
+    esa_comm *comm = ctx->comm;
+    u64 mine[2] = {ctx->shard_count, 0}, all[2 * ESA_MAX_RANKS];
+    if (ctx->shard_count > 0)
+    {
+      u32 last = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&last, ctx->d_sa + ctx->shard_count - 1, sizeof last, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      mine[1] = last;
+    }
+    comm_exchange_host_u64(ctx, comm, mine, 2, all);
+    u32 halo = 0;
+    for (int r = 0; r < comm->rank; r++)
+    {
+      if (all[2 * r] > 0)
+      {
+        halo = (u32) all[2 * r + 1];
+      }
+    }
+    if (ctx->shard_count > 0)
+    {
+      finalize_tables_direct(ctx, demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
+    } else
+    {
+      ctx->d_suf64 = (demand & ESA_SUFTAB) ? ar.alloc<u64>(4) : nullptr;
+      ctx->d_bwt = (demand & ESA_BWTTAB) ? ar.alloc<u8>(4) : nullptr;
+      ctx->d_lcp = want_lcp ? ar.alloc<u8>(4) : nullptr;
+    }
+    // scalars of the whole table
+    u64 sc[2] = {ctx->maxbranchdepth, ctx->longest};
+    comm_exchange_host_u64(ctx, comm, sc, 2, all);
+    for (int r = 0; r < comm->nranks; r++)
+    {
+      ctx->maxbranchdepth = std::max(ctx->maxbranchdepth, all[2 * r]);
+      ctx->longest = std::max(ctx->longest, all[2 * r + 1]);
+    }
   }
   if (demand & ESA_STI1TAB)
   {
@@ -302,6 +373,9 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     stats->active_sum = so.active_sum;
     stats->active_first = so.active_first;
     stats->device_bytes_peak = ar.peak;
+    stats->shard_first = ctx->shard_first;
+    stats->shard_count = ctx->shard_count;
+    stats->comm_bytes_sent = ctx->comm != nullptr ? ctx->comm->bytes_sent : 0;
     collect_kernel_stats(ctx, stats);
     stats->ms_doubling = 0;
   }
@@ -325,9 +399,11 @@ u64 do_download(FullCtx *ctx, esa_result *out)
   }
   CUDA_CHECK(cudaSetDevice(ctx->device));
   memset(out, 0, sizeof *out);
-  const u64 N = ctx->n + 1;
+  const u64 N = ctx->shard_count;  // the whole table on one GPU, this rank's range in a sharded build
   u64 bytes = 0;
   out->n = ctx->n;
+  out->shard_first = ctx->shard_first;
+  out->shard_count = ctx->shard_count;
   out->numofcodes = ctx->numofcodes;
   out->nllv = ctx->nllv;
   out->maxbranchdepth = ctx->maxbranchdepth;
@@ -443,6 +519,8 @@ void esa_shutdown(esa_ctx *c)
   FullCtx *ctx = static_cast<FullCtx *>(c);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  comm_destroy(ctx->comm);
+  ctx->comm = nullptr;
   ctx->arena.release();
   ctx->prof.destroy();
   ctx->x.pool.destroy();
@@ -490,7 +568,12 @@ int esa_construct(esa_ctx *c, uint32_t prefixlength, uint32_t demand, esa_stats 
     return ESA_ERR_ARGUMENT;
   }
   FullCtx *ctx = static_cast<FullCtx *>(c);
-  return guarded(errbuf, errlen, [&]() { do_construct(ctx, prefixlength, demand, stats); });
+  const int rc = guarded(errbuf, errlen, [&]() { do_construct(ctx, prefixlength, demand, stats); });
+  if (rc != ESA_OK && ctx->comm != nullptr && ctx->comm->group != nullptr)
+  {
+    esa_group_abort(ctx->comm->group);  // the other ranks must not wait for this one forever
+  }
+  return rc;
 }
 
 int esa_download(esa_ctx *c, esa_result *out, char *errbuf, size_t errlen)
@@ -524,7 +607,17 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
     CUDA_CHECK(cudaSetDevice(ctx->device));
     CUDA_CHECK(cudaEventRecord(ctx->x.ev_e, s));
     do_upload(ctx, tis, n, numofchars);
-    do_construct(ctx, prefixlength, demand, stats);  // records ev_a .. ev_d, synchronises
+    try
+    {
+      do_construct(ctx, prefixlength, demand, stats);  // records ev_a .. ev_d, synchronises
+    } catch (...)
+    {
+      if (ctx->comm != nullptr && ctx->comm->group != nullptr)
+      {
+        esa_group_abort(ctx->comm->group);
+      }
+      throw;
+    }
     const u64 d2h = do_download(ctx, out);
     if (stats != nullptr)
     {
@@ -579,6 +672,10 @@ int esa_check(esa_ctx *c, char *errbuf, size_t errlen)
     {
       esa_throw(ESA_ERR_STATE, "esa_check called before esa_construct");
     }
+    if (is_sharded(ctx))
+    {
+      esa_throw(ESA_ERR_STATE, "esa_check needs the whole table on one device: not available on a sharded context");
+    }
     CUDA_CHECK(cudaSetDevice(ctx->device));
     bad = run_checks(ctx, msg);
   });
@@ -592,6 +689,70 @@ int esa_check(esa_ctx *c, char *errbuf, size_t errlen)
     return ESA_ERR_CHECK;
   }
   return ESA_OK;
+}
+
+int esa_comm_unique_id(uint8_t id[ESA_COMM_ID_BYTES], char *errbuf, size_t errlen)
+{
+  if (id == nullptr)
+  {
+    set_err(errbuf, errlen, "id is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  return guarded(errbuf, errlen, [&]() { comm_nccl_unique_id(id); });
+}
+
+int esa_comm_attach_nccl(esa_ctx *c, const uint8_t id[ESA_COMM_ID_BYTES], int nranks, int rank, char *errbuf,
+                         size_t errlen)
+{
+  if (c == nullptr || id == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx or id is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  return guarded(errbuf, errlen, [&]() {
+    comm_destroy(c->comm);
+    c->comm = nullptr;
+    c->uploaded = c->constructed = false;
+    c->comm = comm_nccl_attach(c, id, nranks, rank);
+  });
+}
+
+int esa_comm_attach_group(esa_ctx *c, esa_group *group, int rank, char *errbuf, size_t errlen)
+{
+  if (c == nullptr || group == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx or group is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  return guarded(errbuf, errlen, [&]() {
+    comm_destroy(c->comm);
+    c->comm = nullptr;
+    c->uploaded = c->constructed = false;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    // ranks on other devices are read with peer copies and, for the small reductions, direct loads
+    int count = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&count));
+    for (int d = 0; d < count; d++)
+    {
+      int can = 0;
+      if (d != c->device && cudaDeviceCanAccessPeer(&can, c->device, d) == cudaSuccess && can)
+      {
+        cudaDeviceEnablePeerAccess(d, 0);
+      }
+    }
+    cudaGetLastError();  // "already enabled" is fine
+    c->comm = comm_group_attach(c, group, rank);
+  });
+}
+
+void esa_comm_detach(esa_ctx *c)
+{
+  if (c != nullptr)
+  {
+    comm_destroy(c->comm);
+    c->comm = nullptr;
+    c->uploaded = c->constructed = false;
+  }
 }
 
 int esa_debug_radix_sort(esa_ctx *c, int key_bytes, void *keys, uint32_t *vals, uint64_t n, uint32_t begin_bit,

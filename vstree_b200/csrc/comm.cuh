@@ -1,0 +1,68 @@
+// comm.cuh -- the exchange steps of the sharded build: one rank per GPU, collectives ordered on the rank's compute
+// stream.
+//
+// The reference has no distributed code at all.  The sharded suffix sorter needs
+//   * small exchanges of counts (host values of every rank),
+//   * one all-to-all of (key, position) pairs after the splitter pass,
+//   * per doubling round one all-to-all of rank requests and one of the answers,
+//   * all-reduces of the bucket table pieces, a gather of the special-initial suffixes to the last rank and a
+//     one-element halo between neighbouring shards.
+// Two transports implement them:
+//   NCCL   one PROCESS per GPU (torchrun / MPI style launch); libnccl.so.2 is resolved with dlopen at attach time so
+//          that the single-GPU library has no link-time dependency on it.  Grouped ncclSend/ncclRecv over NVLink.
+//   group  one THREAD per rank inside one process (the mkvtree host driver with several GPUs, and the tests, which
+//          run several ranks on ONE device): peers publish their buffers in a shared table and every rank pulls its
+//          part with cudaMemcpyAsync (peer-to-peer over NVLink when the ranks sit on different devices).
+#pragma once
+
+#include "common.cuh"
+
+constexpr int ESA_MAX_RANKS = 64;
+
+// in-process group (transport "group")
+struct esa_group
+{
+  int nranks = 0;
+  void *sync = nullptr;             // abortable barrier state (comm.cu)
+  struct Slot
+  {
+    const void *ptr = nullptr;      // published device buffer
+    const u64 *off = nullptr;       // published host offset/count tables (nranks entries)
+    const u64 *cnt = nullptr;
+    int device = -1;
+    std::vector<u64> host;          // published host values
+  } slot[ESA_MAX_RANKS];
+  volatile int failed = 0;          // a rank hit an error: everybody bails out at the next barrier
+};
+
+struct esa_comm
+{
+  int rank = 0;
+  int nranks = 1;
+  void *nccl = nullptr;       // ncclComm_t when the transport is NCCL
+  esa_group *group = nullptr; // else the in-process group
+  double ms_comm = 0;         // host-measured time spent inside collectives (includes waiting for the slowest rank)
+  u64 bytes_sent = 0;         // payload this rank sent to OTHER ranks
+};
+
+// transport setup (comm.cu)
+void comm_nccl_unique_id(u8 id[ESA_COMM_ID_BYTES]);
+esa_comm *comm_nccl_attach(esa_ctx *ctx, const u8 id[ESA_COMM_ID_BYTES], int nranks, int rank);
+esa_comm *comm_group_attach(esa_ctx *ctx, esa_group *g, int rank);
+void comm_destroy(esa_comm *comm);
+
+// ---- collectives; every rank of the communicator must call them in the same order ----
+// every rank learns `count` 64-bit host values of every rank: all[r*count + i]; synchronises the stream
+void comm_exchange_host_u64(esa_ctx *ctx, esa_comm *comm, const u64 *mine, size_t count, u64 *all);
+// in-place sum / max over ranks of `count` 64-bit words in device memory (`d_tmp`: count words of scratch)
+void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, size_t count, bool max_instead_of_sum);
+// variable all-to-all of 32-bit words: counts/offsets are host arrays of nranks entries (in words);
+// recv_cnt[r] must equal what rank r sends here
+void comm_alltoallv_u32(esa_ctx *ctx, esa_comm *comm, const u32 *d_send, const u64 *send_off, const u64 *send_cnt,
+                        u32 *d_recv, const u64 *recv_off, const u64 *recv_cnt);
+// variable all-gather of 32-bit words: rank r contributes cnt[r] words, placed at off[r] of d_recv on every rank
+void comm_allgatherv_u32(esa_ctx *ctx, esa_comm *comm, const u32 *d_send, u32 *d_recv, const u64 *off,
+                         const u64 *cnt);
+// gather to one rank (root): rank r sends cnt[r] words, root places them at off[r]
+void comm_gatherv_u32(esa_ctx *ctx, esa_comm *comm, int root, const u32 *d_send, u32 *d_recv, const u64 *off,
+                      const u64 *cnt);

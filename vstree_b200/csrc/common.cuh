@@ -66,6 +66,7 @@ struct Arena
     release();
     CUDA_CHECK(cudaMalloc((void **) &base, bytes));
     capacity = bytes;
+    high = capacity;
   }
   void release()
   {
@@ -74,24 +75,46 @@ struct Arena
       cudaFree(base);
     }
     base = nullptr;
-    capacity = top = 0;
+    capacity = top = high = 0;
   }
-  void reset() { top = 0; }
+  void reset()
+  {
+    top = 0;
+    high = capacity;
+  }
+  // second bump pointer from the high end: tables whose size is only known in the middle of a build (a shard of
+  // the suffix array after the exchange) but that must survive the rewinds of the scratch region
+  size_t high = 0;
+  template <typename T> T *alloc_high(size_t count)
+  {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t) 255;
+    if (high < bytes || high - bytes < top)
+    {
+      esa_throw(ESA_ERR_MEMORY, "device arena exhausted (persistent side): need %zu bytes, %zu free", bytes,
+                high > top ? high - top : (size_t) 0);
+    }
+    high -= bytes;
+    if (capacity - high + top > peak)
+    {
+      peak = capacity - high + top;
+    }
+    return (T *) (base + high);
+  }
   size_t mark() const { return top; }
   void rewind(size_t m) { top = m; }
   template <typename T> T *alloc(size_t count)
   {
     size_t bytes = (count * sizeof(T) + 255) & ~(size_t) 255;
-    if (top + bytes > capacity)
+    if (top + bytes > high)
     {
-      esa_throw(ESA_ERR_MEMORY, "device arena exhausted: need %zu more bytes, capacity %zu", top + bytes - capacity,
+      esa_throw(ESA_ERR_MEMORY, "device arena exhausted: need %zu more bytes, capacity %zu", top + bytes - high,
                 capacity);
     }
     T *p = (T *) (base + top);
     top += bytes;
-    if (top > peak)
+    if (top + (capacity - high) > peak)
     {
-      peak = top;
+      peak = top + (capacity - high);
     }
     return p;
   }
@@ -139,6 +162,7 @@ struct KernelProfiler
   }
 };
 
+struct esa_comm;
 struct esa_ctx
 {
   int device = -1;
@@ -176,7 +200,11 @@ struct esa_ctx
   u64 *d_skp = nullptr;    // [N]
   u32 *d_plcpv = nullptr;  // [N] V[i] = i + PLCP[i]
   u64 nllv = 0, maxbranchdepth = 0, longest = 0;
+  // sharded build: this rank holds suffix-array entries [shard_first, shard_first + shard_count) in d_sa, d_suf64,
+  // d_lcp, d_bwt, d_hround (all indexed from 0); one GPU: [0, n+1)
+  u64 shard_first = 0, shard_count = 0;
   size_t arena_after_upload = 0;
+  struct esa_comm *comm = nullptr;  // attached communicator (sharded builds), see comm.cuh
 
   // small pinned scratch for scalar read-backs
   u64 *h_scalars = nullptr;  // 64 words
@@ -263,6 +291,10 @@ struct SortOutcome
   u64 num_sorted;   // suffixes that went through the sort (N - specials - 1)
 };
 void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *outcome, size_t scratch_mark);
+// sharded variant (one rank of a communicator); sets ctx->d_sa / d_hround (shard-local, arena high side),
+// ctx->shard_first / shard_count, the replicated ctx->d_isa and ctx->d_bck
+void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
+                         SortOutcome *outcome);
 
 // lcp.cu: V[i] = i + PLCP[i] for all text positions (ctx->d_plcpv)
 void compute_plcp(esa_ctx *ctx, u32 *d_v);
@@ -270,6 +302,6 @@ void compute_plcp(esa_ctx *ctx, u32 *d_v);
 // derive.cu
 void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v);
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 int run_checks(esa_ctx *ctx, std::string &msg);

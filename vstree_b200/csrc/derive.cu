@@ -311,7 +311,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
     ctx->d_llv = ar.alloc<u64>(2 * ctx->nllv);
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, (double) N + 24.0 * ctx->nllv,
                (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, nullptr, ctx->d_lcp, tile_large,
-                                                              ctx->nllv, ctx->d_llv)));
+                                                              ctx->nllv, ctx->d_llv, 0)));
   }
 }
 

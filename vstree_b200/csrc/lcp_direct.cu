@@ -58,8 +58,11 @@ __global__ void __launch_bounds__(FN_THREADS)
 finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa,
                        const u8 *__restrict__ hround, u32 h0, bool want_lcp, u8 *__restrict__ lcp8,
                        u32 *__restrict__ lcpfull, u8 *__restrict__ bwt, u64 *__restrict__ suf64,
-                       u32 *__restrict__ tile_large, unsigned long long *__restrict__ scalars)
+                       u32 *__restrict__ tile_large, unsigned long long *__restrict__ scalars, u64 index_base,
+                       u32 halo_prev)
 {
+  // index_base: global suffix-array index of local entry 0 (0 on one GPU); halo_prev: the suffix in front of the
+  // shard (last entry of the previous shard), used for the lcp of local entry 0
   __shared__ u32 red[2][FN_THREADS / 32];
   const u64 tile_base = (u64) blockIdx.x * FN_TILE;
   u32 nlarge = 0, mx = 0;
@@ -74,7 +77,7 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
     u32 s[5];  // s[0] = sa[r0-1], s[1..4] = sa[r0..r0+3]
     u32 hr[4] = {0, 0, 0, 0};
     const int cnt = (int) min((u64) 4, N - r0);
-    s[0] = r0 > 0 ? sa[r0 - 1] : 0u;
+    s[0] = r0 > 0 ? sa[r0 - 1] : halo_prev;
     if (cnt == 4)
     {
       const uint4 s4 = *reinterpret_cast<const uint4 *>(sa + r0);
@@ -117,7 +120,7 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
         {
           bb[q] = s[q + 1] > 0 ? (u8) pr[q + 1].before : (u8) ESA_UNDEFBWTCHAR;
         }
-        if (want_lcp && q < cnt && r0 + q > 0)
+        if (want_lcp && q < cnt && index_base + r0 + q > 0)
         {
           const u32 lb = hr[q] ? (h0 << (hr[q] - 1)) : 0u;
           // pairs split by a doubling round agree on lb symbols: start there (at most lb/WINDOW + 1 steps)
@@ -135,7 +138,7 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
     {
       if (q < cnt && s[q + 1] == 0)
       {
-        scalars[1] = r0 + q;
+        scalars[1] = index_base + r0 + q;
       }
       if (want_lcp && q < cnt)
       {
@@ -226,9 +229,10 @@ void pack_text(esa_ctx *ctx)
 }
 
 // lcp (when demanded) by direct comparison; fills d_lcp, d_llv, d_bwt, d_suf64, maxbranchdepth, longest, nllv
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0)
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev)
 {
-  const u64 N = ctx->n + 1;
+  // count entries of ctx->d_sa (the whole table on one GPU, this rank's shard otherwise)
+  const u64 N = count;
   cudaStream_t s = ctx->stream;
   Arena &ar = ctx->arena;
   const bool want_lcp = (demand & ESA_LCPTAB) != 0;
@@ -259,14 +263,14 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0)
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextPacked2><<<tiles, FN_THREADS, 0, s>>>(
                    text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, h0, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
-                   ctx->d_suf64, tile_large, d_scalars)));
+                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
   } else
   {
     TextBytes text{ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextBytes><<<tiles, FN_THREADS, 0, s>>>(
                    text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, h0, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
-                   ctx->d_suf64, tile_large, d_scalars)));
+                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
   }
   if (want_lcp)
   {
@@ -282,6 +286,6 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0)
     ctx->d_llv = ar.alloc<u64>(2 * ctx->nllv);
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, (double) N + 20.0 * ctx->nllv,
                (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, nullptr, lcpfull, ctx->d_lcp, tile_large,
-                                                              ctx->nllv, ctx->d_llv)));
+                                                              ctx->nllv, ctx->d_llv, index_base)));
   }
 }

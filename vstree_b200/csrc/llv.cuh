@@ -38,7 +38,8 @@ large_scan_kernel(u32 *tile_large, u32 ntiles, unsigned long long *scalars)
 // plcp array (v[sa[r]] - sa[r]) or from lcpfull[r] (direct path; only entries with lcp8 == 255 are defined).
 static __global__ void __launch_bounds__(FN_THREADS)
 llv_emit_kernel(u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v, const u32 *__restrict__ lcpfull,
-                const u8 *__restrict__ lcp8, const u32 *__restrict__ tile_offset, u64 nllv, u64 *__restrict__ llv)
+                const u8 *__restrict__ lcp8, const u32 *__restrict__ tile_offset, u64 nllv, u64 *__restrict__ llv,
+                u64 index_base /* global index of local entry 0 */)
 {
   __shared__ __align__(8) u8 sflag[FN_TILE];
   __shared__ u32 scratch[FN_THREADS / 32 + 1];
@@ -76,7 +77,7 @@ llv_emit_kernel(u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v, co
       {
         value = lcpfull[r];
       }
-      llv[2 * (first + o)] = r;
+      llv[2 * (first + o)] = index_base + r;
       llv[2 * (first + o) + 1] = value;
       o++;
     }

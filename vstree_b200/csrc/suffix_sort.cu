@@ -30,13 +30,14 @@ constexpr u32 NONE32 = 0xffffffffu;
 // [5] carry (unused) [6] longest ...
 
 __global__ void __launch_bounds__(KS_THREADS)
-classify_count_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, u32 *__restrict__ tile_full,
-                      u32 *__restrict__ tile_side, u32 *__restrict__ tile_spec)
+classify_count_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, KmerParams kp,
+                      u32 *__restrict__ tile_full, u32 *__restrict__ tile_side, u32 *__restrict__ tile_spec)
 {
+  // positions [p_begin, p_end) are classified: the whole text [0, n+1) on one GPU, a slice of it when sharded
   __shared__ __align__(16) u8 stext[KS_TILE + KS_HALO];
   __shared__ u32 red[3][KS_THREADS / 32];
-  const u64 tile_base = (u64) blockIdx.x * KS_TILE;
-  const u64 N = n + 1;
+  const u64 tile_base = p_begin + (u64) blockIdx.x * KS_TILE;
+  const u64 N = p_end;
   ks_load_tile(tis, n, tile_base, stext);
   __syncthreads();
   u32 code[KS_ITEMS], dist[KS_ITEMS];
@@ -122,11 +123,12 @@ tile_exclusive_sum_kernel(u32 *a0, u32 *a1, u32 *a2, u32 ntiles, u64 *scalars, i
 }
 
 __global__ void __launch_bounds__(KS_THREADS)
-classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32 *__restrict__ tile_full,
+classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, KmerParams kp,
+                     const u32 *__restrict__ tile_full,
                      const u32 *__restrict__ tile_side, const u32 *__restrict__ tile_spec,
                      const u64 *__restrict__ scalars, u32 *__restrict__ main_key, u32 *__restrict__ main_pos,
                      u32 *__restrict__ side_key, u32 *__restrict__ side_pos, u32 *__restrict__ side_dj,
-                     u32 *__restrict__ sa, u32 *__restrict__ rank)
+                     u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ spec_list)
 {
   __shared__ __align__(16) u8 stext[KS_TILE + KS_HALO];
   // staging for coalesced output; index e is stored at e + e/32 so that the 16-strided per-thread writes hit
@@ -134,8 +136,8 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32
   __shared__ u32 skey[KS_TILE + KS_TILE / 32];
   __shared__ u32 spos[KS_TILE + KS_TILE / 32];
   __shared__ u32 scratch[KS_THREADS / 32 + 1];
-  const u64 tile_base = (u64) blockIdx.x * KS_TILE;
-  const u64 N = n + 1;
+  const u64 tile_base = p_begin + (u64) blockIdx.x * KS_TILE;
+  const u64 N = p_end;
   ks_load_tile(tis, n, tile_base, stext);
   __syncthreads();
   u32 code[KS_ITEMS], dist[KS_ITEMS];
@@ -176,9 +178,15 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, KmerParams kp, const u32
     {
       if (dist[i] == 0)
       {
-        const u64 slot = M + off_spec + rp;  // tail of the table, position order
-        sa[slot] = (u32) p;
-        rank[p] = (u32) slot;
+        if (spec_list != nullptr)
+        {
+          spec_list[off_spec + rp] = (u32) p;  // sharded build: the tail is assembled after the exchange
+        } else
+        {
+          const u64 slot = M + off_spec + rp;  // tail of the table, position order
+          sa[slot] = (u32) p;
+          rank[p] = (u32) slot;
+        }
         rp++;
       } else if (dist[i] < kp.h)
       {
@@ -274,7 +282,8 @@ constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
 // flag bit0 = group head, bit1 = active (member of a group of size > 1).
 template <typename KeyT, bool FIRST>
 __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m,
-                                         u64 tile_base, KeyT *skey /* [RG_TILE+2] */, u32 *sslot, u8 *sflag)
+                                         u64 tile_base, KeyT *skey /* [RG_TILE+2] */, u32 *sslot, u8 *sflag,
+                                         u32 slot_base)
 {
 #pragma unroll
   for (int j = 0; j < RG_ITEMS; j++)
@@ -284,7 +293,7 @@ __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u3
     if (t < m)
     {
       skey[l + 1] = keys[t];
-      sslot[l] = FIRST ? (u32) t : slots[t];
+      sslot[l] = FIRST ? (u32) t + slot_base : slots[t];  // slots are global suffix-array indices
     }
   }
   if (threadIdx.x == 0)
@@ -325,14 +334,14 @@ __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u3
 template <typename KeyT, bool FIRST>
 __global__ void __launch_bounds__(RG_THREADS)
 regroup_summary_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m,
-                       u32 *__restrict__ tile_maxrank, u32 *__restrict__ tile_active)
+                       u32 *__restrict__ tile_maxrank, u32 *__restrict__ tile_active, u32 slot_base)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
   __shared__ __align__(8) u8 sflag[RG_TILE];
   __shared__ u32 red[2][RG_THREADS / 32];
   const u64 tile_base = (u64) blockIdx.x * RG_TILE;
-  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag);
+  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base);
   u32 mx = 0, cnt = 0;
 #pragma unroll
   for (int j = 0; j < RG_ITEMS; j++)
@@ -410,7 +419,8 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
                      const u32 *__restrict__ tile_maxrank, const u32 *__restrict__ tile_active, u32 *__restrict__ sa,
                      u32 *__restrict__ rank, u64 *__restrict__ next_key, u32 *__restrict__ next_pos,
                      u32 *__restrict__ next_slots, u32 rank_shift, u8 *__restrict__ hround, u32 round,
-                     u32 *__restrict__ rank_out /* if set: rank_out[t] = rank instead of the scatter rank[pos] */)
+                     u32 *__restrict__ rank_out /* if set: rank_out[t] = rank instead of the scatter rank[pos] */,
+                     u32 slot_base /* first global slot of this shard; sa and hround are shard-local arrays */)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
@@ -420,7 +430,7 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
   __shared__ u32 scratch[RG_THREADS / 32 + 1];
   __shared__ u32 sincl[RG_THREADS];
   const u64 tile_base = (u64) blockIdx.x * RG_TILE;
-  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag);
+  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base);
   // blocked phase: thread owns local items [tid*8, tid*8+8)
   const int b0 = threadIdx.x * RG_ITEMS;
   const u64 f8 = *reinterpret_cast<const u64 *>(sflag + b0);
@@ -469,7 +479,7 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
       const u32 p = pos[t], slot = sslot[l], r = srank[l], d = sdest[l];
       if (!FIRST)
       {
-        sa[slot] = p;  // FIRST: the sorted position buffer already is sa[0..m)
+        sa[slot - slot_base] = p;  // FIRST: the sorted position buffer already is sa[0..m)
       }
       if (rank_out != nullptr)
       {
@@ -490,7 +500,7 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
         // suffixes agree on the depth of the round (lcp lower bound for the direct lcp kernel)
         if ((u64) (skey[l + 1] >> rank_shift) == (u64) (skey[l] >> rank_shift))
         {
-          hround[slot] = (u8) round;
+          hround[slot - slot_base] = (u8) round;
         }
       }
     }
@@ -594,7 +604,8 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   const u32 ktiles = (u32) div_up_u64(N, KS_TILE);
   u32 *tile_full = ar.alloc<u32>(ktiles), *tile_side = ar.alloc<u32>(ktiles), *tile_spec = ar.alloc<u32>(ktiles);
   ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N,
-             (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, kp, tile_full, tile_side, tile_spec)));
+             (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side,
+                                                                   tile_spec)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0,
              (tile_exclusive_sum_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles, d_scalars,
                                                                      0)));
@@ -617,9 +628,9 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   void *sort_temp = ar.alloc<char>(temp_bytes);
 
   ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N + 8.0 * M + 8.0 * nspec,
-             (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, kp, tile_full, tile_side, tile_spec,
+             (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side, tile_spec,
                                                                   d_scalars, key_a, pos_a, side_key, side_pos, side_dj,
-                                                                  sa, rank)));
+                                                                  sa, rank, nullptr)));
   // side suffixes: stable sort by h0-j, written straight behind the full ones
   if (nside == 1)
   {
@@ -695,7 +706,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   u32 *tile_maxrank = ar.alloc<u32>(rtiles), *tile_active = ar.alloc<u32>(rtiles);
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
              (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
-                                                                                tile_active)));
+                                                                                tile_active, 0u)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0,
              (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
   u64 m = read_scalar(ctx, d_scalars, 4);
@@ -719,7 +730,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
              (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
                                                                               tile_active, sa, rank, dk_in, dp_in,
                                                                               slots_cur, rank_shift, nullptr, 0u,
-                                                                              part_rank)));
+                                                                              part_rank, 0u)));
   if (part_rank != nullptr)
   {
     scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
@@ -754,7 +765,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     rtiles = (u32) div_up_u64(m, RG_TILE);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
                (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                   tile_active)));
+                                                                                   tile_active, 0u)));
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
     const u64 m_next = read_scalar(ctx, d_scalars, 4);
@@ -764,7 +775,8 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
                                                                                  tile_active, sa, rank, ko, po,
                                                                                  slots_next, rank_shift,
                                                                                  ctx->d_hround, outcome->rounds,
-                                                                                 two_level ? part_rank : nullptr)));
+                                                                                 two_level ? part_rank : nullptr,
+                                                                                 0u)));
     if (two_level)
     {
       scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
@@ -782,5 +794,587 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     {
       esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
     }
+  }
+}
+
+// =========================================================================================================
+// Sharded build: rank g of G builds the suffix-array range that belongs to a contiguous
+// range of "bins" (the top 8 bits of the initial sort key, i.e. the first symbols of the suffix).
+//
+//   1. every rank classifies ITS SLICE of text positions (the text itself is replicated);
+//   2. splitter pass: per-bin counts, summed over the ranks, cut into G ranges of about equal size;
+//   3. all-to-all: (key, position) pairs travel to the owner of their bin; suffixes with a special inside the
+//      h0-prefix ("side" suffixes, few) are all-gathered so that their (h0-j, position) order can be established
+//      exactly as on one GPU; special-initial suffixes are gathered to the last rank (tail of the table);
+//   4. each rank sorts its range: 32-bit LSD sort, regroup, doubling rounds.  rank[] is a dense array by text
+//      position of which a rank only ever fills and reads the entries of the suffixes it owns; the doubling key
+//      rank[s+h] of a suffix owned elsewhere is fetched from its owner: requests are partitioned by owner (the
+//      owner of s+h follows from the replicated text), exchanged, answered by a gather, and returned.
+//   All per-rank work is O(N/G) except the text upload; the exchange volume is 8 bytes per suffix once plus 8 bytes per
+//   active suffix and round.
+#include "comm.cuh"
+
+namespace
+{
+
+constexpr u32 SPECIAL_KEY = 0xffffffffu;
+
+struct OwnerLut
+{
+  u8 owner[256];  // bin -> rank, non-decreasing
+  u32 shift;      // bin = key >> shift
+  u32 last;       // rank that holds the special-initial suffixes (G-1)
+};
+
+// initial sort key of the suffix at position q, recomputed from the text: the same value classify_emit_kernel
+// produced for q on whichever rank classified it (padded h-mer code << 1 | special-inside flag)
+__device__ __forceinline__ u32 initial_key_at(const u8 *__restrict__ tis, u64 q, const KmerParams &kp)
+{
+  u32 code = 0;
+  for (u32 i = 0; i < kp.h; i++)
+  {
+    const u32 a = tis[q + i];  // tis is padded with 255 behind position n
+    if (a >= ESA_WILDCARD)
+    {
+      if (i == 0)
+      {
+        return SPECIAL_KEY;
+      }
+      for (u32 j = i; j < kp.h; j++)
+      {
+        code = code * kp.sigma + (kp.sigma - 1);
+      }
+      return (code << 1) | 1u;
+    }
+    code = code * kp.sigma + a;
+  }
+  return code << 1;
+}
+
+__device__ __forceinline__ u32 owner_of_key(u32 key, const OwnerLut &lut)
+{
+  return key == SPECIAL_KEY ? lut.last : (u32) lut.owner[(key >> lut.shift) & 0xffu];
+}
+
+__global__ void bin_hist_kernel(const u32 *__restrict__ keys, u64 count, u32 shift, unsigned long long *__restrict__ hist)
+{
+  __shared__ u32 sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
+  {
+    atomicAdd(&sh[(keys[i] >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x] != 0)
+  {
+    atomicAdd(&hist[threadIdx.x], (unsigned long long) sh[threadIdx.x]);
+  }
+}
+
+// owner of every key of a list (side suffixes), with per-owner counts
+__global__ void key_owner_kernel(const u32 *__restrict__ keys, u64 count, OwnerLut lut, u32 *__restrict__ owner,
+                                 unsigned long long *__restrict__ owner_count)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    const u32 o = owner_of_key(keys[t], lut);
+    owner[t] = o;
+    atomicAdd(&owner_count[o], 1ull);
+  }
+}
+
+// special-initial suffixes: their final slots are the tail of the table, in position order
+__global__ void spec_tail_kernel(const u32 *__restrict__ spec, u64 count, u64 first_local, u32 slot_base,
+                                 u32 *__restrict__ sa, u32 *__restrict__ rank)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    const u32 p = spec[t];
+    sa[first_local + t] = p;
+    rank[p] = slot_base + (u32) (first_local + t);
+  }
+}
+
+// doubling, step 1: tag every active suffix with the owner of its h-successor (low key bits) and count per owner
+__global__ void __launch_bounds__(256)
+owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, const u8 *__restrict__ tis,
+                 KmerParams kp, OwnerLut lut, unsigned long long *__restrict__ owner_count)
+{
+  __shared__ u32 sh[ESA_MAX_RANKS];
+  if (threadIdx.x < ESA_MAX_RANKS)
+  {
+    sh[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m)
+  {
+    const u32 o = owner_of_key(initial_key_at(tis, (u64) pos[t] + h, kp), lut);
+    key[t] |= (u64) o;
+    atomicAdd(&sh[o], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < ESA_MAX_RANKS && sh[threadIdx.x] != 0)
+  {
+    atomicAdd(&owner_count[threadIdx.x], (unsigned long long) sh[threadIdx.x]);
+  }
+}
+
+// doubling, step 2 (owner side): answer[j] = rank of the suffix h symbols behind the requested one
+__global__ void serve_rank_kernel(const u32 *__restrict__ req_pos, u64 count, u64 h, const u32 *__restrict__ rank,
+                                  u32 *__restrict__ answer)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    answer[t] = rank[(u64) req_pos[t] + h];
+  }
+}
+
+// doubling, step 3: the answers replace the owner tag in the low key bits
+__global__ void merge_answer_kernel(u64 *__restrict__ key, const u32 *__restrict__ answer, u64 m, u32 rank_shift)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m)
+  {
+    key[t] = ((key[t] >> rank_shift) << rank_shift) | (u64) answer[t];
+  }
+}
+
+u32 grid_for(u64 count, u32 block) { return (u32) div_up_u64(count, block); }
+
+}  // namespace
+
+void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
+                         SortOutcome *outcome)
+{
+  const int G = comm->nranks, me = comm->rank;
+  const u64 n = ctx->n, N = n + 1;
+  const u32 sigma = ctx->sigma;
+  cudaStream_t s = ctx->stream;
+  Arena &ar = ctx->arena;
+  const u32 h0 = choose_h0(sigma);
+  const KmerParams kp = make_kmer_params(sigma, h0);
+  const u32 key_bits = bits_for(((u64) kp.all_pad << 1) | 1);
+  u32 *rank = ctx->d_isa;  // dense by text position; only the entries of suffixes this rank owns are defined
+  u64 all[ESA_MAX_RANKS * (ESA_MAX_RANKS + 4)];
+  u64 mine[ESA_MAX_RANKS + 4];
+
+  u64 *d_scalars = ar.alloc<u64>(16);
+  unsigned long long *d_counts = (unsigned long long *) ar.alloc<u64>(256);
+  u64 *d_counts_tmp = ar.alloc<u64>(256);
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_scalars, 0, 16 * sizeof(u64), s)));
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 256 * sizeof(u64), s)));
+
+  // ---- 1. classification of my slice of text positions (slices are KS_TILE aligned for the 16-byte loads)
+  const u64 slice = div_up_u64(div_up_u64(N, (u64) G), KS_TILE) * KS_TILE;
+  const u64 p_begin = min(N, (u64) me * slice), p_end = min(N, (u64) (me + 1) * slice);
+  const u32 ktiles = (u32) div_up_u64(p_end - p_begin, KS_TILE);
+  u32 *tile_full = ar.alloc<u32>(ktiles + 1), *tile_side = ar.alloc<u32>(ktiles + 1), *tile_spec = ar.alloc<u32>(ktiles + 1);
+  u64 nfull = 0, nside = 0, nspec = 0;
+  if (ktiles > 0)
+  {
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin),
+               (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
+                                                                     tile_side, tile_spec)));
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+               (tile_exclusive_sum_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
+                                                                       d_scalars, 0)));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
+  }
+  if (nfull + nside + nspec != p_end - p_begin)
+  {
+    esa_throw(ESA_ERR_CUDA, "classification lost suffixes on rank %d", me);
+  }
+  u32 *key_l = ar.alloc<u32>(nfull + 64), *pos_l = ar.alloc<u32>(nfull + 64);
+  u32 *key_t = ar.alloc<u32>(nfull + 64), *pos_t = ar.alloc<u32>(nfull + 64);
+  u32 *lside_key = ar.alloc<u32>(nside + 1), *lside_pos = ar.alloc<u32>(nside + 1), *lside_dj = ar.alloc<u32>(nside + 1);
+  u32 *lspec = ar.alloc<u32>(nspec + 1);
+  if (ktiles > 0)
+  {
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin) + 8.0 * (nfull + nside) + 4.0 * nspec,
+               (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
+                                                                    tile_side, tile_spec, d_scalars, key_l, pos_l,
+                                                                    lside_key, lside_pos, lside_dj, nullptr, nullptr,
+                                                                    lspec)));
+  }
+
+  // ---- 2. splitter pass: bins of the top 8 key bits
+  OwnerLut lut;
+  lut.shift = key_bits > 8 ? key_bits - 8 : 0;
+  lut.last = (u32) (G - 1);
+  if (nfull > 0)
+  {
+    const u32 grid = (u32) min((u64) ctx->num_sms * 8, div_up_u64(nfull, 256));
+    ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 4.0 * nfull,
+               (bin_hist_kernel<<<grid, 256, 0, s>>>(key_l, nfull, lut.shift, d_counts)));
+  }
+  u64 local_hist[256];
+  CUDA_CHECK(cudaMemcpyAsync(local_hist, d_counts, sizeof local_hist, cudaMemcpyDeviceToHost, s));
+  comm_allreduce_u64(ctx, comm, (u64 *) d_counts, d_counts_tmp, 256, false);
+  u64 global_hist[256];
+  CUDA_CHECK(cudaMemcpyAsync(global_hist, d_counts, sizeof global_hist, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  {
+    u64 total = 0, acc = 0;
+    for (int b = 0; b < 256; b++)
+    {
+      total += global_hist[b];
+    }
+    int r = 0;
+    for (int b = 0; b < 256; b++)
+    {
+      // a bin goes to the rank in whose quota its midpoint falls; owners never decrease
+      const u64 midpoint = acc + global_hist[b] / 2;
+      while (r + 1 < G && total > 0 && midpoint * (u64) G >= (u64) (r + 1) * total)
+      {
+        r++;
+      }
+      lut.owner[b] = (u8) r;
+      acc += global_hist[b];
+    }
+  }
+
+  // ---- 3a. counts of every rank: full per destination, side, special
+  u64 send_cnt[ESA_MAX_RANKS] = {0}, send_off[ESA_MAX_RANKS], recv_cnt[ESA_MAX_RANKS], recv_off[ESA_MAX_RANKS];
+  for (int b = 0; b < 256; b++)
+  {
+    send_cnt[lut.owner[b]] += local_hist[b];
+  }
+  for (int r = 0; r < G; r++)
+  {
+    mine[r] = send_cnt[r];
+  }
+  mine[G] = nside;
+  mine[G + 1] = nspec;
+  const size_t row = (size_t) G + 2;
+  comm_exchange_host_u64(ctx, comm, mine, row, all);
+  u64 side_cnt[ESA_MAX_RANKS], side_off[ESA_MAX_RANKS], spec_cnt[ESA_MAX_RANKS], spec_off[ESA_MAX_RANKS];
+  u64 nside_tot = 0, nspec_tot = 0, mfull = 0, off = 0;
+  for (int r = 0; r < G; r++)
+  {
+    send_off[r] = off;
+    off += send_cnt[r];
+    recv_cnt[r] = all[(size_t) r * row + me];
+    recv_off[r] = mfull;
+    mfull += recv_cnt[r];
+    side_cnt[r] = all[(size_t) r * row + G];
+    side_off[r] = nside_tot;
+    nside_tot += side_cnt[r];
+    spec_cnt[r] = all[(size_t) r * row + G + 1];
+    spec_off[r] = nspec_tot;
+    nspec_tot += spec_cnt[r];
+  }
+
+  // ---- 3b. side suffixes: all-gather (rank order = position order), stable sort by h0-j, keep mine
+  const size_t temp_bytes = max(max(radix_sort_temp_bytes(mfull + nside_tot + 64, 4), radix_sort_temp_bytes(mfull + nside_tot + 64, 8)),
+                                radix_sort_temp_bytes(nfull + 64, 4));
+  void *sort_temp = ar.alloc<char>(temp_bytes);
+  u32 *gs_key = ar.alloc<u32>(nside_tot + 1), *gs_pos = ar.alloc<u32>(nside_tot + 1), *gs_dj = ar.alloc<u32>(nside_tot + 1);
+  u32 *gs_tmp = ar.alloc<u32>(nside_tot + 1), *gs_key2 = ar.alloc<u32>(nside_tot + 1), *gs_pos2 = ar.alloc<u32>(nside_tot + 1);
+  u32 *gs_own = ar.alloc<u32>(nside_tot + 1);
+  u64 nside_mine = 0, side_first = 0;
+  u32 *my_side_key = gs_key, *my_side_pos = gs_pos;
+  u32 kdiv = 1;
+  u32 *bck_cnt = nullptr;
+  if (want_bck)
+  {
+    for (u32 i = prefixlength; i < h0; i++)
+    {
+      kdiv *= sigma;
+    }
+    bck_cnt = ar.alloc<u32>(ctx->numofcodes);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(bck_cnt, 0, ctx->numofcodes * sizeof(u32), s)));
+  }
+  if (nside_tot > 0)
+  {
+    comm_allgatherv_u32(ctx, comm, lside_key, gs_key, side_off, side_cnt);
+    comm_allgatherv_u32(ctx, comm, lside_pos, gs_pos, side_off, side_cnt);
+    comm_allgatherv_u32(ctx, comm, lside_dj, gs_dj, side_off, side_cnt);
+    if (want_bck)
+    {
+      ESA_LAUNCH(ctx, ESA_K_BCK, 8.0 * nside_tot,
+                 (side_bucket_count_kernel<<<grid_for(nside_tot, 256), 256, 0, s>>>(gs_key, gs_dj, nside_tot, h0,
+                                                                                     prefixlength, kdiv, bck_cnt)));
+    }
+    const u32 *sk = gs_key, *sp = gs_pos;
+    if (nside_tot > 1)
+    {
+      const int w = radix_sort_pairs_u32(ctx, gs_dj, gs_tmp, gs_pos, gs_pos2, nside_tot, 0, 8, sort_temp, temp_bytes);
+      const int w2 = radix_sort_pairs_u32(ctx, gs_dj, gs_tmp, gs_key, gs_key2, nside_tot, 0, 8, sort_temp, temp_bytes);
+      if (w != 1 || w2 != 1)
+      {
+        esa_throw(ESA_ERR_CUDA, "internal: side sort expected exactly one pass");
+      }
+      sk = gs_key2;
+      sp = gs_pos2;
+    }
+    // owner of every side suffix; then a stable partition by owner
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
+    ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 8.0 * nside_tot,
+               (key_owner_kernel<<<grid_for(nside_tot, 256), 256, 0, s>>>(sk, nside_tot, lut, gs_own, d_counts)));
+    u64 own_cnt[ESA_MAX_RANKS];
+    CUDA_CHECK(cudaMemcpyAsync(own_cnt, d_counts, sizeof own_cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int r = 0; r < me; r++)
+    {
+      side_first += own_cnt[r];
+    }
+    nside_mine = own_cnt[me];
+    if (nside_tot > 1)
+    {
+      // sk/sp live in gs_key2/gs_pos2 -> partitioned copies go back into gs_key/gs_pos
+      const int w = radix_sort_pairs_u32(ctx, gs_own, gs_tmp, const_cast<u32 *>(sp), gs_pos, nside_tot, 0, 8, sort_temp, temp_bytes);
+      const int w2 = radix_sort_pairs_u32(ctx, gs_own, gs_tmp, const_cast<u32 *>(sk), gs_key, nside_tot, 0, 8, sort_temp, temp_bytes);
+      if (w != 1 || w2 != 1)
+      {
+        esa_throw(ESA_ERR_CUDA, "internal: side partition expected exactly one pass");
+      }
+    }
+    my_side_key = gs_key + side_first;
+    my_side_pos = gs_pos + side_first;
+  }
+
+  // ---- 3c. all-to-all of the full suffixes: stable partition by bin, then one send per destination
+  const u64 M = mfull + nside_mine;  // suffixes of my range that take part in the sort
+  const u64 Mal = M + 64;
+  u32 *key_a = ar.alloc<u32>(Mal), *key_b = ar.alloc<u32>(Mal), *pos_a = ar.alloc<u32>(Mal), *pos_b = ar.alloc<u32>(Mal);
+  {
+    const u32 *ks = key_l, *ps = pos_l;
+    if (nfull > 1 && radix_sort_pairs_u32(ctx, key_l, key_t, pos_l, pos_t, nfull, lut.shift, key_bits, sort_temp, temp_bytes))
+    {
+      ks = key_t;
+      ps = pos_t;
+    }
+    comm_alltoallv_u32(ctx, comm, ks, send_off, send_cnt, key_a, recv_off, recv_cnt);
+    comm_alltoallv_u32(ctx, comm, ps, send_off, send_cnt, pos_a, recv_off, recv_cnt);
+  }
+  if (nside_mine > 0)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(key_a + mfull, my_side_key, nside_mine * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(pos_a + mfull, my_side_pos, nside_mine * 4, cudaMemcpyDeviceToDevice, s));
+  }
+
+  // ---- 3d. shape of the table: my range, the tail of special-initial suffixes on the last rank
+  mine[0] = M;
+  comm_exchange_host_u64(ctx, comm, mine, 1, all);
+  u64 slot_base64 = 0, Mtot = 0;
+  for (int r = 0; r < G; r++)
+  {
+    if (r < me)
+    {
+      slot_base64 += all[r];
+    }
+    Mtot += all[r];
+  }
+  if (Mtot + nspec_tot != N)
+  {
+    esa_throw(ESA_ERR_COMM, "exchange lost suffixes: %llu + %llu != %llu", (unsigned long long) Mtot,
+              (unsigned long long) nspec_tot, (unsigned long long) N);
+  }
+  const u32 slot_base = (u32) slot_base64;
+  const u64 shard_count = M + (me == G - 1 ? nspec_tot : 0);
+  ctx->shard_first = slot_base64;
+  ctx->shard_count = shard_count;
+  u32 *sa = ctx->d_sa = ar.alloc_high<u32>(shard_count + 64);
+  if (want_hround)
+  {
+    ctx->d_hround = ar.alloc_high<u8>(shard_count + 64);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, (double) shard_count, CUDA_CHECK(cudaMemsetAsync(ctx->d_hround, 0, shard_count + 64, s)));
+  }
+  if (nspec_tot > 0)
+  {
+    u32 *gspec = me == G - 1 ? ar.alloc<u32>(nspec_tot + 1) : nullptr;
+    comm_gatherv_u32(ctx, comm, G - 1, lspec, gspec, spec_off, spec_cnt);
+    if (me == G - 1)
+    {
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 12.0 * nspec_tot,
+                 (spec_tail_kernel<<<grid_for(nspec_tot, 256), 256, 0, s>>>(gspec, nspec_tot, M, slot_base, sa, rank)));
+    }
+  }
+
+  // ---- 4. the initial sort of my range
+  u32 *skey = key_a, *spos = pos_a;
+  if (M > 1 && radix_sort_pairs_u32(ctx, key_a, key_b, pos_a, pos_b, M, 0, key_bits, sort_temp, temp_bytes))
+  {
+    skey = key_b;
+    spos = pos_b;
+  }
+  if (M > 0)
+  {
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 8.0 * M, CUDA_CHECK(cudaMemcpyAsync(sa, spos, M * sizeof(u32), cudaMemcpyDeviceToDevice, s)));
+  }
+
+  // ---- bck: lower bounds inside my range, summed over the ranks
+  if (want_bck)
+  {
+    const u64 nc = ctx->numofcodes;
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(ctx->d_bck, 0, 2 * nc * sizeof(u64), s)));
+    ESA_LAUNCH(ctx, ESA_K_BCK, 8.0 * nc,
+               (bck_left_kernel<<<grid_for(nc, 256), 256, 0, s>>>(skey, M, nc, kdiv, ctx->d_bck)));
+    const size_t mark = ar.mark();
+    u64 *tmp = ar.alloc<u64>(2 * nc);
+    comm_allreduce_u64(ctx, comm, ctx->d_bck, tmp, 2 * nc, false);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ar.rewind(mark);
+    ESA_LAUNCH(ctx, ESA_K_BCK, 20.0 * nc,
+               (bck_mid_kernel<<<grid_for(nc, 256), 256, 0, s>>>(nc, N, nspec_tot, bck_cnt, ctx->d_bck)));
+  }
+
+  // ---- first regroup
+  outcome->h0 = h0;
+  outcome->rounds = 0;
+  outcome->active_sum = 0;
+  outcome->active_first = 0;
+  outcome->num_sorted = M;
+  const u32 rank_shift = max(bits_for(N - 1), 8u);
+  const u32 owner_bits = bits_for((u64) G - 1);
+  u32 rtiles = (u32) div_up_u64(M, RG_TILE);
+  u32 *tile_maxrank = ar.alloc<u32>(rtiles + 1), *tile_active = ar.alloc<u32>(rtiles + 1);
+  u64 m = 0;
+  if (M > 0)
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
+               (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
+                                                                                  tile_active, slot_base)));
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+               (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
+    m = read_scalar(ctx, d_scalars, 4);
+  }
+  outcome->active_first = m;
+  const u64 mal = m + 64;
+  u64 *dk_in = ar.alloc<u64>(mal);
+  u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
+  u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
+  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS && ar.high - ar.top > 12 * (M + 64) + 24 * mal + (64 << 20))
+  {
+    part_rank = ar.alloc<u32>(M + 64);
+    part_tp = ar.alloc<u32>(M + 64);
+    part_tv = ar.alloc<u32>(M + 64);
+  }
+  if (M > 0)
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
+               (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
+                                                                                tile_active, sa, rank, dk_in, dp_in,
+                                                                                slots_cur, rank_shift, nullptr, 0u,
+                                                                                part_rank, slot_base)));
+    if (part_rank != nullptr)
+    {
+      scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+    }
+  }
+  // ping-pong partners of the doubling buffers alias the 32-bit sort region (dead after the first regroup)
+  u64 *dk_out = reinterpret_cast<u64 *>(key_a);
+  u32 *dp_out = pos_a;
+  u32 *slots_next = pos_b;
+
+  // ---- 5. doubling, all ranks in lock step until no rank has an active suffix left
+  u64 h = h0;
+  while (true)
+  {
+    u64 req_cnt[ESA_MAX_RANKS] = {0}, req_off[ESA_MAX_RANKS], in_cnt[ESA_MAX_RANKS], in_off[ESA_MAX_RANKS];
+    if (m > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 28.0 * m,
+                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, ctx->d_tis, kp, lut, d_counts)));
+      CUDA_CHECK(cudaMemcpyAsync(req_cnt, d_counts, G * sizeof(u64), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    for (int r = 0; r < G; r++)
+    {
+      mine[r] = req_cnt[r];
+    }
+    mine[G] = m;
+    comm_exchange_host_u64(ctx, comm, mine, (size_t) G + 1, all);
+    u64 m_world = 0, in_tot = 0, o2 = 0;
+    for (int r = 0; r < G; r++)
+    {
+      m_world += all[(size_t) r * (G + 1) + G];
+      in_cnt[r] = all[(size_t) r * (G + 1) + me];
+      in_off[r] = in_tot;
+      in_tot += in_cnt[r];
+      req_off[r] = o2;
+      o2 += req_cnt[r];
+    }
+    if (m_world == 0)
+    {
+      break;
+    }
+    outcome->rounds++;
+    outcome->active_sum += m;
+    ctx->lcp_work_estimate += m * (h / 32 + 1);
+    if (outcome->rounds > 64)
+    {
+      esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
+    }
+    // partition my requests by owner (stable, one pass over the tag bits)
+    u64 *kreq = dk_in, *kalt = dk_out;
+    u32 *preq = dp_in, *palt = dp_out;
+    if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, owner_bits, sort_temp, temp_bytes))
+    {
+      kreq = dk_out, kalt = dk_in;
+      preq = dp_out, palt = dp_in;
+    }
+    const size_t round_mark = ar.mark();
+    u32 *req_in = ar.alloc<u32>(in_tot + 1), *ans_out = ar.alloc<u32>(in_tot + 1), *ans_in = ar.alloc<u32>(m + 1);
+    comm_alltoallv_u32(ctx, comm, preq, req_off, req_cnt, req_in, in_off, in_cnt);
+    if (in_tot > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 12.0 * in_tot,
+                 (serve_rank_kernel<<<grid_for(in_tot, 256), 256, 0, s>>>(req_in, in_tot, h, rank, ans_out)));
+    }
+    comm_alltoallv_u32(ctx, comm, ans_out, in_off, in_cnt, ans_in, req_off, req_cnt);
+    u64 m_next = 0;
+    if (m > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 20.0 * m,
+                 (merge_answer_kernel<<<grid_for(m, 256), 256, 0, s>>>(kreq, ans_in, m, rank_shift)));
+      ar.rewind(round_mark);  // the round's exchange buffers are dead (later users are stream ordered)
+      u64 *ks = kreq, *ko = kalt;
+      u32 *ps = preq, *po = palt;
+      if (m > 1 && radix_sort_pairs_u64(ctx, kreq, kalt, preq, palt, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
+      {
+        ks = kalt, ko = kreq;
+        ps = palt, po = preq;
+      }
+      rtiles = (u32) div_up_u64(m, RG_TILE);
+      ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
+                 (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
+                                                                                     tile_active, slot_base)));
+      ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+                 (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
+      m_next = read_scalar(ctx, d_scalars, 4);
+      const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
+      ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
+                 (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
+                                                                                   tile_active, sa, rank, ko, po,
+                                                                                   slots_next, rank_shift,
+                                                                                   ctx->d_hround, outcome->rounds,
+                                                                                   two_level ? part_rank : nullptr,
+                                                                                   slot_base)));
+      if (two_level)
+      {
+        scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+      }
+      dk_in = ko;
+      dp_in = po;
+      dk_out = ks;
+      dp_out = ps;
+      u32 *t = slots_cur;
+      slots_cur = slots_next;
+      slots_next = t;
+    } else
+    {
+      ar.rewind(round_mark);
+    }
+    m = m_next;
+    h *= 2;
   }
 }
