@@ -8,8 +8,10 @@ One "step" = one enhanced-suffix-array build (esa_construct: suffix array, inver
 HBM, CUDA events on the library's launching stream); `e2e` times esa_build through the C ABI with HOST buffers
 (pinned input, H2D + build + D2H of every demanded table inside the timed region).  The dominant kernel
 (radix_pass) is timed per launch with CUDA events inside the library and reported against the measured HBM peak.
-N > 1 (torchrun): every rank builds an independent index of its own sequence (weak scaling, no data-path
-collective); value = all ranks' symbols / max-over-ranks time.
+N > 1 (torchrun, one process per GPU): ONE index of N x the single-GPU sequence length is built by all ranks together
+(weak scaling): the suffix array is cut into N ranges along first-symbols bins, suffixes travel to their range's rank
+in an NCCL all-to-all, every rank sorts its range and derives lcp/bwt for it.  value = symbols of the
+whole index / max-over-ranks device time.
 """
 import argparse
 import json
@@ -29,8 +31,11 @@ WORKLOADS = {
            "-dna", "random_dna", {"seed": 42}),
     "c3": ("synthetic 250 Mbp repeat-rich DNA (configs[2])", 250_000_000, 4, "-dna", "repeat_rich_dna", {"seed": 7}),
     "c4": ("synthetic 500 M-residue protein (configs[3])", 500_000_000, 20, "-protein", "random_protein", {"seed": 11}),
+    "c5": ("synthetic 3 Gbp human-genome-scale DNA (configs[4]), strong scaling", 3_000_000_000, 4, "-dna",
+           "human_like_dna", {"seed": 2026, "records": 24}),
     "small": ("synthetic 4 Mbp random DNA (smoke size)", 4_000_000, 4, "-dna", "random_dna", {"seed": 42}),
 }
+STRONG = {"c5"}  # workloads whose total size is fixed when GPUs are added
 TABLES = ("suf", "lcp", "bwt")
 
 
@@ -43,16 +48,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_tis(workload, rank=0):
+def make_tis(workload, world=1):
+    """The sequence of the whole index: every rank generates the same one (it is replicated on the GPUs)."""
     from vstree_b200 import synth
     desc, n, sigma, flag, gen, kw = WORKLOADS[workload]
-    kw = dict(kw)
-    kw["seed"] = kw.get("seed", 0) + 1000 * rank  # every rank its own sequence
-    return getattr(synth, gen)(n, **kw), sigma, flag
+    if workload not in STRONG:
+        n *= world
+    return getattr(synth, gen)(n, **dict(kw)), sigma, flag
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line'): NVML polled every few
+    milliseconds from a thread (the timed region of a 100 Mbp build is shorter than nvidia-smi's own loop period);
+    nvidia-smi -lms is the fallback when the NVML binding is unusable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -61,22 +69,65 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.nvml = None
+        self.stop_flag = False
+        self.sm_max = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = sorted(x[0] for x in self.samples)
+            reasons = sorted(k for k, bit in names.items() if any(x[1] & bit for x in self.samples))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +150,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def time_reference_cli(tis, sigma, flag, k, repeats=1):
@@ -191,6 +242,7 @@ def main():
     import torch
     import torch.distributed as dist
     from vstree_b200 import Esa, load_library
+    from vstree_b200.capi import comm_unique_id
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the host arm)")
@@ -198,11 +250,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     desc, n, sigma, flag, gen, kw = WORKLOADS[args.workload]
+    if args.workload not in STRONG:
+        n *= world
     lib = load_library()
     k = int(lib.esa_recommended_prefixlength(sigma, n))
-    tis = np.ascontiguousarray(make_tis(args.workload, rank)[0])
+    tis = np.ascontiguousarray(make_tis(args.workload, world)[0])
     pinned = torch.from_numpy(tis).pin_memory()  # the e2e leg copies from pinned host memory
     esa = Esa(local_rank)
+    if world > 1:
+        # the library's own NCCL communicator; its id travels over torch.distributed
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        esa.attach_nccl(box[0], world, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
 
     def barrier():
@@ -236,7 +295,8 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
     clocks = sampler.stop()
-    esa.check()  # the tables of the last timed step are consistent (device-side property checks)
+    if world == 1:
+        esa.check()  # the tables of the last timed step are consistent (device-side property checks)
 
     # ---- end-to-end leg: esa_build through the C ABI with host buffers --------------------------------------
     e2e_ms, h2d, d2h = 0.0, 0, 0
@@ -246,6 +306,13 @@ def main():
         tabs, st = esa.build(pinned, sigma, k, TABLES, want_stats=True, copy=False)
         dt = (time.perf_counter() - t1) * 1000.0
         checksum = int(tabs["suf"][:: max(1, n // 1000)].sum())  # touch the result on the host
+        if i == 0 and world > 1:
+            # sharded build: the ranges tile the table and together hold a permutation of 0..n
+            part = torch.tensor([int(tabs["suf"].sum(dtype=np.uint64)) % (1 << 56), tabs["shard_count"]],
+                                dtype=torch.int64, device="cuda")
+            dist.all_reduce(part)
+            N = n + 1
+            assert int(part[1]) == N and int(part[0]) % (1 << 56) == (N * (N - 1) // 2) % (1 << 56), "sharded suftab is not a permutation"
         esa.free(tabs)
         if i > 0:
             e2e_ms += dt
@@ -285,12 +352,16 @@ def main():
                  for name, v in kern.items() if v["launches"]}
         line = {
             "metric": "mkvtree index build throughput (suf+lcp+bwt)",
-            "value": world * n * args.steps / (dev_ms_max * 1e-3) / 1e6,
+            "value": n * args.steps / (dev_ms_max * 1e-3) / 1e6,
             "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": desc, "n": n, "prefixlength": k, "tables": list(TABLES),
-                       "parallelism": "one independent index per GPU" if world > 1 else "single GPU",
+                       "parallelism": (f"one index sharded over {world} GPUs by suffix-array range (NCCL all-to-all of "
+                                       "suffixes, owner-routed rank requests per doubling round); per-rank figures "
+                                       "below are rank 0's") if world > 1 else "single GPU",
+                       "shard_count_rank0": last["shard_count"], "comm_bytes_sent_rank0": last["comm_bytes_sent"],
                        "l2": "256 MiB flush buffer written between timed steps; working set >> 126 MB L2",
                        "timing": "sum of per-step CUDA-event times on the library stream; wall incl. flush "
                                  f"{wall_ms / args.steps:.2f} ms/step",
@@ -304,7 +375,7 @@ def main():
                          "share_of_step": rp["ms"] / dev_ms if dev_ms else None},
             "stages": stage,
             "cpu_baseline": cpu,
-            "e2e": {"value": world * n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
+            "e2e": {"value": n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max},
             "gpu_launches": int(launches),
             "clocks": clocks,

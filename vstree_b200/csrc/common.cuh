@@ -64,6 +64,7 @@ struct Arena
       return;
     }
     release();
+    bytes = (bytes + 255) & ~(size_t) 255;
     CUDA_CHECK(cudaMalloc((void **) &base, bytes));
     capacity = bytes;
     high = capacity;

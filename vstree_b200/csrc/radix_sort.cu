@@ -32,6 +32,9 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #ifndef ESA_SORT_MINBLOCKS
 #define ESA_SORT_MINBLOCKS 2
 #endif
+#ifndef ESA_SORT_EARLY
+#define ESA_SORT_EARLY 1     // publish the tile's digit counts before the ranking phase
+#endif
 #ifndef ESA_SORT_MATCH
 #define ESA_SORT_MATCH 0  // 0: eight ballots per key, 1: shared-memory atomicOr lane masks
 #endif
@@ -157,6 +160,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   u32 *digit_start = wc + SORT_WARPS * RADIX;  // [RADIX] first slot of the digit in the reordered tile
   u32 *gbase = digit_start + RADIX;            // [RADIX] global index of slot 0 of the digit, minus digit_start
   u32 *misc = gbase + RADIX;                   // [0] tile ticket, [1..] scan scratch
+  u32 *thist = misc + 16;                      // [RADIX] digit counts of the tile, published BEFORE the ranking
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0)
@@ -169,8 +173,12 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   {
     mywc[d] = 0;
 #if ESA_SORT_MATCH == 1
-    misc[16 + warp * RADIX + d] = 0;
+    thist[RADIX + warp * RADIX + d] = 0;
 #endif
+  }
+  if (tid < RADIX)
+  {
+    thist[tid] = 0;
   }
   __syncthreads();
   const u32 tile = misc[0];
@@ -187,6 +195,39 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     const u32 idx = wbase + i * 32 + lane;
     keys[i] = idx < tile_count ? kin[tile_base + idx] : (KeyT) ~(KeyT) 0;  // padding sorts last
   }
+#if ESA_SORT_EARLY
+  // ---- early counts: the tile's digit histogram is published before the (long) ranking phase, so that the
+  // look-back of the following tiles, which runs after THEIR ranking, rarely waits.  Measured on B200: 2 % faster
+  // than publishing after the ranking; a warp-cooperative look-back (32 predecessor tiles per round trip) was
+  // 2.5x SLOWER than the one-thread-per-digit walk below -- chains are short in steady state, and the wide
+  // windows only add L2 requests.
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const u32 d = digit_of(keys[i], shift, mask);
+    if (__all_sync(FULL_MASK, d == __shfl_sync(FULL_MASK, d, 0)))
+    {
+      if (lane == 0)
+      {
+        atomicAdd(&thist[d], 32u);  // constant digit (high bits of small keys, runs of equal keys): count once
+      }
+    } else
+    {
+      atomicAdd(&thist[d], 1u);
+    }
+  }
+  __syncthreads();
+  u32 valid_count = 0;
+  if (tid < RADIX)
+  {
+    valid_count = thist[tid];
+    if ((u32) tid == mask)
+    {
+      valid_count -= (u32) TILE - tile_count;  // padding keys carry the largest digit
+    }
+    status[(u64) tile * RADIX + tid] = (tile == 0 ? STATUS_PREFIX : STATUS_AGG) | valid_count;
+  }
+#endif
   // ---- rank inside the warp: stable in (item, lane) order = memory order
   const u32 lt_mask = (1u << lane) - 1;
   // lanes holding the same digit, found with one ballot per digit bit.  MATCH.ANY does the same in one
@@ -195,7 +236,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #if ESA_SORT_MATCH == 1
   // Variant: peers through a per-warp, per-digit lane mask in shared memory (one atomicOr per key, read back after
   // a warp barrier) instead of eight ballots: far fewer instructions, three shared-memory round trips per step.
-  u32 *mymm = misc + 16 + warp * RADIX;
+  u32 *mymm = thist + RADIX + warp * RADIX;
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
@@ -272,21 +313,26 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       run += c;
     }
   }
-  // ---- decoupled look-back: how many keys with my digit precede this tile (within the part)
+  // ---- decoupled look-back, one thread per digit
   if (tid < RADIX)
   {
-    u32 valid_count = bcount;
+    u32 cnt = bcount;
     if ((u32) tid == mask)
     {
-      valid_count -= (u32) TILE - tile_count;  // padding keys carry the largest digit
+      cnt -= (u32) TILE - tile_count;  // padding keys carry the largest digit
     }
     u32 excl = 0;
+#if !ESA_SORT_EARLY
     if (tile == 0)
     {
-      status[tid] = STATUS_PREFIX | valid_count;
+      status[tid] = STATUS_PREFIX | cnt;
     } else
     {
-      status[(u64) tile * RADIX + tid] = STATUS_AGG | valid_count;
+      status[(u64) tile * RADIX + tid] = STATUS_AGG | cnt;
+    }
+#endif
+    if (tile != 0)
+    {
       u32 t = tile - 1;
       while (true)
       {
@@ -302,7 +348,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
         }
         t--;
       }
-      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (excl + valid_count);
+      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (excl + cnt);
     }
     digit_start[tid] = dstart;
     gbase[tid] = base[tid] + excl - dstart;  // wraps modulo 2^32 by design
@@ -344,7 +390,7 @@ template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
 {
   constexpr int TILE = SORT_THREADS * SortTraits<KeyT>::ITEMS;
   return (size_t) TILE * sizeof(KeyT) + (has_vals ? (size_t) TILE * 4 : 0) + (size_t) SORT_WARPS * RADIX * 4
-         + 2 * RADIX * 4 + (1 + RADIX / 32 + 1 + 6) * 4 + (ESA_SORT_MATCH == 1 ? (size_t) SORT_WARPS * RADIX * 4 : 0);
+         + 2 * RADIX * 4 + 16 * 4 + RADIX * 4 + (ESA_SORT_MATCH == 1 ? (size_t) SORT_WARPS * RADIX * 4 : 0);
 }
 
 template <typename KeyT> u64 part_items_max()
