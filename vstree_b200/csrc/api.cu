@@ -182,7 +182,31 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
   }
   CUDA_CHECK(cudaSetDevice(ctx->device));
   ctx->uploaded = ctx->constructed = false;
-  ctx->arena.reserve(arena_estimate(n, ctx->comm != nullptr ? ctx->comm->nranks : 1));
+  const size_t need = arena_estimate(n, ctx->comm != nullptr ? ctx->comm->nranks : 1);
+  if (is_sharded(ctx))
+  {
+    // collective: when any rank's arena has to move, every rank drops its peer mappings first, then all map again
+    esa_comm *comm = ctx->comm;
+    const u64 token = (u64) (uintptr_t) ctx->arena.base ^ ((u64) ctx->arena.capacity << 1);
+    u64 moved = (need > ctx->arena.capacity || token != comm->mapped_token || !comm->direct) ? 1 : 0, all[ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, comm, &moved, 1, all);
+    bool any = false;
+    for (int r = 0; r < comm->nranks; r++)
+    {
+      any = any || all[r] != 0;
+    }
+    if (any)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      comm_unmap_arenas(ctx, comm);
+      comm_exchange_host_u64(ctx, comm, &moved, 1, all);  // nobody holds a mapping any more: arenas may be freed
+      ctx->arena.reserve(need);
+      comm_map_arenas(ctx, comm);
+    }
+  } else
+  {
+    ctx->arena.reserve(need);
+  }
   ctx->arena.reset();
   const u64 padded = ((n + 15) & ~(u64) 15) + 64;
   ctx->d_tis = ctx->arena.alloc<u8>(padded);

@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 #include <pthread.h>
+#include <unistd.h>
 #include <nccl.h>  // types and prototypes only: the library is resolved with dlopen, never linked
 
 namespace
@@ -214,6 +215,8 @@ esa_comm *comm_nccl_attach(esa_ctx *ctx, const u8 id[ESA_COMM_ID_BYTES], int nra
   comm->rank = rank;
   comm->nranks = nranks;
   comm->nccl = c;
+  comm->xchg_bytes = (size_t) 1 << 20;
+  CUDA_CHECK(cudaMalloc((void **) &comm->d_xchg, comm->xchg_bytes));
   return comm;
 }
 
@@ -231,15 +234,127 @@ esa_comm *comm_group_attach(esa_ctx *ctx, esa_group *g, int rank)
   return comm;
 }
 
+void comm_unmap_arenas(esa_ctx *ctx, esa_comm *comm)
+{
+  if (comm == nullptr)
+  {
+    return;
+  }
+  if (ctx != nullptr)
+  {
+    cudaSetDevice(ctx->device);
+  }
+  for (int r = 0; r < ESA_MAX_RANKS; r++)
+  {
+    if (comm->ipc_opened[r] != nullptr)
+    {
+      cudaIpcCloseMemHandle(comm->ipc_opened[r]);
+      comm->ipc_opened[r] = nullptr;
+    }
+    comm->peer_base[r] = nullptr;
+  }
+  cudaGetLastError();
+  comm->direct = false;
+}
+
+void comm_map_arenas(esa_ctx *ctx, esa_comm *comm)
+{
+  comm_unmap_arenas(ctx, comm);
+  if (comm->nranks <= 1)
+  {
+    return;
+  }
+  bool want = true;
+  if (const char *e = getenv("ESA_COMM_DIRECT"))
+  {
+    want = atoi(e) != 0;
+  }
+  // words per rank: [0] usable flag, [1] base pointer value, [2] capacity, [3] process id, [4..11] IPC handle
+  constexpr size_t ROW = 12;
+  u64 mine[ROW] = {0}, all[ROW * ESA_MAX_RANKS];
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 8 * sizeof(u64), "IPC handle size");
+  mine[1] = (u64) (uintptr_t) ctx->arena.base;
+  mine[2] = ctx->arena.capacity;
+  mine[3] = (u64) getpid();
+  bool ok = want && ctx->arena.base != nullptr;
+  if (ok && comm->group == nullptr)
+  {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, ctx->arena.base) == cudaSuccess)
+    {
+      memcpy(&mine[4], &h, sizeof h);
+    } else
+    {
+      cudaGetLastError();
+      ok = false;
+    }
+  }
+  mine[0] = ok ? 1 : 0;
+  comm_exchange_host_u64(ctx, comm, mine, ROW, all);
+  bool everyone = true;
+  for (int r = 0; r < comm->nranks; r++)
+  {
+    everyone = everyone && all[r * ROW] != 0;
+  }
+  u64 mapped = 0;
+  if (everyone)
+  {
+    mapped = 1;
+    for (int r = 0; r < comm->nranks; r++)
+    {
+      if (r == comm->rank)
+      {
+        comm->peer_base[r] = ctx->arena.base;
+      } else if (all[r * ROW + 3] == (u64) getpid())
+      {
+        comm->peer_base[r] = (char *) (uintptr_t) all[r * ROW + 1];  // same process: the pointer itself
+      } else
+      {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &all[r * ROW + 4], sizeof h);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+          cudaGetLastError();
+          mapped = 0;
+          break;
+        }
+        comm->ipc_opened[r] = p;
+        comm->peer_base[r] = (char *) p;
+      }
+    }
+  }
+  // all or nothing: a rank that could not map a peer makes everybody use the message-passing paths
+  u64 votes[ESA_MAX_RANKS];
+  comm_exchange_host_u64(ctx, comm, &mapped, 1, votes);
+  bool agreed = true;
+  for (int r = 0; r < comm->nranks; r++)
+  {
+    agreed = agreed && votes[r] != 0;
+  }
+  if (!agreed)
+  {
+    comm_unmap_arenas(ctx, comm);
+    return;
+  }
+  comm->direct = true;
+  comm->mapped_token = (u64) (uintptr_t) ctx->arena.base ^ ((u64) ctx->arena.capacity << 1);
+}
+
 void comm_destroy(esa_comm *comm)
 {
   if (comm == nullptr)
   {
     return;
   }
+  comm_unmap_arenas(nullptr, comm);
   if (comm->nccl != nullptr)
   {
     nccl().CommDestroy((ncclComm_t) comm->nccl);
+  }
+  if (comm->d_xchg != nullptr)
+  {
+    cudaFree(comm->d_xchg);
   }
   delete comm;
 }
@@ -325,14 +440,17 @@ void comm_exchange_host_u64(esa_ctx *ctx, esa_comm *comm, const u64 *mine, size_
     group_barrier(g);
     return;
   }
-  const size_t mark = ctx->arena.mark();
-  u64 *d_send = ctx->arena.alloc<u64>(count), *d_recv = ctx->arena.alloc<u64>(count * comm->nranks);
+  // small device staging owned by the communicator (the arena may not exist yet, or may be about to move)
+  if ((count + count * comm->nranks) * sizeof(u64) > comm->xchg_bytes)
+  {
+    esa_throw(ESA_ERR_COMM, "host value exchange of %zu words exceeds the staging buffer", count);
+  }
+  u64 *d_send = comm->d_xchg, *d_recv = comm->d_xchg + count;
   CUDA_CHECK(cudaMemcpyAsync(d_send, mine, count * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
   ESA_LAUNCH(ctx, ESA_K_COMM, 0,
              NCCL_CHECK(nccl().AllGather(d_send, d_recv, count, ncclUint64, (ncclComm_t) comm->nccl, ctx->stream)));
   CUDA_CHECK(cudaMemcpyAsync(all, d_recv, count * comm->nranks * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  ctx->arena.rewind(mark);
 }
 
 void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, size_t count, bool max_instead_of_sum)

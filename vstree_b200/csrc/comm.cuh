@@ -41,8 +41,15 @@ struct esa_comm
   int nranks = 1;
   void *nccl = nullptr;       // ncclComm_t when the transport is NCCL
   esa_group *group = nullptr; // else the in-process group
-  double ms_comm = 0;         // host-measured time spent inside collectives (includes waiting for the slowest rank)
   u64 bytes_sent = 0;         // payload this rank sent to OTHER ranks
+  u64 *d_xchg = nullptr;      // NCCL transport: device staging of the host value exchanges
+  size_t xchg_bytes = 0;
+  // peer memory: the device arenas of all ranks, addressable from this rank's device (CUDA IPC between processes, plain
+  // pointers inside one process).  Kernels then store into / load from other ranks' buffers directly over NVLink.
+  bool direct = false;                       // arenas are mapped
+  char *peer_base[ESA_MAX_RANKS] = {nullptr};
+  void *ipc_opened[ESA_MAX_RANKS] = {nullptr};  // mappings to close (NCCL transport)
+  u64 mapped_token = 0;                      // identifies the local arena allocation the peers have mapped
 };
 
 // transport setup (comm.cu)
@@ -50,6 +57,17 @@ void comm_nccl_unique_id(u8 id[ESA_COMM_ID_BYTES]);
 esa_comm *comm_nccl_attach(esa_ctx *ctx, const u8 id[ESA_COMM_ID_BYTES], int nranks, int rank);
 esa_comm *comm_group_attach(esa_ctx *ctx, esa_group *g, int rank);
 void comm_destroy(esa_comm *comm);
+
+// peer memory (collective): after the call comm->direct tells whether every rank could map every arena;
+// ESA_COMM_DIRECT=0 forces the message-passing paths.  Must be re-run (after comm_unmap_arenas) when any arena moved.
+void comm_map_arenas(esa_ctx *ctx, esa_comm *comm);
+void comm_unmap_arenas(esa_ctx *ctx, esa_comm *comm);
+// translate a pointer into this rank's arena to the same offset of rank r's arena
+template <typename T> static inline T *comm_peer_ptr(esa_ctx *ctx, esa_comm *comm, int r, u64 byte_offset)
+{
+  (void) ctx;
+  return reinterpret_cast<T *>(comm->peer_base[r] + byte_offset);
+}
 
 // ---- collectives; every rank of the communicator must call them in the same order ----
 // every rank learns `count` 64-bit host values of every rank: all[r*count + i]; synchronises the stream

@@ -283,6 +283,16 @@ int radix_sort_pairs_u32(esa_ctx *ctx, u32 *keys_a, u32 *keys_b, u32 *vals_a, u3
 int radix_sort_pairs_u64(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
                          u32 end_bit, void *temp, size_t temp_bytes);
 
+// the partition step of the sharded build fused with its all-to-all (stores into peer memory); see radix_sort.cu
+struct RadixRemoteDst
+{
+  u32 *keys[64];   // receive buffers of every rank, as mapped into this rank's address space
+  u32 *vals[64];
+  u8 owner[256];   // digit -> rank
+};
+void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
+                                const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes);
+
 // suffix_sort.cu: fills ctx->d_sa, ctx->d_isa (and ctx->d_bck when demanded) ; returns stats pieces
 struct SortOutcome
 {

@@ -127,7 +127,8 @@ radix_hist_kernel(const KeyT *__restrict__ keys, u32 count, u32 begin_bit, u32 e
 
 // one block per pass, one thread per digit
 __global__ void __launch_bounds__(RADIX)
-radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npass, u32 parts)
+radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npass, u32 parts,
+                  const u32 *__restrict__ given /* if set (npass == 1): first output index of every digit */)
 {
   __shared__ u32 scratch[RADIX / 32 + 1];
   const u32 p = blockIdx.x, d = threadIdx.x;
@@ -137,6 +138,10 @@ radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npas
     total += hist[((u64) part * npass + p) * RADIX + d];
   }
   u32 run = block_exclusive_sum<u32, RADIX>(total, scratch, nullptr);
+  if (given != nullptr)
+  {
+    run = given[d];
+  }
   for (u32 part = 0; part < parts; part++)
   {
     const u64 o = ((u64) part * npass + p) * RADIX + d;
@@ -146,11 +151,14 @@ radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npas
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <typename KeyT, bool HAS_VALS, int ITEMS>
+// REMOTE: the pass is the partition step of the sharded build fused with its all-to-all: digit d belongs to rank
+// remote->owner[d] and its run is stored straight into that rank's receive buffers (peer memory over NVLink);
+// base[d] then is the first index of THIS rank's run of digit d inside the owner's buffers.
+template <typename KeyT, bool HAS_VALS, int ITEMS, bool REMOTE = false>
 __global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
 radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin,
                   u32 *__restrict__ vout, u32 count, u32 shift, u32 mask, const u32 *__restrict__ base,
-                  volatile u32 *status, u32 *ticket)
+                  volatile u32 *status, u32 *ticket, const RadixRemoteDst *__restrict__ remote = nullptr)
 {
   constexpr int TILE = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -376,13 +384,29 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     if (p < tile_count)
     {
       const KeyT k = skeys[p];
-      const u32 g = gbase[digit_of(k, shift, mask)] + p;
-      kout[g] = k;
-      if (HAS_VALS)
+      const u32 d = digit_of(k, shift, mask);
+      const u32 g = gbase[d] + p;
+      if (REMOTE)
       {
-        vout[g] = svals[p];
+        const u32 o = remote->owner[d];
+        reinterpret_cast<KeyT *>(remote->keys[o])[g] = k;
+        if (HAS_VALS)
+        {
+          remote->vals[o][g] = svals[p];
+        }
+      } else
+      {
+        kout[g] = k;
+        if (HAS_VALS)
+        {
+          vout[g] = svals[p];
+        }
       }
     }
+  }
+  if (REMOTE)
+  {
+    __threadfence_system();  // the stores crossed NVLink: visible to the owner before this kernel counts as done
   }
 }
 
@@ -461,7 +485,7 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
                (radix_hist_kernel<KeyT><<<grid, HIST_THREADS, 0, s>>>(ka + off, cnt, begin_bit, end_bit, npass,
                                                                         hist + (u64) part * npass * RADIX)));
   }
-  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<npass, RADIX, 0, s>>>(hist, base, npass, L.parts)));
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<npass, RADIX, 0, s>>>(hist, base, npass, L.parts, nullptr)));
 
   const size_t smem = pass_smem_bytes<KeyT>(has_vals);
   KeyT *ksrc = ka, *kdst = kb;
@@ -504,6 +528,11 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
 
 template <typename KeyT> void set_smem_attr()
 {
+  if (sizeof(KeyT) == 4)
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<u32, true, SortTraits<u32>::ITEMS, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem_bytes<u32>(true)));
+  }
   CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, true, SortTraits<KeyT>::ITEMS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem_bytes<KeyT>(true)));
   CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<KeyT, false, SortTraits<KeyT>::ITEMS>,
@@ -516,6 +545,59 @@ void radix_sort_init()
 {
   set_smem_attr<u32>();
   set_smem_attr<u64>();
+}
+
+// Stable partition of (key, value) pairs by the digit in key bits [begin_bit, end_bit) (at most 8 bits) whose output
+// goes to OTHER ranks' buffers: see the REMOTE note at radix_pass_kernel.  d_start[256] (device) holds, per digit, the
+// first index of this rank's run inside the owner's buffers.
+void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
+                                const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes)
+{
+  constexpr int ITEMS = SortTraits<u32>::ITEMS;
+  constexpr u64 TILE = (u64) SORT_THREADS * ITEMS;
+  if (n == 0)
+  {
+    return;
+  }
+  if (end_bit <= begin_bit || end_bit - begin_bit > RADIX_BITS)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "remote partition needs a digit of 1..8 bits");
+  }
+  const TempLayout L = temp_layout<u32>(n);
+  if (temp_bytes < L.total)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "radix sort scratch too small: %zu < %zu", temp_bytes, L.total);
+  }
+  char *t = (char *) temp;
+  u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off),
+      *status = (u32 *) (t + L.status_off);
+  const u64 pim = part_items_max<u32>();
+  cudaStream_t s = ctx->stream;
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
+  for (u32 part = 0; part < L.parts; part++)
+  {
+    const u64 off = (u64) part * pim;
+    const u32 cnt = (u32) (n - off < pim ? n - off : pim);
+    const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(cnt, (u64) HIST_THREADS * HIST_ITEMS));
+    ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, (double) cnt * 4,
+               (radix_hist_kernel<u32><<<grid, HIST_THREADS, 0, s>>>(keys + off, cnt, begin_bit, end_bit, 1,
+                                                                       hist + (u64) part * RADIX)));
+  }
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<1, RADIX, 0, s>>>(hist, base, 1, L.parts, d_start)));
+  const u32 mask = (1u << (end_bit - begin_bit)) - 1;
+  const size_t smem = pass_smem_bytes<u32>(true);
+  for (u32 part = 0; part < L.parts; part++)
+  {
+    const u64 off = (u64) part * pim;
+    const u32 cnt = (u32) (n - off < pim ? n - off : pim);
+    const u32 tiles = (u32) div_up_u64(cnt, TILE);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 4, s)));
+    // algorithmic bytes: one local read, one store into peer memory
+    ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 2.0 * cnt * 8,
+               (radix_pass_kernel<u32, true, ITEMS, true><<<tiles, SORT_THREADS, smem, s>>>(
+                   keys + off, nullptr, vals + off, nullptr, cnt, begin_bit, mask, base + (u64) part * RADIX, status,
+                   tickets + part, d_remote)));
+  }
 }
 
 size_t radix_sort_temp_bytes(u64 n, u32 key_bytes)

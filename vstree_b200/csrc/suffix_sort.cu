@@ -944,6 +944,24 @@ __global__ void merge_answer_kernel(u64 *__restrict__ key, const u32 *__restrict
   }
 }
 
+// doubling with peer memory: the rank of the h-successor is loaded straight from its owner's rank array over NVLink
+struct PeerRanks
+{
+  const u32 *rank[ESA_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256)
+gather_rank_peer_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, const u8 *__restrict__ tis,
+                        KmerParams kp, OwnerLut lut, PeerRanks peers)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m)
+  {
+    const u64 q = (u64) pos[t] + h;
+    const u32 o = owner_of_key(initial_key_at(tis, q, kp), lut);
+    key[t] |= (u64) __ldcv(peers.rank[o] + q);  // never cached: the owner rewrites it between rounds
+  }
+}
+
 u32 grid_for(u64 count, u32 block) { return (u32) div_up_u64(count, block); }
 
 }  // namespace
@@ -965,7 +983,6 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
 
   u64 *d_scalars = ar.alloc<u64>(16);
   unsigned long long *d_counts = (unsigned long long *) ar.alloc<u64>(256);
-  u64 *d_counts_tmp = ar.alloc<u64>(256);
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_scalars, 0, 16 * sizeof(u64), s)));
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 256 * sizeof(u64), s)));
 
@@ -1014,12 +1031,25 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 4.0 * nfull,
                (bin_hist_kernel<<<grid, 256, 0, s>>>(key_l, nfull, lut.shift, d_counts)));
   }
-  u64 local_hist[256];
-  CUDA_CHECK(cudaMemcpyAsync(local_hist, d_counts, sizeof local_hist, cudaMemcpyDeviceToHost, s));
-  comm_allreduce_u64(ctx, comm, (u64 *) d_counts, d_counts_tmp, 256, false);
-  u64 global_hist[256];
-  CUDA_CHECK(cudaMemcpyAsync(global_hist, d_counts, sizeof global_hist, cudaMemcpyDeviceToHost, s));
+  u64 local_hist[256 + 2];
+  CUDA_CHECK(cudaMemcpyAsync(local_hist, d_counts, 256 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  local_hist[256] = nside;
+  local_hist[257] = nspec;
+  // every rank learns every rank's bin counts: the splitters, all send/receive counts and, for the fused
+  // partition + all-to-all, the exact place of every (sender, bin) run in its owner's buffer follow from this matrix
+  constexpr size_t HROW = 258;
+  std::vector<u64> hist_all((size_t) G * HROW);
+  comm_exchange_host_u64(ctx, comm, local_hist, HROW, hist_all.data());
+  u64 global_hist[256];
+  for (int b = 0; b < 256; b++)
+  {
+    global_hist[b] = 0;
+    for (int r = 0; r < G; r++)
+    {
+      global_hist[b] += hist_all[(size_t) r * HROW + b];
+    }
+  }
   {
     u64 total = 0, acc = 0;
     for (int b = 0; b < 256; b++)
@@ -1040,33 +1070,31 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     }
   }
 
-  // ---- 3a. counts of every rank: full per destination, side, special
-  u64 send_cnt[ESA_MAX_RANKS] = {0}, send_off[ESA_MAX_RANKS], recv_cnt[ESA_MAX_RANKS], recv_off[ESA_MAX_RANKS];
+  // ---- 3a. counts: full suffixes per (sender, destination), side and special-initial suffixes per rank
+  u64 send_cnt[ESA_MAX_RANKS] = {0}, send_off[ESA_MAX_RANKS], recv_cnt[ESA_MAX_RANKS] = {0}, recv_off[ESA_MAX_RANKS];
   for (int b = 0; b < 256; b++)
   {
     send_cnt[lut.owner[b]] += local_hist[b];
+    if (lut.owner[b] == me)
+    {
+      for (int r = 0; r < G; r++)
+      {
+        recv_cnt[r] += hist_all[(size_t) r * HROW + b];
+      }
+    }
   }
-  for (int r = 0; r < G; r++)
-  {
-    mine[r] = send_cnt[r];
-  }
-  mine[G] = nside;
-  mine[G + 1] = nspec;
-  const size_t row = (size_t) G + 2;
-  comm_exchange_host_u64(ctx, comm, mine, row, all);
   u64 side_cnt[ESA_MAX_RANKS], side_off[ESA_MAX_RANKS], spec_cnt[ESA_MAX_RANKS], spec_off[ESA_MAX_RANKS];
   u64 nside_tot = 0, nspec_tot = 0, mfull = 0, off = 0;
   for (int r = 0; r < G; r++)
   {
     send_off[r] = off;
     off += send_cnt[r];
-    recv_cnt[r] = all[(size_t) r * row + me];
     recv_off[r] = mfull;
     mfull += recv_cnt[r];
-    side_cnt[r] = all[(size_t) r * row + G];
+    side_cnt[r] = hist_all[(size_t) r * HROW + 256];
     side_off[r] = nside_tot;
     nside_tot += side_cnt[r];
-    spec_cnt[r] = all[(size_t) r * row + G + 1];
+    spec_cnt[r] = hist_all[(size_t) r * HROW + 257];
     spec_off[r] = nspec_tot;
     nspec_tot += spec_cnt[r];
   }
@@ -1144,6 +1172,43 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   const u64 M = mfull + nside_mine;  // suffixes of my range that take part in the sort
   const u64 Mal = M + 64;
   u32 *key_a = ar.alloc<u32>(Mal), *key_b = ar.alloc<u32>(Mal), *pos_a = ar.alloc<u32>(Mal), *pos_b = ar.alloc<u32>(Mal);
+  if (comm->direct)
+  {
+    // fused partition + all-to-all: one pass over my (key, position) pairs whose output runs land directly in the
+    // owners' key_a / pos_a over NVLink.  Layout inside an owner: bin-major, then sender, then the sender's order
+    // (= text position order), so the owner receives its range already partitioned by the top key digit.
+    u64 my_off[2] = {(u64) ((char *) key_a - ar.base), (u64) ((char *) pos_a - ar.base)}, offs[2 * ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, comm, my_off, 2, offs);  // also: every rank has carved its receive buffers
+    RadixRemoteDst h_dst;
+    memset(&h_dst, 0, sizeof h_dst);
+    for (int r = 0; r < G; r++)
+    {
+      h_dst.keys[r] = comm_peer_ptr<u32>(ctx, comm, r, offs[2 * r]);
+      h_dst.vals[r] = comm_peer_ptr<u32>(ctx, comm, r, offs[2 * r + 1]);
+    }
+    memcpy(h_dst.owner, lut.owner, 256);
+    u32 h_start[256];
+    u64 run_of_owner[ESA_MAX_RANKS] = {0};
+    for (int b = 0; b < 256; b++)
+    {
+      const int o = lut.owner[b];
+      u64 before_me = 0;
+      for (int r = 0; r < me; r++)
+      {
+        before_me += hist_all[(size_t) r * HROW + b];
+      }
+      h_start[b] = (u32) (run_of_owner[o] + before_me);
+      run_of_owner[o] += global_hist[b];
+    }
+    RadixRemoteDst *d_dst = reinterpret_cast<RadixRemoteDst *>(ar.alloc<char>(sizeof(RadixRemoteDst)));
+    u32 *d_start = ar.alloc<u32>(256);
+    CUDA_CHECK(cudaMemcpyAsync(d_dst, &h_dst, sizeof h_dst, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(d_start, h_start, sizeof h_start, cudaMemcpyHostToDevice, s));
+    radix_partition_remote_u32(ctx, key_l, pos_l, nfull, lut.shift, key_bits > lut.shift ? key_bits : lut.shift + 1,
+                               d_dst, d_start, sort_temp, temp_bytes);
+    comm->bytes_sent += 8 * (nfull - send_cnt[me]);
+    CUDA_CHECK(cudaStreamSynchronize(s));  // my stores are done; the exchange below tells me when everybody's are
+  } else
   {
     const u32 *ks = key_l, *ps = pos_l;
     if (nfull > 1 && radix_sort_pairs_u32(ctx, key_l, key_t, pos_l, pos_t, nfull, lut.shift, key_bits, sort_temp, temp_bytes))
@@ -1275,6 +1340,97 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u32 *slots_next = pos_b;
 
   // ---- 5. doubling, all ranks in lock step until no rank has an active suffix left
+  if (comm->direct)
+  {
+    // peer-memory variant: two barriers per round keep the remote loads of rank[] apart from the owners' updates
+    u64 my_off = (u64) ((char *) rank - ar.base), offs[ESA_MAX_RANKS];
+    CUDA_CHECK(cudaStreamSynchronize(s));  // my first regroup has written its ranks
+    u64 pair[2] = {my_off, m}, pairs[2 * ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, comm, pair, 2, pairs);
+    PeerRanks peers;
+    u64 m_world = 0;
+    for (int r = 0; r < G; r++)
+    {
+      offs[r] = pairs[2 * r];
+      peers.rank[r] = comm_peer_ptr<const u32>(ctx, comm, r, offs[r]);
+      m_world += pairs[2 * r + 1];
+    }
+    u64 hh = h0;
+    while (m_world > 0)
+    {
+      outcome->rounds++;
+      outcome->active_sum += m;
+      ctx->lcp_work_estimate += m * (hh / 32 + 1);
+      if (outcome->rounds > 64)
+      {
+        esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
+      }
+      u64 m_next = 0;
+      u64 *ks = dk_in, *ko = dk_out;
+      u32 *ps = dp_in, *po = dp_out;
+      if (m > 0)
+      {
+        ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
+                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, hh, ctx->d_tis, kp, lut, peers)));
+        comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
+        if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
+        {
+          ks = dk_out, ko = dk_in;
+          ps = dp_out, po = dp_in;
+        }
+        rtiles = (u32) div_up_u64(m, RG_TILE);
+        ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
+                   (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
+                                                                                       tile_active, slot_base)));
+        ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+                   (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
+        m_next = read_scalar(ctx, d_scalars, 4);
+      } else
+      {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+      }
+      // barrier 1: every rank has finished reading rank[] (its gather precedes this point on its stream)
+      u64 world_next[ESA_MAX_RANKS], sum_next = 0;
+      comm_exchange_host_u64(ctx, comm, &m_next, 1, world_next);
+      for (int r = 0; r < G; r++)
+      {
+        sum_next += world_next[r];
+      }
+      if (m > 0)
+      {
+        const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
+        ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
+                   (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
+                                                                                     tile_active, sa, rank, ko, po,
+                                                                                     slots_next, rank_shift,
+                                                                                     ctx->d_hround, outcome->rounds,
+                                                                                     two_level ? part_rank : nullptr,
+                                                                                     slot_base)));
+        if (two_level)
+        {
+          scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+        }
+        dk_in = ko;
+        dp_in = po;
+        dk_out = ks;
+        dp_out = ps;
+        u32 *t = slots_cur;
+        slots_cur = slots_next;
+        slots_next = t;
+      }
+      if (sum_next > 0)
+      {
+        // barrier 2: every rank has finished updating rank[] before anybody gathers again
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        u64 zero = 0, dummy[ESA_MAX_RANKS];
+        comm_exchange_host_u64(ctx, comm, &zero, 1, dummy);
+      }
+      m = m_next;
+      m_world = sum_next;
+      hh *= 2;
+    }
+    return;
+  }
   u64 h = h0;
   while (true)
   {
