@@ -237,6 +237,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
+    # libraries (NCCL's version banner) write to fd 1: keep stdout for the ONE JSON line
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -362,6 +365,9 @@ def main():
                                        "suffixes, owner-routed rank requests per doubling round); per-rank figures "
                                        "below are rank 0's") if world > 1 else "single GPU",
                        "shard_count_rank0": last["shard_count"], "comm_bytes_sent_rank0": last["comm_bytes_sent"],
+                       "exchange": ("peer memory (CUDA IPC): partition pass stores into the owners' buffers, doubling "
+                                    "keys loaded from the owners' rank arrays") if last["comm_direct"] else
+                                   ("NCCL send/recv" if world > 1 else None),
                        "l2": "256 MiB flush buffer written between timed steps; working set >> 126 MB L2",
                        "timing": "sum of per-step CUDA-event times on the library stream; wall incl. flush "
                                  f"{wall_ms / args.steps:.2f} ms/step",
@@ -380,7 +386,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     esa.close()
     if world > 1:
         dist.barrier()

@@ -95,6 +95,8 @@ def test_sharded_equals_single_gpu_on_a_larger_input(group):
     sizes = [s["shard_count"] for s in stats]
     assert max(sizes) < 2.0 * (len(tis) + 1) / group.nranks, f"ranges badly balanced: {sizes}"
     assert all(s["comm_bytes_sent"] > 0 for s in stats)
+    want_direct = os.environ.get("ESA_COMM_DIRECT", "1") != "0"
+    assert all(bool(s["comm_direct"]) == want_direct for s in stats)
 
 
 def test_sharded_protein_and_staged_calls(group):

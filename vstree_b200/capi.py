@@ -29,7 +29,7 @@ class KernelStat(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("ms_total", ctypes.c_double), ("ms_initial_sort", ctypes.c_double), ("ms_doubling", ctypes.c_double),
                 ("ms_lcp", ctypes.c_double), ("ms_derive", ctypes.c_double), ("h0", ctypes.c_uint32),
-                ("rounds", ctypes.c_uint32), ("lcp_path", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("active_sum", ctypes.c_uint64), ("active_first", ctypes.c_uint64),
+                ("rounds", ctypes.c_uint32), ("lcp_path", ctypes.c_uint32), ("comm_direct", ctypes.c_uint32), ("active_sum", ctypes.c_uint64), ("active_first", ctypes.c_uint64),
                 ("launches", ctypes.c_uint64), ("device_bytes_peak", ctypes.c_uint64),
                 ("kernel", KernelStat * len(KERNEL_FAMILIES)), ("ms_h2d", ctypes.c_double),
                 ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),

@@ -400,6 +400,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     stats->shard_first = ctx->shard_first;
     stats->shard_count = ctx->shard_count;
     stats->comm_bytes_sent = ctx->comm != nullptr ? ctx->comm->bytes_sent : 0;
+    stats->comm_direct = (is_sharded(ctx) && ctx->comm->direct) ? 1 : 0;
     collect_kernel_stats(ctx, stats);
     stats->ms_doubling = 0;
   }
