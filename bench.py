@@ -365,9 +365,9 @@ def main():
                                        "suffixes, owner-routed rank requests per doubling round); per-rank figures "
                                        "below are rank 0's") if world > 1 else "single GPU",
                        "shard_count_rank0": last["shard_count"], "comm_bytes_sent_rank0": last["comm_bytes_sent"],
-                       "exchange": ("peer memory (CUDA IPC): partition pass stores into the owners' buffers, doubling "
-                                    "keys loaded from the owners' rank arrays") if last["comm_direct"] else
-                                   ("NCCL send/recv" if world > 1 else None),
+                       "exchange": ("partition pass fused with the all-to-all: stores into the owners' buffers through "
+                                    "CUDA IPC peer mappings; doubling-round rank requests/answers by NCCL send/recv")
+                                   if last["comm_direct"] else ("NCCL send/recv" if world > 1 else None),
                        "l2": "256 MiB flush buffer written between timed steps; working set >> 126 MB L2",
                        "timing": "sum of per-step CUDA-event times on the library stream; wall incl. flush "
                                  f"{wall_ms / args.steps:.2f} ms/step",

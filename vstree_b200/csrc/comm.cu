@@ -255,6 +255,7 @@ void comm_unmap_arenas(esa_ctx *ctx, esa_comm *comm)
   }
   cudaGetLastError();
   comm->direct = false;
+  comm->direct_loads = false;
 }
 
 void comm_map_arenas(esa_ctx *ctx, esa_comm *comm)
@@ -338,6 +339,15 @@ void comm_map_arenas(esa_ctx *ctx, esa_comm *comm)
     return;
   }
   comm->direct = true;
+  comm->direct_loads = true;
+  for (int r = 0; r < comm->nranks; r++)
+  {
+    comm->direct_loads = comm->direct_loads && all[r * ROW + 3] == (u64) getpid();
+  }
+  if (const char *e = getenv("ESA_COMM_DIRECT_LOADS"))
+  {
+    comm->direct_loads = atoi(e) != 0;
+  }
   comm->mapped_token = (u64) (uintptr_t) ctx->arena.base ^ ((u64) ctx->arena.capacity << 1);
 }
 

@@ -47,6 +47,10 @@ struct esa_comm
   // peer memory: the device arenas of all ranks, addressable from this rank's device (CUDA IPC between processes, plain
   // pointers inside one process).  Kernels then store into / load from other ranks' buffers directly over NVLink.
   bool direct = false;                       // arenas are mapped
+  // Random 4-byte LOADS from a peer arena are only used when all ranks live in one process: through a legacy
+  // CUDA IPC mapping they ran 85x slower on B200 (261 ms instead of 2.9 ms for 31 M loads over 4 GPUs; small pages in
+  // the importer's page tables), while the streaming STORES of the fused partition pass are unaffected.
+  bool direct_loads = false;
   char *peer_base[ESA_MAX_RANKS] = {nullptr};
   void *ipc_opened[ESA_MAX_RANKS] = {nullptr};  // mappings to close (NCCL transport)
   u64 mapped_token = 0;                      // identifies the local arena allocation the peers have mapped

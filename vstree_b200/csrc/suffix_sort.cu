@@ -1340,7 +1340,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u32 *slots_next = pos_b;
 
   // ---- 5. doubling, all ranks in lock step until no rank has an active suffix left
-  if (comm->direct)
+  if (comm->direct && comm->direct_loads)
   {
     // peer-memory variant: two barriers per round keep the remote loads of rank[] apart from the owners' updates
     u64 my_off = (u64) ((char *) rank - ar.base), offs[ESA_MAX_RANKS];
