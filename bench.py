@@ -257,8 +257,21 @@ def main():
         n *= world
     lib = load_library()
     k = int(lib.esa_recommended_prefixlength(sigma, n))
-    tis = np.ascontiguousarray(make_tis(args.workload, world)[0])
-    pinned = torch.from_numpy(tis).pin_memory()  # the e2e leg copies from pinned host memory
+    if world == 1:
+        tis = np.ascontiguousarray(make_tis(args.workload, world)[0])
+        pinned = torch.from_numpy(tis).pin_memory()  # the e2e leg copies from pinned host memory
+    else:
+        # the sequence is replicated: rank 0 generates it, the other ranks receive it (host memory of the box is
+        # finite: eight generators of a 3 Gbp sequence would not fit next to the pinned tables)
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            dev.copy_(torch.from_numpy(np.ascontiguousarray(make_tis(args.workload, world)[0])))
+        dist.broadcast(dev, src=0)
+        pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
+        pinned.copy_(dev)
+        del dev
+        torch.cuda.empty_cache()
+        tis = pinned.numpy()
     esa = Esa(local_rank)
     if world > 1:
         # the library's own NCCL communicator; its id travels over torch.distributed

@@ -184,6 +184,11 @@ void esa_group_abort(esa_group *group);   /* wakes ranks waiting in a collective
 void esa_group_reset(esa_group *group);   /* after all ranks returned from a failed call: group usable again */
 int esa_comm_attach_group(esa_ctx *ctx, esa_group *group, int rank, char *errbuf, size_t errlen);
 void esa_comm_detach(esa_ctx *ctx);
+/* Host logic of the exchange step, exposed for tests (no GPU needed): from every rank's per-bin suffix counts
+ * hist[r*stride + b] (256 bins = top 8 bits of the initial sort key) derive the bin -> rank table, what rank `me`
+ * sends to / receives from every rank, and where its run of every bin starts inside the owner's buffer. */
+int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, int me, uint8_t owner[256], uint64_t *send_cnt,
+                   uint64_t *recv_cnt, uint32_t start[256]);
 
 /* ---- suffix-to-text checks on the device (reference DEBUG checks: bese.c:355-528, cprsuf.c:66-95,
  * mkvprocess.c:672-763).  Runs on the tables left resident by the last esa_construct.  Returns 0 when

@@ -288,7 +288,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   ctx->d_spm = nullptr;
   ctx->d_hround = nullptr;
   ctx->lcp_work_estimate = 0;
-  if (ctx->sigma <= 4 && (demand & (ESA_LCPTAB | ESA_BWTTAB)))
+  if (ctx->sigma <= 4 && ((demand & (ESA_LCPTAB | ESA_BWTTAB)) || sharded))
   {
     pack_text(ctx);  // 2-bit text + special mask for the random suffix-start accesses of lcp and bwt
   }

@@ -7,12 +7,10 @@
 //   2. radix_scan_kernel   exclusive scan of each digit histogram -> global bin bases
 //   3. radix_pass_kernel   per digit ONE read + ONE write of the pairs: each 512-thread CTA takes a tile
 //                          (dynamic ticket), ranks its keys with warp match/ballot, learns the number of equal
-//                          digits in all earlier tiles by decoupled look-back over a status array (single 32-bit
-//                          word = 2 flag bits + 30 value bits), reorders the tile in shared memory and writes
+//                          digits in all earlier tiles by decoupled look-back over a status array (single 64-bit
+//                          word = 2 flag bits + 62 value bits), reorders the tile in shared memory and writes
 //                          each digit run coalesced.  Stable.
 // Algorithmic bytes: hist = n*sizeof(key); pass = 2*n*(sizeof(key)+sizeof(value)).
-// Inputs beyond 2^30-1 pairs are cut into parts so that look-back prefixes fit 30 bits; the per-part
-// histograms give every part its own bin bases, so parts are independent launches.
 #include "scan.cuh"
 
 namespace
@@ -42,9 +40,11 @@ constexpr int SORT_THREADS = ESA_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_ITEMS = 8;
-constexpr u32 STATUS_AGG = 1u << 30;
-constexpr u32 STATUS_PREFIX = 2u << 30;
-constexpr u32 STATUS_VALUE_MASK = (1u << 30) - 1;
+// look-back status word: 2 flag bits + 62 value bits (counts reach 2^32 - 2, so 32-bit words with 30 value bits
+// would force inputs beyond 2^30 pairs to be cut into separately histogrammed parts)
+constexpr u64 STATUS_AGG = (u64) 1 << 62;
+constexpr u64 STATUS_PREFIX = (u64) 2 << 62;
+constexpr u64 STATUS_VALUE_MASK = ((u64) 1 << 62) - 1;
 
 template <typename KeyT> struct SortTraits;
 template <> struct SortTraits<u32>
@@ -158,7 +158,7 @@ template <typename KeyT, bool HAS_VALS, int ITEMS, bool REMOTE = false>
 __global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
 radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin,
                   u32 *__restrict__ vout, u32 count, u32 shift, u32 mask, const u32 *__restrict__ base,
-                  volatile u32 *status, u32 *ticket, const RadixRemoteDst *__restrict__ remote = nullptr)
+                  volatile u64 *status, u32 *ticket, const RadixRemoteDst *__restrict__ remote = nullptr)
 {
   constexpr int TILE = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -233,7 +233,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     {
       valid_count -= (u32) TILE - tile_count;  // padding keys carry the largest digit
     }
-    status[(u64) tile * RADIX + tid] = (tile == 0 ? STATUS_PREFIX : STATUS_AGG) | valid_count;
+    status[(u64) tile * RADIX + tid] = (tile == 0 ? STATUS_PREFIX : STATUS_AGG) | (u64) valid_count;
   }
 #endif
   // ---- rank inside the warp: stable in (item, lane) order = memory order
@@ -333,10 +333,10 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #if !ESA_SORT_EARLY
     if (tile == 0)
     {
-      status[tid] = STATUS_PREFIX | cnt;
+      status[tid] = STATUS_PREFIX | (u64) cnt;
     } else
     {
-      status[(u64) tile * RADIX + tid] = STATUS_AGG | cnt;
+      status[(u64) tile * RADIX + tid] = STATUS_AGG | (u64) cnt;
     }
 #endif
     if (tile != 0)
@@ -344,19 +344,19 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       u32 t = tile - 1;
       while (true)
       {
-        const u32 s = status[(u64) t * RADIX + tid];
-        if ((s >> 30) == 0)
+        const u64 s = status[(u64) t * RADIX + tid];
+        if ((s >> 62) == 0)
         {
           continue;  // predecessor has not published yet
         }
-        excl += s & STATUS_VALUE_MASK;
-        if ((s >> 30) == 2)
+        excl += (u32) (s & STATUS_VALUE_MASK);
+        if ((s >> 62) == 2)
         {
           break;
         }
         t--;
       }
-      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (excl + cnt);
+      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (u64) (excl + cnt);
     }
     digit_start[tid] = dstart;
     gbase[tid] = base[tid] + excl - dstart;  // wraps modulo 2^32 by design
@@ -417,11 +417,10 @@ template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
          + 2 * RADIX * 4 + 16 * 4 + RADIX * 4 + (ESA_SORT_MATCH == 1 ? (size_t) SORT_WARPS * RADIX * 4 : 0);
 }
 
-template <typename KeyT> u64 part_items_max()
-{
-  constexpr u64 TILE = (u64) SORT_THREADS * SortTraits<KeyT>::ITEMS;
-  return (((u64) 1 << 30) - 1) / TILE * TILE;
-}
+// the whole input is one part: indices and counts are 32-bit (n < 2^32 is guaranteed by the API) and the look-back
+// words carry 62 value bits.  (Round 1 cut inputs beyond 2^30 pairs into parts with 30-bit status words; the parts of
+// passes after the first were histogrammed from the wrong slices -- found on the 3 Gbp configuration.)
+template <typename KeyT> u64 part_items_max() { return (u64) 1 << 32; }
 
 struct TempLayout
 {
@@ -446,7 +445,7 @@ template <typename KeyT> TempLayout temp_layout(u64 n)
   L.hist_off = take((size_t) L.parts * L.npass_max * RADIX * 4);
   L.ticket_off = take((size_t) L.parts * L.npass_max * 4);
   L.base_off = take((size_t) L.parts * L.npass_max * RADIX * 4);
-  L.status_off = take((size_t) tiles_per_part * RADIX * 4);
+  L.status_off = take((size_t) tiles_per_part * RADIX * 8);
   L.total = off;
   return L;
 }
@@ -470,7 +469,8 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
   }
   char *t = (char *) temp;
   u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off),
-      *status = (u32 *) (t + L.status_off);
+      *status_words = (u32 *) (t + L.status_off);
+  u64 *status = (u64 *) status_words;
   const u64 pim = part_items_max<KeyT>();
   cudaStream_t s = ctx->stream;
 
@@ -500,7 +500,7 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
       const u64 off = (u64) part * pim;
       const u32 cnt = (u32) (n - off < pim ? n - off : pim);
       const u32 tiles = (u32) div_up_u64(cnt, TILE);
-      ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 4, s)));
+      ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 8, s)));
       const u32 *pbase = base + ((u64) part * npass + p) * RADIX;
       u32 *ticket = tickets + (u64) part * npass + p;
       const double bytes = 2.0 * cnt * (sizeof(KeyT) + (has_vals ? 4 : 0));
@@ -543,6 +543,7 @@ template <typename KeyT> void set_smem_attr()
 
 void radix_sort_init()
 {
+
   set_smem_attr<u32>();
   set_smem_attr<u64>();
 }
@@ -570,7 +571,8 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
   }
   char *t = (char *) temp;
   u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off),
-      *status = (u32 *) (t + L.status_off);
+      *status_words = (u32 *) (t + L.status_off);
+  u64 *status = (u64 *) status_words;
   const u64 pim = part_items_max<u32>();
   cudaStream_t s = ctx->stream;
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
@@ -591,7 +593,7 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
     const u64 off = (u64) part * pim;
     const u32 cnt = (u32) (n - off < pim ? n - off : pim);
     const u32 tiles = (u32) div_up_u64(cnt, TILE);
-    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 4, s)));
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 8, s)));
     // algorithmic bytes: one local read, one store into peer memory
     ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 2.0 * cnt * 8,
                (radix_pass_kernel<u32, true, ITEMS, true><<<tiles, SORT_THREADS, smem, s>>>(

@@ -813,6 +813,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 //   All per-rank work is O(N/G) except the text upload; the exchange volume is 8 bytes per suffix once plus 8 bytes per
 //   active suffix and round.
 #include "comm.cuh"
+#include "textcmp.cuh"
 
 namespace
 {
@@ -850,6 +851,39 @@ __device__ __forceinline__ u32 initial_key_at(const u8 *__restrict__ tis, u64 q,
   }
   return code << 1;
 }
+
+// the same for a 4-letter alphabet from the 2-bit packed text: one 64-bit window and its special mask instead of h
+// byte loads (the packed window holds symbol i in bits [2i, 2i+2); the code wants symbol 0 in its top digit)
+__device__ __forceinline__ u32 initial_key_at_packed(const TextPacked2 &text, u64 q, u32 h)
+{
+  const u64 w = text.window(q);
+  const u32 m = text.mask_window(q);
+  const u32 d = m ? (u32) (__ffs((int) m) - 1) : 32u;
+  if (d == 0)
+  {
+    return SPECIAL_KEY;
+  }
+  u64 r = __brevll(w);
+  r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+  u32 code = (u32) (r >> (64 - 2 * h));
+  if (d < h)
+  {
+    code |= (1u << (2 * (h - d))) - 1;  // padded with the largest letter behind the special
+    return (code << 1) | 1u;
+  }
+  return code << 1;
+}
+
+struct KeyFromText
+{
+  const u8 *tis;
+  TextPacked2 packed;  // packed.pk == nullptr: byte path
+  KmerParams kp;
+  __device__ __forceinline__ u32 operator()(u64 q) const
+  {
+    return packed.pk != nullptr ? initial_key_at_packed(packed, q, kp.h) : initial_key_at(tis, q, kp);
+  }
+};
 
 __device__ __forceinline__ u32 owner_of_key(u32 key, const OwnerLut &lut)
 {
@@ -900,8 +934,8 @@ __global__ void spec_tail_kernel(const u32 *__restrict__ spec, u64 count, u64 fi
 
 // doubling, step 1: tag every active suffix with the owner of its h-successor (low key bits) and count per owner
 __global__ void __launch_bounds__(256)
-owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, const u8 *__restrict__ tis,
-                 KmerParams kp, OwnerLut lut, unsigned long long *__restrict__ owner_count)
+owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, KeyFromText keyof, OwnerLut lut,
+                 unsigned long long *__restrict__ owner_count)
 {
   __shared__ u32 sh[ESA_MAX_RANKS];
   if (threadIdx.x < ESA_MAX_RANKS)
@@ -912,7 +946,7 @@ owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 
   const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (t < m)
   {
-    const u32 o = owner_of_key(initial_key_at(tis, (u64) pos[t] + h, kp), lut);
+    const u32 o = owner_of_key(keyof((u64) pos[t] + h), lut);
     key[t] |= (u64) o;
     atomicAdd(&sh[o], 1u);
   }
@@ -950,14 +984,14 @@ struct PeerRanks
   const u32 *rank[ESA_MAX_RANKS];
 };
 __global__ void __launch_bounds__(256)
-gather_rank_peer_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, const u8 *__restrict__ tis,
-                        KmerParams kp, OwnerLut lut, PeerRanks peers)
+gather_rank_peer_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, KeyFromText keyof,
+                        OwnerLut lut, PeerRanks peers)
 {
   const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (t < m)
   {
     const u64 q = (u64) pos[t] + h;
-    const u32 o = owner_of_key(initial_key_at(tis, q, kp), lut);
+    const u32 o = owner_of_key(keyof(q), lut);
     key[t] |= (u64) __ldcv(peers.rank[o] + q);  // never cached: the owner rewrites it between rounds
   }
 }
@@ -965,6 +999,65 @@ gather_rank_peer_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 
 u32 grid_for(u64 count, u32 block) { return (u32) div_up_u64(count, block); }
 
 }  // namespace
+
+// Host logic of the exchange step.  hist[r*stride + b] = number of full suffixes of bin b (top 8 bits of the initial key)
+// that rank r classified.  Bins are dealt to the ranks in order, a bin going to the rank in whose quota (total / nranks)
+// its midpoint falls, so owners never decrease and a bin is never split (equal keys stay on one rank).  An owner's
+// receive buffer is laid out bin-major, then by sender: start[b] is where rank `me` must put its run of bin b.
+extern "C" int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, int me, uint8_t owner[256],
+                              uint64_t *send_cnt, uint64_t *recv_cnt, uint32_t start[256])
+{
+  if (hist == nullptr || nranks < 1 || nranks > ESA_MAX_RANKS || me < 0 || me >= nranks || stride < 256)
+  {
+    return ESA_ERR_ARGUMENT;
+  }
+  u64 global[256], total = 0, acc = 0;
+  for (int b = 0; b < 256; b++)
+  {
+    global[b] = 0;
+    for (int r = 0; r < nranks; r++)
+    {
+      global[b] += hist[(size_t) r * stride + b];
+    }
+    total += global[b];
+  }
+  int cur = 0;
+  for (int b = 0; b < 256; b++)
+  {
+    const u64 midpoint = acc + global[b] / 2;
+    while (cur + 1 < nranks && total > 0 && midpoint * (u64) nranks >= (u64) (cur + 1) * total)
+    {
+      cur++;
+    }
+    owner[b] = (u8) cur;
+    acc += global[b];
+  }
+  u64 run_of_owner[ESA_MAX_RANKS] = {0};
+  for (int r = 0; r < nranks; r++)
+  {
+    send_cnt[r] = recv_cnt[r] = 0;
+  }
+  for (int b = 0; b < 256; b++)
+  {
+    const int o = owner[b];
+    send_cnt[o] += hist[(size_t) me * stride + b];
+    u64 before_me = 0;
+    for (int r = 0; r < nranks; r++)
+    {
+      if (o == me)
+      {
+        recv_cnt[r] += hist[(size_t) r * stride + b];
+      }
+      if (r < me)
+      {
+        before_me += hist[(size_t) r * stride + b];
+      }
+    }
+    start[b] = (u32) (run_of_owner[o] + before_me);
+    run_of_owner[o] += global[b];
+  }
+  return ESA_OK;
+}
 
 void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
                          SortOutcome *outcome)
@@ -1041,6 +1134,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   constexpr size_t HROW = 258;
   std::vector<u64> hist_all((size_t) G * HROW);
   comm_exchange_host_u64(ctx, comm, local_hist, HROW, hist_all.data());
+  // splitters, counts per (sender, destination) and the place of my runs in the owners' buffers (host logic,
+  // exported as esa_shard_plan for the CPU tests)
   u64 global_hist[256];
   for (int b = 0; b < 256; b++)
   {
@@ -1050,39 +1145,9 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       global_hist[b] += hist_all[(size_t) r * HROW + b];
     }
   }
-  {
-    u64 total = 0, acc = 0;
-    for (int b = 0; b < 256; b++)
-    {
-      total += global_hist[b];
-    }
-    int r = 0;
-    for (int b = 0; b < 256; b++)
-    {
-      // a bin goes to the rank in whose quota its midpoint falls; owners never decrease
-      const u64 midpoint = acc + global_hist[b] / 2;
-      while (r + 1 < G && total > 0 && midpoint * (u64) G >= (u64) (r + 1) * total)
-      {
-        r++;
-      }
-      lut.owner[b] = (u8) r;
-      acc += global_hist[b];
-    }
-  }
-
-  // ---- 3a. counts: full suffixes per (sender, destination), side and special-initial suffixes per rank
   u64 send_cnt[ESA_MAX_RANKS] = {0}, send_off[ESA_MAX_RANKS], recv_cnt[ESA_MAX_RANKS] = {0}, recv_off[ESA_MAX_RANKS];
-  for (int b = 0; b < 256; b++)
-  {
-    send_cnt[lut.owner[b]] += local_hist[b];
-    if (lut.owner[b] == me)
-    {
-      for (int r = 0; r < G; r++)
-      {
-        recv_cnt[r] += hist_all[(size_t) r * HROW + b];
-      }
-    }
-  }
+  u32 h_start[256];
+  esa_shard_plan(hist_all.data(), HROW, G, me, lut.owner, send_cnt, recv_cnt, h_start);
   u64 side_cnt[ESA_MAX_RANKS], side_off[ESA_MAX_RANKS], spec_cnt[ESA_MAX_RANKS], spec_off[ESA_MAX_RANKS];
   u64 nside_tot = 0, nspec_tot = 0, mfull = 0, off = 0;
   for (int r = 0; r < G; r++)
@@ -1187,19 +1252,6 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       h_dst.vals[r] = comm_peer_ptr<u32>(ctx, comm, r, offs[2 * r + 1]);
     }
     memcpy(h_dst.owner, lut.owner, 256);
-    u32 h_start[256];
-    u64 run_of_owner[ESA_MAX_RANKS] = {0};
-    for (int b = 0; b < 256; b++)
-    {
-      const int o = lut.owner[b];
-      u64 before_me = 0;
-      for (int r = 0; r < me; r++)
-      {
-        before_me += hist_all[(size_t) r * HROW + b];
-      }
-      h_start[b] = (u32) (run_of_owner[o] + before_me);
-      run_of_owner[o] += global_hist[b];
-    }
     RadixRemoteDst *d_dst = reinterpret_cast<RadixRemoteDst *>(ar.alloc<char>(sizeof(RadixRemoteDst)));
     u32 *d_start = ar.alloc<u32>(256);
     CUDA_CHECK(cudaMemcpyAsync(d_dst, &h_dst, sizeof h_dst, cudaMemcpyHostToDevice, s));
@@ -1340,6 +1392,10 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u32 *slots_next = pos_b;
 
   // ---- 5. doubling, all ranks in lock step until no rank has an active suffix left
+  KeyFromText keyof;
+  keyof.tis = ctx->d_tis;
+  keyof.packed = TextPacked2{sigma == 4 ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
+  keyof.kp = kp;
   if (comm->direct && comm->direct_loads)
   {
     // peer-memory variant: two barriers per round keep the remote loads of rank[] apart from the owners' updates
@@ -1371,7 +1427,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       if (m > 0)
       {
         ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
-                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, hh, ctx->d_tis, kp, lut, peers)));
+                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, hh, keyof, lut, peers)));
         comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
         if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
         {
@@ -1439,7 +1495,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     {
       ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
       ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 28.0 * m,
-                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, ctx->d_tis, kp, lut, d_counts)));
+                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut, d_counts)));
       CUDA_CHECK(cudaMemcpyAsync(req_cnt, d_counts, G * sizeof(u64), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
