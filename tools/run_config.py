@@ -1,6 +1,6 @@
 """Builds one BASELINE.json configuration at full size on one GPU (or sharded over the visible GPUs, one thread per
 device), checks the tables with the device-side property checks and prints one JSON line with timings.
-    python tools/run_config.py c3|c4|c5|c2 [ngpus]"""
+    python tools/run_config.py c3|c4|c5|c2 [ngpus] [n override] [devices: "same" = all ranks on device 0]"""
 import json
 import os
 import sys
@@ -17,6 +17,9 @@ from vstree_b200.capi import EsaGroup  # noqa: E402
 workload = sys.argv[1]
 ngpus = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 desc, n, sigma, flag, gen, kw = bench.WORKLOADS[workload]
+if len(sys.argv) > 3 and int(sys.argv[3]) > 0:
+    bench.WORKLOADS[workload] = (desc, int(sys.argv[3]), sigma, flag, gen, kw)
+same_device = len(sys.argv) > 4 and sys.argv[4] == "same"
 t0 = time.time()
 tis = np.ascontiguousarray(bench.make_tis(workload)[0])
 n = len(tis)
@@ -37,7 +40,7 @@ if ngpus == 1:
         out["download_s"] = round(time.time() - t1, 2)
         stats = [st]
 else:
-    with EsaGroup(list(range(ngpus))) as grp:
+    with EsaGroup([0] * ngpus if same_device else list(range(ngpus))) as grp:
         grp.upload(tis, sigma)
         for rep in range(2):
             stats = grp.construct(k, bench.TABLES)

@@ -313,27 +313,13 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   // sum(active * depth / 32) explodes (long exact tandem arrays); then the text-order plcp path, whose cost does
   // not depend on the lcp values
   bool use_plcp = false;
-  if (want_lcp)
+  u32 halo = 0;
+  if (sharded)
   {
-    use_plcp = !sharded && (ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N));
-  }
-  if (use_plcp)
-  {
-    ctx->d_plcpv = ar.alloc<u32>(N + 64);
-    compute_plcp(ctx, ctx->d_plcpv);
-  }
-  CUDA_CHECK(cudaEventRecord(ctx->x.ev_c, s));
-  if (use_plcp)
-  {
-    finalize_tables(ctx, demand, ctx->d_plcpv);
-  } else if (!sharded)
-  {
-    finalize_tables_direct(ctx, demand, so.h0, N, 0, 0);
-  } else
-  {
-    // halo: the suffix in front of my range is the last entry of the nearest non-empty range before mine
+    // halo: the suffix in front of my range is the last entry of the nearest non-empty range before mine; the lcp
+    // path is chosen on the work estimate of all ranks together
     esa_comm *comm = ctx->comm;
-    u64 mine[2] = {ctx->shard_count, 0}, all[2 * ESA_MAX_RANKS];
+    u64 mine[3] = {ctx->shard_count, 0, ctx->lcp_work_estimate}, all[3 * ESA_MAX_RANKS];
     if (ctx->shard_count > 0)
     {
       u32 last = 0;
@@ -341,28 +327,61 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       CUDA_CHECK(cudaStreamSynchronize(s));
       mine[1] = last;
     }
-    comm_exchange_host_u64(ctx, comm, mine, 2, all);
-    u32 halo = 0;
-    for (int r = 0; r < comm->rank; r++)
+    comm_exchange_host_u64(ctx, comm, mine, 3, all);
+    u64 work = 0;
+    for (int r = 0; r < comm->nranks; r++)
     {
-      if (all[2 * r] > 0)
+      if (r < comm->rank && all[3 * r] > 0)
       {
-        halo = (u32) all[2 * r + 1];
+        halo = (u32) all[3 * r + 1];
       }
+      work += all[3 * r + 2];
     }
-    if (ctx->shard_count > 0)
+    ctx->lcp_work_estimate = work;
+  }
+  if (want_lcp)
+  {
+    use_plcp = ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N);
+  }
+  if (use_plcp)
+  {
+    ctx->d_plcpv = ar.alloc<u32>(N + 64);
+    if (sharded)
     {
-      finalize_tables_direct(ctx, demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
+      compute_plcp_sharded(ctx, ctx->comm, ctx->d_plcpv, so.h0, halo);
     } else
+    {
+      compute_plcp(ctx, ctx->d_plcpv);
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_c, s));
+  if (!sharded)
+  {
+    if (use_plcp)
+    {
+      finalize_tables(ctx, demand, ctx->d_plcpv, N, 0);
+    } else
+    {
+      finalize_tables_direct(ctx, demand, so.h0, N, 0, 0);
+    }
+  } else
+  {
+    if (ctx->shard_count == 0)
     {
       ctx->d_suf64 = (demand & ESA_SUFTAB) ? ar.alloc<u64>(4) : nullptr;
       ctx->d_bwt = (demand & ESA_BWTTAB) ? ar.alloc<u8>(4) : nullptr;
       ctx->d_lcp = want_lcp ? ar.alloc<u8>(4) : nullptr;
+    } else if (use_plcp)
+    {
+      finalize_tables(ctx, demand, ctx->d_plcpv, ctx->shard_count, ctx->shard_first);
+    } else
+    {
+      finalize_tables_direct(ctx, demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
     }
     // scalars of the whole table
-    u64 sc[2] = {ctx->maxbranchdepth, ctx->longest};
-    comm_exchange_host_u64(ctx, comm, sc, 2, all);
-    for (int r = 0; r < comm->nranks; r++)
+    u64 sc[2] = {ctx->maxbranchdepth, ctx->longest}, all[2 * ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, ctx->comm, sc, 2, all);
+    for (int r = 0; r < ctx->comm->nranks; r++)
     {
       ctx->maxbranchdepth = std::max(ctx->maxbranchdepth, all[2 * r]);
       ctx->longest = std::max(ctx->longest, all[2 * r + 1]);

@@ -309,10 +309,11 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
 
 // lcp.cu: V[i] = i + PLCP[i] for all text positions (ctx->d_plcpv)
 void compute_plcp(esa_ctx *ctx, u32 *d_v);
+void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 h0, u32 halo_prev);
 
 // derive.cu
 void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
-void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v);
+void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base);
 void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 int run_checks(esa_ctx *ctx, std::string &msg);

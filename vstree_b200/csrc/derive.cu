@@ -17,7 +17,7 @@ namespace
 __global__ void __launch_bounds__(FN_THREADS)
 finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, const u32 *__restrict__ v,
                 u8 *__restrict__ lcp8, u8 *__restrict__ bwt, u64 *__restrict__ suf64, u32 *__restrict__ tile_large,
-                unsigned long long *__restrict__ scalars)
+                unsigned long long *__restrict__ scalars, u64 index_base /* global index of local entry 0 */)
 {
   __shared__ u32 red[2][FN_THREADS / 32];
   const u64 tile_base = (u64) blockIdx.x * FN_TILE;
@@ -62,7 +62,7 @@ finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, c
       {
         if (s[q] == 0)
         {
-          scalars[1] = r0 + q;
+          scalars[1] = index_base + r0 + q;
         }
       }
       if (v != nullptr)
@@ -89,7 +89,7 @@ finalize_kernel(const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa, c
         }
         if (s == 0)
         {
-          scalars[1] = r;
+          scalars[1] = index_base + r;
         }
         if (bwt != nullptr)
         {
@@ -270,9 +270,11 @@ __global__ void check_sti1_kernel(u64 numofcodes, const u64 *__restrict__ bck, c
 
 }  // namespace
 
-void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
+void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base)
 {
-  const u64 N = ctx->n + 1;
+  // count entries of ctx->d_sa (the whole table on one GPU, this rank's range otherwise); d_v is the complete
+  // text-order plcp array in both cases
+  const u64 N = count;
   cudaStream_t s = ctx->stream;
   Arena &ar = ctx->arena;
   const bool want_lcp = d_v != nullptr;
@@ -280,15 +282,15 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_scalars, 0, 8 * sizeof(u64), s)));
   if (demand & ESA_SUFTAB)
   {
-    ctx->d_suf64 = ar.alloc<u64>(N);
+    ctx->d_suf64 = ar.alloc<u64>(N + 4);
   }
   if (demand & ESA_BWTTAB)
   {
-    ctx->d_bwt = ar.alloc<u8>(N);
+    ctx->d_bwt = ar.alloc<u8>(N + 4);
   }
   if (want_lcp)
   {
-    ctx->d_lcp = ar.alloc<u8>(N);
+    ctx->d_lcp = ar.alloc<u8>(N + 4);
   }
   const u32 tiles = (u32) div_up_u64(N, FN_TILE);
   u32 *tile_large = ar.alloc<u32>(tiles);
@@ -296,7 +298,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
                                      + (want_lcp ? 5.0 : 0.0));
   ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
              (finalize_kernel<<<tiles, FN_THREADS, 0, s>>>(ctx->d_tis, N, ctx->d_sa, d_v, ctx->d_lcp, ctx->d_bwt,
-                                                            ctx->d_suf64, tile_large, d_scalars)));
+                                                            ctx->d_suf64, tile_large, d_scalars, index_base)));
   if (want_lcp)
   {
     ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, LLV_SCAN_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
@@ -311,7 +313,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v)
     ctx->d_llv = ar.alloc<u64>(2 * ctx->nllv);
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, (double) N + 24.0 * ctx->nllv,
                (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, nullptr, ctx->d_lcp, tile_large,
-                                                              ctx->nllv, ctx->d_llv, 0)));
+                                                              ctx->nllv, ctx->d_llv, index_base)));
   }
 }
 

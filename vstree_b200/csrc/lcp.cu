@@ -8,6 +8,7 @@
 // reducible one copies the value of the nearest irreducible position on its left with one "last valid" scan.
 // Specials never match (bese.c:26-55), so a comparison stops at the first special on either side; the text
 // buffer is padded with 255 behind position n, which doubles as the sentinel.
+#include "comm.cuh"
 #include "scan.cuh"
 #include "textcmp.cuh"
 
@@ -196,7 +197,122 @@ plcp_fill_kernel(u32 *__restrict__ v, u64 N, const u32 *__restrict__ tile_carry)
   }
 }
 
+// ---- sharded builds: the irreducible values of a rank's OWN suffixes, visited in suffix-array order ----
+// v is the dense text-order array, pre-set to MARK; after a minimum all-reduce over the ranks it holds every irreducible
+// value and the text-order fill below completes it on every rank.  hround gives the doubling depth at which a slot
+// split from its predecessor: the comparison starts there (lcp.cu header of lcp_direct.cu).
+template <typename Text>
+__global__ void __launch_bounds__(256)
+plcp_irreducible_shard_kernel(Text text, u64 count, const u32 *__restrict__ sa, const u8 *__restrict__ hround, u32 h0,
+                              u64 index_base, u32 halo_prev, u32 *__restrict__ v)
+{
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= count)
+  {
+    return;
+  }
+  const u32 i = sa[r];
+  if (index_base + r == 0)
+  {
+    v[i] = i;  // lcp of the first suffix is 0 (bese.c:639)
+    return;
+  }
+  const u32 j = r > 0 ? sa[r - 1] : halo_prev;
+  const u32 ci = text.before(i), cj = text.before(j);
+  if (ci == cj && ci < ESA_WILDCARD)
+  {
+    return;  // reducible: takes the value of its left neighbour in text order
+  }
+  const u32 hr = hround != nullptr ? hround[r] : 0u;
+  const u32 lb = hr ? (h0 << (hr - 1)) : 0u;
+  v[i] = i + text.lcp(i, j, lb);
+}
+
+// value of the last irreducible position of every tile (MARK if none), for the text-order fill
+__global__ void __launch_bounds__(PL_THREADS) plcp_tile_last_kernel(const u32 *__restrict__ v, u64 N, u32 *__restrict__ tile_last)
+{
+  __shared__ u32 red_idx[PL_THREADS / 32];
+  __shared__ u32 red_val[PL_THREADS / 32];
+  const u64 tile_base = (u64) blockIdx.x * PL_TILE;
+  u32 last_idx = 0, last_val = MARK;
+#pragma unroll
+  for (int j = 0; j < PL_ITEMS; j++)
+  {
+    const int l = j * PL_THREADS + threadIdx.x;
+    const u64 i = tile_base + l;
+    const u32 val = i < N ? v[i] : MARK;
+    if (val != MARK)
+    {
+      last_idx = (u32) l + 1;
+      last_val = val;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const u32 oi = __shfl_down_sync(FULL_MASK, last_idx, o);
+    const u32 ov = __shfl_down_sync(FULL_MASK, last_val, o);
+    if (oi > last_idx)
+    {
+      last_idx = oi;
+      last_val = ov;
+    }
+  }
+  if (lane == 0)
+  {
+    red_idx[warp] = last_idx;
+    red_val[warp] = last_val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    u32 bi = 0, bv = MARK;
+    for (int w = 0; w < PL_THREADS / 32; w++)
+    {
+      if (red_idx[w] > bi)
+      {
+        bi = red_idx[w];
+        bv = red_val[w];
+      }
+    }
+    tile_last[blockIdx.x] = bv;
+  }
+}
+
 }  // namespace
+
+// sharded text-order plcp: every rank ends up with the complete V array
+void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 h0, u32 halo_prev)
+{
+  const u64 n = ctx->n, N = n + 1;
+  cudaStream_t s = ctx->stream;
+  const u32 tiles = (u32) div_up_u64(N, PL_TILE);
+  u32 *tile_last = ctx->arena.alloc<u32>(tiles);
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 4.0 * N, CUDA_CHECK(cudaMemsetAsync(d_v, 0xff, (N + 64) * sizeof(u32), s)));
+  const u64 count = ctx->shard_count;
+  if (count > 0)
+  {
+    const u32 grid = (u32) div_up_u64(count, 256);
+    if (ctx->d_pk != nullptr)
+    {
+      TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
+                 (plcp_irreducible_shard_kernel<TextPacked2><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
+                                                                                   h0, ctx->shard_first, halo_prev, d_v)));
+    } else
+    {
+      TextBytes text{ctx->d_tis};
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
+                 (plcp_irreducible_shard_kernel<TextBytes><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
+                                                                                 h0, ctx->shard_first, halo_prev, d_v)));
+    }
+  }
+  comm_allreduce_min_u32(ctx, comm, d_v, N);
+  ESA_LAUNCH(ctx, ESA_K_PLCP, 4.0 * N, (plcp_tile_last_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last)));
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (last_valid_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_last, tiles)));
+  ESA_LAUNCH(ctx, ESA_K_PLCP, 8.0 * N, (plcp_fill_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last)));
+}
 
 void compute_plcp(esa_ctx *ctx, u32 *d_v)
 {
