@@ -433,6 +433,53 @@ void oracle_inverse_suftab(const uint64_t *suftab, uint64_t n, uint64_t *sti)
 }
 
 /*
+ * Skip table.  reference: src/kurtz/mkskip.c:53-91 (makeskiptable): a stack of (depth, step) pairs walks the lcp
+ * table; an entry is popped by the first later lcp value that is strictly smaller and gets the index in front of
+ * it, entries that survive get totallength.  lcp values of 255 are read from the llv pairs in order.
+ * skiptable has n + 1 entries.  Returns 0, or -1 when memory is exhausted.
+ */
+int oracle_skiptable(const uint8_t *lcptab, const uint64_t *llv, uint64_t n, uint64_t *skiptable)
+{
+  uint64_t *depth = (uint64_t *) malloc((n + 2) * sizeof(uint64_t));
+  uint64_t *step = (uint64_t *) malloc((n + 2) * sizeof(uint64_t));
+  uint64_t top = 0, exception = 0;
+  if (depth == NULL || step == NULL)
+  {
+    free(depth);
+    free(step);
+    return -1;
+  }
+  depth[top] = 0;
+  step[top] = 0;
+  top++;
+  for (uint64_t i = 1; i <= n; i++)
+  {
+    uint64_t cur = lcptab[i];
+    if (cur == 255)
+    {
+      cur = llv[2 * exception + 1];
+      exception++;
+    }
+    while (cur < depth[top - 1])
+    {
+      skiptable[step[top - 1]] = i - 1;
+      top--;
+    }
+    depth[top] = cur;
+    step[top] = i;
+    top++;
+  }
+  while (top > 0)
+  {
+    skiptable[step[top - 1]] = n;
+    top--;
+  }
+  free(depth);
+  free(step);
+  return 0;
+}
+
+/*
  * Property checks restating the reference's DEBUG invariants; return 0 when the tables are consistent,
  * otherwise a positive code naming the first violated property.
  *   1: suftab is not a permutation of 0..n            reference: src/Mkvtree/bese.c:355-451 (checksuftab)

@@ -33,20 +33,25 @@ def main():
                 f.write(fasta)
             args = [flag, "-pl"] + ([str(pl)] if pl else []) + ["-tis", "-ois", "-suf", "-lcp", "-bwt", "-bck", "-sti1"]
             rc, out, err, files = ou.run_mkvtree(ou.REF_MKVTREE, path, args)
+            # the skip table in a second run (-sti1 suppresses .suf, -skp needs it: mkvtree.c:376,474-475)
+            args2 = [flag, "-pl"] + ([str(pl)] if pl else []) + ["-suf", "-lcp", "-skp"]
+            rc2, out2, err2, files2 = ou.run_mkvtree(ou.REF_MKVTREE, path, args2)
         assert rc == 0, (name, err)
+        assert rc2 == 0, (name, err2)
+        files["skp"] = files2["skp"]
         assert files["tis"] == tis.tobytes(), f"{name}: FASTA round trip does not reproduce tis"
         prj = ou.parse_prj(files["prj"].decode())
         entry = {"name": name, "sigma": sigma, "flag": flag, "n": int(len(tis)), "prefixlength": prj["prefixlength"],
                  "longest": prj["longest"], "maxbranchdepth": prj["maxbranchdepth"],
                  "largelcpvalues": prj["largelcpvalues"], "specialcharacters": prj["specialcharacters"],
                  "specialranges": prj["specialranges"], "numofsequences": prj["numofsequences"],
-                 "sha": {k: sha(files[k]) for k in ("tis", "ois", "suf", "lcp", "llv", "bwt", "bck", "sti1", "des", "sds")
+                 "sha": {k: sha(files[k]) for k in ("tis", "ois", "suf", "lcp", "llv", "bwt", "bck", "sti1", "des", "sds", "skp")
                          if k in files}}
         if "ssp" in files:
             entry["sha"]["ssp"] = sha(files["ssp"])
         if len(tis) <= 64:
             entry["tables"] = {k: np.frombuffer(files[k], ou.TABLE_DTYPES[k]).tolist()
-                               for k in ("suf", "lcp", "llv", "bwt", "bck", "sti1")}
+                               for k in ("suf", "lcp", "llv", "bwt", "bck", "sti1", "skp")}
         cases.append(entry)
         print(name, entry["n"], "k=%d" % entry["prefixlength"], "maxlcp=%d" % entry["maxbranchdepth"],
               "llv=%d" % entry["largelcpvalues"])

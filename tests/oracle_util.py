@@ -37,6 +37,8 @@ def oracle_lib():
         lib.oracle_check_tables.restype = ctypes.c_int
         lib.oracle_check_tables.argtypes = [u8p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, u64p, u8p, u64p,
                                             ctypes.c_uint64, u8p, u64p, u8p]
+        lib.oracle_skiptable.restype = ctypes.c_int
+        lib.oracle_skiptable.argtypes = [u8p, u64p, ctypes.c_uint64, u64p]
         lib.oracle_numofcodes.restype = ctypes.c_uint64
         lib.oracle_numofcodes.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         lib.oracle_recommendedprefixlength.restype = ctypes.c_uint32
@@ -76,6 +78,19 @@ def oracle_build(tis, numofchars, prefixlength, bck=True, sti1=True):
             "maxbranchdepth": maxbd.value, "longest": longest.value, "largelcpvalues": nllv.value}
 
 
+def oracle_skiptable(lcp, llv):
+    """Skip table from the oracle's lcp/llv (restates src/kurtz/mkskip.c)."""
+    lib = oracle_lib()
+    lcp = np.ascontiguousarray(lcp, np.uint8)
+    llv = np.ascontiguousarray(np.concatenate([llv, np.zeros(2, np.uint64)]), np.uint64)
+    n = len(lcp) - 1
+    skp = np.zeros(n + 1, np.uint64)
+    rc = lib.oracle_skiptable(_p(lcp, ctypes.c_uint8), _p(llv, ctypes.c_uint64), n, _p(skp, ctypes.c_uint64))
+    if rc != 0:
+        raise RuntimeError("oracle_skiptable failed")
+    return skp
+
+
 def oracle_check(tis, numofchars, prefixlength, tables):
     """DEBUG-invariant property check (0 = consistent)."""
     lib = oracle_lib()
@@ -100,7 +115,7 @@ def have_ref():
 
 
 TABLE_DTYPES = {"suf": np.uint64, "lcp": np.uint8, "llv": np.uint64, "bwt": np.uint8, "bck": np.uint64,
-                "sti1": np.uint8, "tis": np.uint8, "ois": np.uint8, "sds": np.uint64, "ssp": np.uint64}
+                "sti1": np.uint8, "tis": np.uint8, "ois": np.uint8, "sds": np.uint64, "ssp": np.uint64, "skp": np.uint64}
 
 
 def parse_prj(text):

@@ -147,6 +147,10 @@ def test_existing_index_is_removed(tmp_path):
     (["-db", "in.fna", "-dna", "-tis", "-pl", "1024"], {"in.fna": DNA}),
     (["-db", "in.fna", "-dna", "-tis", "-pl", "9"], {"in.fna": DNA}),
     (["-db", "in.fna", "-dna", "-tis", "stray"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-skp"], {"in.fna": DNA}),                          # -skp requires -lcp and -suf
+    (["-db", "in.fna", "-dna", "-lcp", "-skp"], {"in.fna": DNA}),
+    (["-db", "in.fna", "-dna", "-allout"], {"in.fna": DNA}),                       # -allout requires -pl
+    (["-db", "in.fna", "-dna", "-pl", "-allout", "-tis"], {"in.fna": DNA}),
     (["-db", "in.fna", "-protein", "-tis"], {"in.fna": DNA}),                      # lower-case letters are illegal
     (["-db", "in.fna", "-dna", "-tis"], {"in.fna": b">a\nACGT\n>b\n\n>c\nAC\n"}),  # empty sequence
     (["-db", "in.fna", "-dna", "-tis"], {"in.fna": b">a\nAC>GT\n"}),               # '>' inside a line
@@ -194,6 +198,10 @@ def test_host_tables_on_reference_fixtures(tmp_path, refdata):
     (["-db", "in.fna", "-dna", "-v"], DNA),                                        # sorts, writes nothing
     (["-db", "in.fna", "-dna", "-pl", "-bwt", "-indexname", "x"], DNA),
     (["-db", "in.fna", "-protein", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-v"], PROT),
+    (["-db", "in.fna", "-dna", "-pl", "-suf", "-lcp", "-skp", "-v"], DNA),         # skip table, written last
+    (["-db", "in.fna", "-dna", "-suf", "-lcp", "-skp"], DNA),                      # without -pl
+    (["-db", "in.fna", "-dna", "-pl", "-allout", "-v"], DNA),
+    (["-db", "in.fna", "-protein", "-pl", "1", "-allout", "-v"], PROT),
 ])
 def test_full_cli_small(tmp_path, args, data):
     compare(tmp_path, {"in.fna": data}, args)
@@ -209,6 +217,9 @@ def test_full_cli_golden_inputs(tmp_path, name):
     kind = "dna" if flag == "-dna" else "protein"
     compare(tmp_path, {"g.fa": synth.to_fasta(tis, kind)},
             ["-db", "g.fa", flag, "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-v"])
+    for fn in os.listdir(tmp_path):
+        shutil.rmtree(tmp_path / fn)
+    compare(tmp_path, {"g.fa": synth.to_fasta(tis, kind)}, ["-db", "g.fa", flag, "-pl", "-allout", "-v"])
 
 
 @needs_ref

@@ -112,6 +112,28 @@ def test_golden_cases(esa, name):
     esa.check()
 
 
+@pytest.mark.parametrize("name", list(CASES.keys()))
+def test_skip_table_golden_cases(esa, name):
+    """-skp (src/kurtz/mkskip.c:53-91): byte parity with the reference's .skp and with the C restatement, on both
+    lcp paths (the exact large values come from lcpfull on the direct path and from the plcp array otherwise)."""
+    g = golden()[name]
+    tis, sigma = make_input(name)
+    got, _ = esa.build(tis, sigma, g["prefixlength"], tables=("suf", "lcp", "skp"))
+    want = ou.oracle_build(tis, sigma, g["prefixlength"])
+    skp = ou.oracle_skiptable(want["lcp"], want["llv"])
+    assert np.array_equal(got["skp"], skp), first_diff(got["skp"], skp)
+    assert sha(got["skp"]) == g["sha"]["skp"]
+    assert np.array_equal(got["suf"], want["suf"]) and np.array_equal(got["lcp"], want["lcp"])
+
+
+def test_skip_table_alone_forces_lcp(esa):
+    tis = synth.repeat_rich_dna(300000, seed=5, copies=10, divergence=0.01, tandem_frac=0.05, tandem_len=3000)
+    want = ou.oracle_build(tis, 4, 6)
+    skp = ou.oracle_skiptable(want["lcp"], want["llv"])
+    got, _ = esa.build(tis, 4, 6, tables=("skp",))
+    assert np.array_equal(got["skp"], skp) and np.array_equal(got["lcp"], want["lcp"]) and got["suf"] is None
+
+
 def test_kat_survey(esa):
     tis = np.array([0, 1, 2, 3, 254, 0, 1, 2, 255, 0, 1, 2, 3, 255, 254, 254, 0, 1], np.uint8)
     got, _ = esa.build(tis, 4, 1, tables=ALL)

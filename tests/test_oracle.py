@@ -132,3 +132,8 @@ def test_against_committed_goldens(case):
     assert t["longest"] == case["longest"]
     assert t["maxbranchdepth"] == case["maxbranchdepth"]
     assert t["largelcpvalues"] == case["largelcpvalues"]
+    # skip table (src/kurtz/mkskip.c), pinned by the reference's own .skp
+    skp = ou.oracle_skiptable(t["lcp"], t["llv"])
+    assert sha(skp) == case["sha"]["skp"], "skp"
+    if "tables" in case:
+        assert skp.tolist() == case["tables"]["skp"]

@@ -182,6 +182,7 @@ class Esa:
                 "llv": arr(res.llv, 2 * res.nllv, np.uint64) if res.lcptab else None,
                 "bwt": arr(res.bwttab, N, np.uint8), "bck": arr(res.bcktab, 2 * res.numofcodes, np.uint64),
                 "sti1": arr(res.stitab1, N, np.uint8), "sti": arr(res.stitab, N, np.uint64),
+                "skp": arr(res.skiptab, N, np.uint64),
                 "maxbranchdepth": int(res.maxbranchdepth), "longest": int(res.longest),
                 "largelcpvalues": int(res.nllv), "numofcodes": int(res.numofcodes),
                 "shard_first": int(res.shard_first), "shard_count": int(res.shard_count)}

@@ -232,6 +232,10 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   {
     demand |= ESA_LCPTAB | ESA_BCKTAB;  // reference: mkvtree.c:376
   }
+  if (demand & ESA_SKPTAB)
+  {
+    demand |= ESA_LCPTAB;  // the skip table is derived from the lcp table (mkvprocess.c:767-815)
+  }
   if ((demand & (ESA_BCKTAB | ESA_STI1TAB)) && prefixlength == 0)
   {
     esa_throw(ESA_ERR_ARGUMENT, "option -bck requires option -pl");  // reference: mkvtree.c:470-473
@@ -255,7 +259,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   ctx->d_suf64 = nullptr;
   ctx->d_lcp = ctx->d_bwt = ctx->d_sti1 = nullptr;
   ctx->d_bck = ctx->d_llv = ctx->d_sti64 = ctx->d_skp = nullptr;
-  ctx->d_plcpv = nullptr;
+  ctx->d_plcpv = ctx->d_lcpfull = nullptr;
   ctx->nllv = ctx->maxbranchdepth = ctx->longest = 0;
   ctx->prof.reset();
   ctx->prof.enabled = stats != nullptr;
@@ -391,6 +395,10 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   {
     compute_sti1(ctx, prefixlength);
   }
+  if (demand & ESA_SKPTAB)
+  {
+    compute_skp(ctx, use_plcp ? ctx->d_plcpv : nullptr, ctx->d_lcpfull);
+  }
   if (demand & ESA_STITAB)
   {
     widen_isa(ctx);
@@ -481,6 +489,11 @@ u64 do_download(FullCtx *ctx, esa_result *out)
   if (ctx->d_sti64 != nullptr)
   {
     out->stitab = download_table(ctx, ctx->d_sti64, N);
+    bytes += 8 * N;
+  }
+  if (ctx->d_skp != nullptr)
+  {
+    out->skiptab = download_table(ctx, ctx->d_skp, N);
     bytes += 8 * N;
   }
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -200,6 +200,7 @@ struct esa_ctx
   u64 *d_sti64 = nullptr;  // [N]
   u64 *d_skp = nullptr;    // [N]
   u32 *d_plcpv = nullptr;  // [N] V[i] = i + PLCP[i]
+  u32 *d_lcpfull = nullptr;  // direct lcp path: exact values of the entries whose lcp8 is 255
   u64 nllv = 0, maxbranchdepth = 0, longest = 0;
   // sharded build: this rank holds suffix-array entries [shard_first, shard_first + shard_count) in d_sa, d_suf64,
   // d_lcp, d_bwt, d_hround (all indexed from 0); one GPU: [0, n+1)
@@ -316,4 +317,5 @@ void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base);
 void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
+void compute_skp(esa_ctx *ctx, const u32 *d_v, const u32 *d_lcpfull);  // skp.cu
 int run_checks(esa_ctx *ctx, std::string &msg);

@@ -251,6 +251,7 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 ind
   {
     ctx->d_lcp = ar.alloc<u8>(N + 4);
     lcpfull = ar.alloc<u32>(N + 4);
+    ctx->d_lcpfull = lcpfull;
   }
   const u32 tiles = (u32) div_up_u64(N, FN_TILE);
   u32 *tile_large = ar.alloc<u32>(tiles);

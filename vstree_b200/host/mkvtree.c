@@ -11,7 +11,7 @@
  * The host keeps alphabet transformation and file I/O; there is no CPU implementation of the sort behind it:
  * without a GPU the program fails.
  *
- * Not supported (reported as errors): -q, -rev, -cpl, -maxdepth, -skp/-allout, GenBank/EMBL/SwissProt input,
+ * Not supported (reported as errors): -q, -rev, -cpl, -maxdepth, GenBank/EMBL/SwissProt input,
  * input without one of -dna/-protein/-smap.
  */
 #define _GNU_SOURCE
@@ -311,7 +311,7 @@ static int parseoptions(Options *o, int argc, char **argv)
   }
   /* what this build does not do (see the header comment) */
   {
-    static const int unsupported[] = {OPTQ, OPTREV, OPTCPL, OPTMAXDEPTH, OPTSKP, OPTALLOUT};
+    static const int unsupported[] = {OPTQ, OPTREV, OPTCPL, OPTMAXDEPTH};
     for (size_t i = 0; i < sizeof unsupported / sizeof unsupported[0]; i++)
     {
       if (o->isset[unsupported[i]])
@@ -1196,7 +1196,7 @@ int main(int argc, char **argv)
         goto failure;
       }
     }
-    builddemand = ESA_SUFTAB | (opt.demand & (ESA_BWTTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB));
+    builddemand = ESA_SUFTAB | (opt.demand & (ESA_BWTTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB));
     if (esa_build(ctx, ms.tis, ms.totallength, numofchars, k, builddemand, &res, &stats, err, sizeof err) != 0)
     {
       fail("%s", err);
@@ -1308,6 +1308,13 @@ int main(int argc, char **argv)
       fputs("L\nV\nI\nF\nK\nR\nE\nD\nA\nG\nS\nT\nN\nQ\nY\nW\nP\nH\nM\nC\nXUBZ*-\n", fp);
     }
     fclose(fp);
+  }
+  /* makeskptab runs last in the reference (src/Mkvtree/mkvprocess.c:767-815, called at :1075 after the project
+     and alphabet files are out), so the -v transcript names .skp last */
+  if ((opt.demand & ESA_SKPTAB) && res.skiptab != NULL
+      && writetable(opt.indexname, "skp", res.skiptab, sizeof(uint64_t), ms.totallength + 1, 1) != 0)
+  {
+    goto failure;
   }
   if (verbose)
   {
