@@ -15,7 +15,7 @@ all: $(LIBDIR)/libvstree_b200.so $(BINDIR)/mkvtree
 # the drop-in host driver: plain C, links the C ABI only
 $(BINDIR)/mkvtree: vstree_b200/host/mkvtree.c include/vstree_b200.h $(LIBDIR)/libvstree_b200.so
 	@mkdir -p $(BINDIR)
-	gcc -O2 -std=gnu99 -Wall -Wextra -Iinclude -o $@ vstree_b200/host/mkvtree.c -L$(LIBDIR) -lvstree_b200 -lz \
+	gcc -O2 -std=gnu99 -Wall -Wextra -Iinclude -o $@ vstree_b200/host/mkvtree.c -L$(LIBDIR) -lvstree_b200 -lz -lpthread \
 	    -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)

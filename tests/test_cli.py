@@ -224,6 +224,31 @@ def test_full_cli_golden_inputs(tmp_path, name):
 
 @needs_ref
 @pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 5])
+@pytest.mark.parametrize("name", ["dna_specials_50k", "human_like_400k", "protein_200k", "kat_survey"])
+def test_full_cli_several_gpus_one_index(tmp_path, monkeypatch, name, ranks):
+    """MKVTREE_GPUS: the driver's ranks build the ranges of ONE index (here all on device 0); the files are the
+    reference's byte for byte."""
+    monkeypatch.setenv("MKVTREE_GPUS", str(ranks))
+    monkeypatch.setenv("MKVTREE_GPUS_ONE_DEVICE", "1")
+    tis, sigma = make_input(name)
+    flag = CASES[name][2]
+    kind = "dna" if flag == "-dna" else "protein"
+    compare(tmp_path, {"g.fa": synth.to_fasta(tis, kind)},
+            ["-db", "g.fa", flag, "-pl", "-suf", "-lcp", "-bwt", "-bck", "-tis", "-ois", "-v"])
+
+
+@pytest.mark.gpu
+def test_cli_several_gpus_refuses_sti1(tmp_path, monkeypatch):
+    monkeypatch.setenv("MKVTREE_GPUS", "2")
+    monkeypatch.setenv("MKVTREE_GPUS_ONE_DEVICE", "1")
+    (tmp_path / "in.fna").write_bytes(DNA)
+    rc, out, err, files = run(OURS, ["-db", "in.fna", "-dna", "-pl", "-sti1"], str(tmp_path))
+    assert rc == 1 and "sharded build" in err
+
+
+@needs_ref
+@pytest.mark.gpu
 def test_full_cli_multifile_gz(tmp_path):
     compare(tmp_path, {"a.fna.gz": gzip.compress(DNA), "b.fna": b">only\nTTTTGGGGCCCCAAAANNNNACGT\n"},
             ["-db", "a.fna.gz", "b.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-tis", "-indexname", "two",

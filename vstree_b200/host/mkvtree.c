@@ -18,6 +18,7 @@
 #include <ctype.h>
 #include <errno.h>
 #include <limits.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -1027,8 +1028,65 @@ static int writetable(const char *indexname, const char *suffix, const void *dat
   return 0;
 }
 
+/* ---- several GPUs build ONE index (include/vstree_b200.h, "sharded builds", transport B) ------------------------
+ * MKVTREE_GPUS=G makes the driver start G threads, one per device, which build the G ranges of the suffix array
+ * together; the ranges are written to the index files one after the other, so the files are the same as with one
+ * GPU.  (MKVTREE_GPUS_ONE_DEVICE=1 puts all ranks on device MKVTREE_GPU: for tests on a single-GPU machine.) */
+#define MAXGPUS 16
+typedef struct
+{
+  esa_ctx *ctx;
+  const uint8_t *tis;
+  uint64_t n;
+  uint32_t numofchars, prefixlength, demand;
+  esa_result res;
+  esa_stats stats;
+  int rc;
+  char err[512];
+} Rankjob;
+
+static void *rankmain(void *arg)
+{
+  Rankjob *job = (Rankjob *) arg;
+  job->rc = esa_build(job->ctx, job->tis, job->n, job->numofchars, job->prefixlength, job->demand, &job->res,
+                      &job->stats, job->err, sizeof job->err);
+  return NULL;
+}
+
+/* one table, all ranges in rank order; `which` picks the table pointer, counts are per range */
+static int writeranges(const char *indexname, const char *suffix, FILE *fp, Rankjob *jobs, int njobs, size_t size,
+                       int which)
+{
+  int r;
+  if (fp == NULL && (fp = openthefile(indexname, suffix, 1)) == NULL)
+  {
+    return -1;
+  }
+  for (r = 0; r < njobs; r++)
+  {
+    const esa_result *res = &jobs[r].res;
+    const void *data = which == 0 ? (const void *) res->lcptab : which == 1 ? (const void *) res->llv
+                     : which == 2 ? (const void *) res->suftab : (const void *) res->bwttab;
+    const uint64_t count = which == 1 ? res->nllv : res->shard_count;
+    if (count > 0 && fwrite(data, size, count, fp) != count)
+    {
+      fclose(fp);
+      return fail("cannot write %lu items of size %lu: errormsg=\"%s\"", (unsigned long) count, (unsigned long) size,
+                  strerror(errno));
+    }
+  }
+  if (fclose(fp) != 0)
+  {
+    return fail("cannot close file \"%s.%s\"", indexname, suffix);
+  }
+  return 0;
+}
+
 int main(int argc, char **argv)
 {
+  Rankjob jobs[MAXGPUS];
+  esa_group *group = NULL;
+  int njobs = 1;
   Options opt;
   Alphabet alpha;
   Multiseq ms;
@@ -1188,30 +1246,94 @@ int main(int argc, char **argv)
     {
       say("sorting suffixes");
     }
+    builddemand = ESA_SUFTAB | (opt.demand & (ESA_BWTTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB));
     {
-      const char *dev = getenv("MKVTREE_GPU");
-      if (esa_init(&ctx, dev != NULL ? atoi(dev) : 0, err, sizeof err) != 0)
+      const char *dev = getenv("MKVTREE_GPU"), *many = getenv("MKVTREE_GPUS"), *one = getenv("MKVTREE_GPUS_ONE_DEVICE");
+      const int first = dev != NULL ? atoi(dev) : 0;
+      int r;
+      njobs = many != NULL ? atoi(many) : 1;
+      if (njobs < 1 || njobs > MAXGPUS)
+      {
+        fail("MKVTREE_GPUS must be in the range 1..%d", MAXGPUS);
+        goto failure;
+      }
+      memset(jobs, 0, sizeof jobs);
+      if (njobs > 1 && esa_group_create(&group, njobs, err, sizeof err) != 0)
       {
         fail("%s", err);
         goto failure;
       }
-    }
-    builddemand = ESA_SUFTAB | (opt.demand & (ESA_BWTTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB));
-    if (esa_build(ctx, ms.tis, ms.totallength, numofchars, k, builddemand, &res, &stats, err, sizeof err) != 0)
-    {
-      fail("%s", err);
-      goto failure;
+      for (r = 0; r < njobs; r++)
+      {
+        const int device = (one != NULL && atoi(one) != 0) ? first : first + r;
+        if (esa_init(&jobs[r].ctx, device, err, sizeof err) != 0
+            || (njobs > 1 && esa_comm_attach_group(jobs[r].ctx, group, r, err, sizeof err) != 0))
+        {
+          fail("%s", err);
+          goto failure;
+        }
+        jobs[r].tis = ms.tis;
+        jobs[r].n = ms.totallength;
+        jobs[r].numofchars = numofchars;
+        jobs[r].prefixlength = k;
+        jobs[r].demand = builddemand;
+      }
+      if (njobs == 1)
+      {
+        rankmain(&jobs[0]);
+      } else
+      {
+        pthread_t threads[MAXGPUS];
+        for (r = 0; r < njobs; r++)
+        {
+          if (pthread_create(&threads[r], NULL, rankmain, &jobs[r]) != 0)
+          {
+            fail("cannot start the thread of GPU %d", r);
+            esa_group_abort(group);
+            njobs = r;
+            break;
+          }
+        }
+        for (r = 0; r < njobs; r++)
+        {
+          pthread_join(threads[r], NULL);
+        }
+      }
+      for (r = 0; r < njobs; r++)
+      {
+        if (jobs[r].rc != 0 && jobs[r].rc != ESA_ERR_COMM)
+        {
+          fail("%s", jobs[r].err);  /* the rank that failed first; the others only report that a peer failed */
+          goto failure;
+        }
+      }
+      for (r = 0; r < njobs; r++)
+      {
+        if (jobs[r].rc != 0)
+        {
+          fail("%s", jobs[r].err);
+          goto failure;
+        }
+      }
+      ctx = jobs[0].ctx;
+      res = jobs[0].res;       /* bcktab, longest, maxbranchdepth are complete on every rank */
+      stats = jobs[0].stats;
+      for (r = 1; r < njobs; r++)
+      {
+        res.nllv += jobs[r].res.nllv;
+        stats.d2h_bytes += jobs[r].stats.d2h_bytes;
+        if (jobs[r].stats.device_bytes_peak > stats.device_bytes_peak)
+        {
+          stats.device_bytes_peak = jobs[r].stats.device_bytes_peak;
+        }
+      }
     }
     if (lcpfp != NULL)
     {
-      if (fwrite(res.lcptab, 1, ms.totallength + 1, lcpfp) != ms.totallength + 1 || fclose(lcpfp) != 0)
-      {
-        fail("cannot write %lu items of size 1: errormsg=\"%s\"", (unsigned long) (ms.totallength + 1),
-             strerror(errno));
-        goto failure;
-      }
+      FILE *fp = lcpfp;
       lcpfp = NULL;
-      if (writetable(opt.indexname, "llv", res.llv, sizeof(esa_pairuint), res.nllv, 1) != 0)
+      if (writeranges(opt.indexname, "lcp", fp, jobs, njobs, 1, 0) != 0
+          || writeranges(opt.indexname, "llv", NULL, jobs, njobs, sizeof(esa_pairuint), 1) != 0)
       {
         goto failure;
       }
@@ -1221,8 +1343,7 @@ int main(int argc, char **argv)
     {
       goto failure;
     }
-    if ((opt.demand & ESA_SUFTAB)
-        && writetable(opt.indexname, "suf", res.suftab, sizeof(uint64_t), ms.totallength + 1, 1) != 0)
+    if ((opt.demand & ESA_SUFTAB) && writeranges(opt.indexname, "suf", NULL, jobs, njobs, sizeof(uint64_t), 2) != 0)
     {
       goto failure;
     }
@@ -1230,7 +1351,7 @@ int main(int argc, char **argv)
     {
       goto failure;
     }
-    if ((opt.demand & ESA_BWTTAB) && writetable(opt.indexname, "bwt", res.bwttab, 1, ms.totallength + 1, 1) != 0)
+    if ((opt.demand & ESA_BWTTAB) && writeranges(opt.indexname, "bwt", NULL, jobs, njobs, 1, 3) != 0)
     {
       goto failure;
     }
@@ -1326,8 +1447,13 @@ int main(int argc, char **argv)
   }
   if (ctx != NULL)
   {
-    esa_free(ctx, &res);
-    esa_shutdown(ctx);
+    int r;
+    for (r = 0; r < njobs; r++)
+    {
+      esa_free(jobs[r].ctx, &jobs[r].res);
+      esa_shutdown(jobs[r].ctx);
+    }
+    esa_group_destroy(group);
   }
   return EXIT_SUCCESS;
 
