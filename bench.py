@@ -382,6 +382,9 @@ def main():
                                     "CUDA IPC peer mappings; doubling-round rank requests/answers by NCCL send/recv")
                                    if last["comm_direct"] else ("NCCL send/recv" if world > 1 else None),
                        "l2": "256 MiB flush buffer written between timed steps; working set >> 126 MB L2",
+                       "e2e_path": "esa_build: pinned tis H2D, build, D2H of suf/lcp/llv/bwt into pinned tables; the "
+                                   "suftab crosses PCIe as 32-bit entries from the moment the sort is done and is "
+                                   "widened to the reference's 8-byte Uint by host threads when >= 6 are free per rank",
                        "timing": "sum of per-step CUDA-event times on the library stream; wall incl. flush "
                                  f"{wall_ms / args.steps:.2f} ms/step",
                        "h0": last["h0"], "doubling_rounds": last["rounds"], "active_first": last["active_first"],

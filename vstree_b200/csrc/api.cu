@@ -3,8 +3,11 @@
 // Mirrors the call sequence of the reference's mkvtreeprocess (src/Mkvtree/mkvprocess.c:976-1060):
 // suffix sort (+ inline lcp) -> llv -> bck -> longest -> suf -> sti1 -> bwt, but every table is produced on the
 // device; the host only moves bytes.
+#include <emmintrin.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include <algorithm>
 
@@ -111,9 +114,67 @@ struct PinnedPool
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// esa_build only: the 64-bit suftab is the bulk of the device-to-host traffic (8 of 10 bytes per suffix), and PCIe,
+// not HBM, bounds the end-to-end time.  So the one-call path ships the 32-bit suffix array as soon as the sort is
+// done (copy stream, in chunks, overlapping the lcp/bwt sweep) and widens it to the reference's 8-byte Uint on host
+// cores while later chunks are still in flight.  The staged API (esa_construct/esa_download) keeps the widened table
+// on the device.
+struct HostWiden
+{
+  bool active = false;
+  u32 *staging = nullptr;  // pinned: the 32-bit entries as they arrive
+  u64 *dst = nullptr;      // pinned: the table handed out in esa_result
+  u64 count = 0, chunk = 0;
+  u32 nchunks = 0;
+  int nthreads = 0, device = 0;
+  std::vector<cudaEvent_t> events;
+  std::vector<pthread_t> threads;
+  struct Arg
+  {
+    HostWiden *w;
+    int tid;
+  };
+  std::vector<Arg> args;
+};
+
+void widen_range(const u32 *src, u64 *dst, u64 cnt)
+{
+  u64 i = 0;
+  const __m128i zero = _mm_setzero_si128();
+  for (; i + 4 <= cnt; i += 4)
+  {
+    const __m128i x = _mm_load_si128((const __m128i *) (src + i));
+    _mm_stream_si128((__m128i *) (dst + i), _mm_unpacklo_epi32(x, zero));  // streaming stores: no read for ownership
+    _mm_stream_si128((__m128i *) (dst + i + 2), _mm_unpackhi_epi32(x, zero));
+  }
+  for (; i < cnt; i++)
+  {
+    dst[i] = src[i];
+  }
+  _mm_sfence();
+}
+
+void *widen_worker(void *p)
+{
+  HostWiden::Arg *a = (HostWiden::Arg *) p;
+  HostWiden *w = a->w;
+  cudaSetDevice(w->device);
+  for (u32 c = (u32) a->tid; c < w->nchunks; c += (u32) w->nthreads)
+  {
+    cudaEventSynchronize(w->events[c]);
+    const u64 b = (u64) c * w->chunk, e = std::min(w->count, b + w->chunk);
+    widen_range(w->staging + b, w->dst + b, e - b);
+  }
+  return nullptr;
+}
+
 struct CtxExtra
 {
   PinnedPool pool;
+  HostWiden widen;
+  bool fuse_download = false;  // set by esa_build around do_construct
+  cudaEvent_t ev_sorted = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
 };
 
@@ -221,6 +282,93 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
   ctx->uploaded = true;
 }
 
+// host threads available to one rank for widening; measured on the B200 box (32 cores, 100 M entries): 2 threads
+// 37.8 ms end to end, 4: 27.8, 8: 24.5, 12: 24.1, against 30.6 ms when the widened table crosses PCIe -- so the
+// fused path is only taken with at least 6 threads per rank (ESA_WIDEN_THREADS overrides, 0 disables)
+int widen_threads(const FullCtx *ctx)
+{
+  if (const char *e = getenv("ESA_WIDEN_THREADS"))
+  {
+    return atoi(e);
+  }
+  const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  const int ranks = ctx->comm != nullptr ? ctx->comm->nranks : 1;
+  const long per_rank = cores / (2 * ranks);
+  return per_rank >= 6 ? (int) std::min<long>(12, per_rank) : 0;
+}
+
+void start_host_widen(FullCtx *ctx)
+{
+  HostWiden &w = ctx->x.widen;
+  w.count = ctx->shard_count;
+  w.device = ctx->device;
+  w.staging = (u32 *) ctx->x.pool.get((w.count + 4) * sizeof(u32));
+  w.dst = (u64 *) ctx->x.pool.get((w.count + 4) * sizeof(u64));
+  w.chunk = std::max<u64>((u64) 1 << 21, div_up_u64(div_up_u64(w.count, 192), 4) * 4);  // multiples of 4 entries
+  w.nchunks = (u32) div_up_u64(w.count, w.chunk);
+  w.nthreads = std::max(1, std::min(widen_threads(ctx), (int) std::max<u32>(1, w.nchunks)));
+  while (w.events.size() < w.nchunks)
+  {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    w.events.push_back(e);
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->x.ev_sorted, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->x.ev_sorted, 0));
+  for (u32 c = 0; c < w.nchunks; c++)
+  {
+    const u64 b = (u64) c * w.chunk, e = std::min(w.count, b + w.chunk);
+    CUDA_CHECK(cudaMemcpyAsync(w.staging + b, ctx->d_sa + b, (e - b) * sizeof(u32), cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+    CUDA_CHECK(cudaEventRecord(w.events[c], ctx->copy_stream));
+  }
+  w.threads.resize(w.nthreads);
+  w.args.resize(w.nthreads);
+  w.active = true;
+  for (int t = 0; t < w.nthreads; t++)
+  {
+    w.args[t] = {&w, t};
+    if (pthread_create(&w.threads[t], nullptr, widen_worker, &w.args[t]) != 0)
+    {
+      // fewer workers than planned: the started ones cover the chunks of the missing ones too
+      for (int u = 0; u < t; u++)
+      {
+        pthread_join(w.threads[u], nullptr);
+      }
+      w.nthreads = 0;
+      CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+      widen_range(w.staging, w.dst, w.count);
+      break;
+    }
+  }
+}
+
+// waits for the workers; returns the widened table (owned by the pinned pool like every result table)
+u64 *finish_host_widen(FullCtx *ctx, bool keep)
+{
+  HostWiden &w = ctx->x.widen;
+  if (!w.active)
+  {
+    return nullptr;
+  }
+  for (int t = 0; t < w.nthreads; t++)
+  {
+    pthread_join(w.threads[t], nullptr);
+  }
+  cudaStreamSynchronize(ctx->copy_stream);
+  w.active = false;
+  ctx->x.pool.put(w.staging);
+  w.staging = nullptr;
+  u64 *r = w.dst;
+  w.dst = nullptr;
+  if (!keep)
+  {
+    ctx->x.pool.put(r);
+    return nullptr;
+  }
+  return r;
+}
+
 void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
 {
   if (!ctx->uploaded)
@@ -313,6 +461,12 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   }
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_b, s));
   ar.rewind(scratch_mark);  // everything the sorter carved is dead now
+  u32 table_demand = demand;  // what the sweeps over the suffix array still have to produce on the device
+  if (ctx->x.fuse_download && (demand & ESA_SUFTAB) && ctx->shard_count >= ((u64) 1 << 22) && widen_threads(ctx) > 0)
+  {
+    start_host_widen(ctx);
+    table_demand &= ~(u32) ESA_SUFTAB;
+  }
   // lcp path: direct comparison in suffix-array order unless the deep groups are so large that the work bound
   // sum(active * depth / 32) explodes (long exact tandem arrays); then the text-order plcp path, whose cost does
   // not depend on the lcp values
@@ -363,24 +517,24 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   {
     if (use_plcp)
     {
-      finalize_tables(ctx, demand, ctx->d_plcpv, N, 0);
+      finalize_tables(ctx, table_demand, ctx->d_plcpv, N, 0);
     } else
     {
-      finalize_tables_direct(ctx, demand, so.h0, N, 0, 0);
+      finalize_tables_direct(ctx, table_demand, so.h0, N, 0, 0);
     }
   } else
   {
     if (ctx->shard_count == 0)
     {
-      ctx->d_suf64 = (demand & ESA_SUFTAB) ? ar.alloc<u64>(4) : nullptr;
+      ctx->d_suf64 = (table_demand & ESA_SUFTAB) ? ar.alloc<u64>(4) : nullptr;
       ctx->d_bwt = (demand & ESA_BWTTAB) ? ar.alloc<u8>(4) : nullptr;
       ctx->d_lcp = want_lcp ? ar.alloc<u8>(4) : nullptr;
     } else if (use_plcp)
     {
-      finalize_tables(ctx, demand, ctx->d_plcpv, ctx->shard_count, ctx->shard_first);
+      finalize_tables(ctx, table_demand, ctx->d_plcpv, ctx->shard_count, ctx->shard_first);
     } else
     {
-      finalize_tables_direct(ctx, demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
+      finalize_tables_direct(ctx, table_demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
     }
     // scalars of the whole table
     u64 sc[2] = {ctx->maxbranchdepth, ctx->longest}, all[2 * ESA_MAX_RANKS];
@@ -460,7 +614,10 @@ u64 do_download(FullCtx *ctx, esa_result *out)
   out->nllv = ctx->nllv;
   out->maxbranchdepth = ctx->maxbranchdepth;
   out->longest = ctx->longest;
-  if (ctx->d_suf64 != nullptr)
+  if (ctx->x.widen.active)
+  {
+    bytes += 4 * N;  // what crossed PCIe for this table
+  } else if (ctx->d_suf64 != nullptr)
   {
     out->suftab = download_table(ctx, ctx->d_suf64, N);
     bytes += 8 * N;
@@ -497,6 +654,10 @@ u64 do_download(FullCtx *ctx, esa_result *out)
     bytes += 8 * N;
   }
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->x.widen.active)
+  {
+    out->suftab = finish_host_widen(ctx, true);
+  }
   return bytes;
 }
 
@@ -544,7 +705,7 @@ int esa_init(esa_ctx **out, int device, char *errbuf, size_t errlen)
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaMallocHost((void **) &ctx->h_scalars, 64 * sizeof(u64)));
-    for (cudaEvent_t *ev : {&ctx->x.ev_a, &ctx->x.ev_b, &ctx->x.ev_c, &ctx->x.ev_d, &ctx->x.ev_e})
+    for (cudaEvent_t *ev : {&ctx->x.ev_a, &ctx->x.ev_b, &ctx->x.ev_c, &ctx->x.ev_d, &ctx->x.ev_e, &ctx->x.ev_sorted})
     {
       CUDA_CHECK(cudaEventCreate(ev));
     }
@@ -581,7 +742,12 @@ void esa_shutdown(esa_ctx *c)
   ctx->arena.release();
   ctx->prof.destroy();
   ctx->x.pool.destroy();
-  for (cudaEvent_t ev : {ctx->x.ev_a, ctx->x.ev_b, ctx->x.ev_c, ctx->x.ev_d, ctx->x.ev_e})
+  finish_host_widen(ctx, false);
+  for (cudaEvent_t ev : ctx->x.widen.events)
+  {
+    cudaEventDestroy(ev);
+  }
+  for (cudaEvent_t ev : {ctx->x.ev_a, ctx->x.ev_b, ctx->x.ev_c, ctx->x.ev_d, ctx->x.ev_e, ctx->x.ev_sorted})
   {
     if (ev != nullptr)
     {
@@ -664,11 +830,15 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
     CUDA_CHECK(cudaSetDevice(ctx->device));
     CUDA_CHECK(cudaEventRecord(ctx->x.ev_e, s));
     do_upload(ctx, tis, n, numofchars);
+    ctx->x.fuse_download = getenv("ESA_NO_HOST_WIDEN") == nullptr;
     try
     {
       do_construct(ctx, prefixlength, demand, stats);  // records ev_a .. ev_d, synchronises
+      ctx->x.fuse_download = false;
     } catch (...)
     {
+      ctx->x.fuse_download = false;
+      finish_host_widen(ctx, false);
       if (ctx->comm != nullptr && ctx->comm->group != nullptr)
       {
         esa_group_abort(ctx->comm->group);
@@ -691,6 +861,7 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
   });
   if (rc != ESA_OK)
   {
+    finish_host_widen(ctx, false);
     esa_free(c, out);
   }
   return rc;
