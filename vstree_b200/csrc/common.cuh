@@ -294,6 +294,11 @@ struct RadixRemoteDst
 void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes);
 
+// doubling_sort.cu: the sort of one doubling round (list grouped by key >> shift; sorts by key bits [0, 2*shift));
+// same return convention as radix_sort_pairs_u64
+int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, void *sort_temp,
+                  size_t temp_bytes);
+
 // suffix_sort.cu: fills ctx->d_sa, ctx->d_isa (and ctx->d_bck when demanded) ; returns stats pieces
 struct SortOutcome
 {

@@ -755,7 +755,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
                (gather_rank_kernel<<<div_up_u32(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, rank)));
     u64 *ks = dk_in, *ko = dk_out;
     u32 *ps = dp_in, *po = dp_out;
-    if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
+    if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
     {
       ks = dk_out;
       ko = dk_in;
@@ -934,8 +934,8 @@ __global__ void spec_tail_kernel(const u32 *__restrict__ spec, u64 count, u64 fi
 
 // doubling, step 1: tag every active suffix with the owner of its h-successor (low key bits) and count per owner
 __global__ void __launch_bounds__(256)
-owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, KeyFromText keyof, OwnerLut lut,
-                 unsigned long long *__restrict__ owner_count)
+owner_tag_kernel(u32 *__restrict__ tag, u32 *__restrict__ idx, const u32 *__restrict__ pos, u64 m, u64 h,
+                 KeyFromText keyof, OwnerLut lut, unsigned long long *__restrict__ owner_count)
 {
   __shared__ u32 sh[ESA_MAX_RANKS];
   if (threadIdx.x < ESA_MAX_RANKS)
@@ -947,7 +947,8 @@ owner_tag_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 
   if (t < m)
   {
     const u32 o = owner_of_key(keyof((u64) pos[t] + h), lut);
-    key[t] |= (u64) o;
+    tag[t] = o;
+    idx[t] = (u32) t;
     atomicAdd(&sh[o], 1u);
   }
   __syncthreads();
@@ -968,13 +969,25 @@ __global__ void serve_rank_kernel(const u32 *__restrict__ req_pos, u64 count, u6
   }
 }
 
-// doubling, step 3: the answers replace the owner tag in the low key bits
-__global__ void merge_answer_kernel(u64 *__restrict__ key, const u32 *__restrict__ answer, u64 m, u32 rank_shift)
+// doubling, step 1b: the requests in owner order (the key/position lists themselves keep their group order)
+__global__ void make_request_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ pos, u64 m,
+                                    u32 *__restrict__ req)
 {
-  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < m)
+  const u64 j = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m)
   {
-    key[t] = ((key[t] >> rank_shift) << rank_shift) | (u64) answer[t];
+    req[j] = pos[idx[j]];
+  }
+}
+
+// doubling, step 3: the answers go into the low key bits of the suffixes that asked
+__global__ void merge_answer_kernel(u64 *__restrict__ key, const u32 *__restrict__ idx,
+                                    const u32 *__restrict__ answer, u64 m)
+{
+  const u64 j = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m)
+  {
+    key[idx[j]] |= (u64) answer[j];
   }
 }
 
@@ -1429,7 +1442,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
         ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
                    (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, hh, keyof, lut, peers)));
         comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
-        if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
+        if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
         {
           ks = dk_out, ko = dk_in;
           ps = dp_out, po = dp_in;
@@ -1491,11 +1504,16 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   while (true)
   {
     u64 req_cnt[ESA_MAX_RANKS] = {0}, req_off[ESA_MAX_RANKS], in_cnt[ESA_MAX_RANKS], in_off[ESA_MAX_RANKS];
+    const size_t round_mark = ar.mark();
+    // requests travel in owner order; the key / position lists themselves stay in group order (doubling_sort relies
+    // on it), so the partition works on (owner tag, list index) pairs
+    u32 *tag_a = ar.alloc<u32>(m + 4), *tag_b = ar.alloc<u32>(m + 4), *idx_a = ar.alloc<u32>(m + 4),
+        *idx_b = ar.alloc<u32>(m + 4), *req_out = ar.alloc<u32>(m + 4);
     if (m > 0)
     {
       ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
-      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 28.0 * m,
-                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut, d_counts)));
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 16.0 * m,
+                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(tag_a, idx_a, dp_in, m, h, keyof, lut, d_counts)));
       CUDA_CHECK(cudaMemcpyAsync(req_cnt, d_counts, G * sizeof(u64), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
@@ -1527,16 +1545,18 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
     }
     // partition my requests by owner (stable, one pass over the tag bits)
-    u64 *kreq = dk_in, *kalt = dk_out;
-    u32 *preq = dp_in, *palt = dp_out;
-    if (m > 1 && radix_sort_pairs_u64(ctx, dk_in, dk_out, dp_in, dp_out, m, 0, owner_bits, sort_temp, temp_bytes))
+    const u32 *idx = idx_a;
+    if (m > 1 && radix_sort_pairs_u32(ctx, tag_a, tag_b, idx_a, idx_b, m, 0, owner_bits, sort_temp, temp_bytes))
     {
-      kreq = dk_out, kalt = dk_in;
-      preq = dp_out, palt = dp_in;
+      idx = idx_b;
     }
-    const size_t round_mark = ar.mark();
+    if (m > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 12.0 * m,
+                 (make_request_kernel<<<grid_for(m, 256), 256, 0, s>>>(idx, dp_in, m, req_out)));
+    }
     u32 *req_in = ar.alloc<u32>(in_tot + 1), *ans_out = ar.alloc<u32>(in_tot + 1), *ans_in = ar.alloc<u32>(m + 1);
-    comm_alltoallv_u32(ctx, comm, preq, req_off, req_cnt, req_in, in_off, in_cnt);
+    comm_alltoallv_u32(ctx, comm, req_out, req_off, req_cnt, req_in, in_off, in_cnt);
     if (in_tot > 0)
     {
       ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 12.0 * in_tot,
@@ -1547,14 +1567,14 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     if (m > 0)
     {
       ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 20.0 * m,
-                 (merge_answer_kernel<<<grid_for(m, 256), 256, 0, s>>>(kreq, ans_in, m, rank_shift)));
+                 (merge_answer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, idx, ans_in, m)));
       ar.rewind(round_mark);  // the round's exchange buffers are dead (later users are stream ordered)
-      u64 *ks = kreq, *ko = kalt;
-      u32 *ps = preq, *po = palt;
-      if (m > 1 && radix_sort_pairs_u64(ctx, kreq, kalt, preq, palt, m, 0, 2 * rank_shift, sort_temp, temp_bytes))
+      u64 *ks = dk_in, *ko = dk_out;
+      u32 *ps = dp_in, *po = dp_out;
+      if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
       {
-        ks = kalt, ko = kreq;
-        ps = palt, po = preq;
+        ks = dk_out, ko = dk_in;
+        ps = dp_out, po = dp_in;
       }
       rtiles = (u32) div_up_u64(m, RG_TILE);
       ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
