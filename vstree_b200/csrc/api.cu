@@ -189,8 +189,17 @@ size_t arena_estimate(u64 n, int nranks)
   const u64 N = n + 1;
   if (nranks <= 1)
   {
-    // tis 1 + sa 4 + isa 4 + bck worst case 5 + doubling regions X and Y 32 + sort scratch and tile summaries ~2
-    return (size_t) (48 * N) + ((size_t) 256 << 20);
+    // tis 1 + packed text 0.4 + sa 4 + isa 4 + round table 1 + bck worst case 5 + sort regions X and Y 32 + two-level
+    // scatter and doubling-round scratch up to 16: 64 bytes per suffix when the device has them, never less than 48
+    size_t free_b = 0, total_b = 0;
+    const size_t want = (size_t) (64 * N) + ((size_t) 256 << 20), floor_b = (size_t) (48 * N) + ((size_t) 256 << 20);
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return want;
+    }
+    const size_t cap = (size_t) (0.92 * (double) total_b);
+    return want <= cap ? want : (floor_b <= cap ? cap : floor_b);
   }
   // sharded: replicated text 1 + packed text 0.4 + dense rank array 4 + bck (with all-reduce scratch) 2.5, plus the
   // per-range share of everything else with head room for uneven ranges (ESA_SHARD_SLACK percent, default 60)

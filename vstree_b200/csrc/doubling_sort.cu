@@ -237,7 +237,7 @@ int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b
   {
     return 0;
   }
-  if (disabled || m < 4096)
+  if (disabled || m < 4096 || ctx->arena.high - ctx->arena.top < 16 * m + ((size_t) 4 << 20))
   {
     return radix_sort_pairs_u64(ctx, keys_a, keys_b, pos_a, pos_b, m, 0, 2 * shift, sort_temp, temp_bytes);
   }

@@ -563,6 +563,25 @@ bool scatter_ranks_partitioned(esa_ctx *ctx, u32 *pos, u32 *val, u64 m, u32 pos_
   return true;
 }
 
+// scratch of the two-level scatter for one doubling round, carved from the arena when there is room (else the
+// ranks are scattered directly by regroup_apply); released with ar.rewind(mark) after the scatter has been queued
+struct ScatterScratch
+{
+  u32 *rank_out = nullptr, *tp = nullptr, *tv = nullptr;
+};
+ScatterScratch round_scatter_scratch(Arena &ar, u64 m, u32 pos_bits)
+{
+  ScatterScratch sc;
+  if (m >= PARTITIONED_SCATTER_MIN && pos_bits > SCATTER_WINDOW_BITS
+      && ar.high - ar.top > 12 * (m + 64) + ((size_t) 8 << 20))
+  {
+    sc.rank_out = ar.alloc<u32>(m + 64);
+    sc.tp = ar.alloc<u32>(m + 64);
+    sc.tv = ar.alloc<u32>(m + 64);
+  }
+  return sc;
+}
+
 u64 read_scalar(esa_ctx *ctx, const u64 *d_scalars, int idx)
 {
   CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars + idx, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -717,14 +736,15 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   const u64 mal = m + 64;
   u64 *dk_in = ar.alloc<u64>(mal);
   u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
-  // scratch of the two-level rank scatter (rank in suffix-array order + the partitioned copy of (pos, rank));
-  // skipped when the arena is too tight, then ranks are scattered directly
+  // two-level rank scatter of the first regroup: its scratch costs nothing -- the rank list in suffix-array order
+  // goes into the position buffer the sort did not end in, the partitioned copy into the two key buffers, which are
+  // dead once regroup_apply has read the sorted keys
   u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
-  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS && ar.capacity - ar.top > 12 * (M + 64) + (1 << 20))
+  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
   {
-    part_rank = ar.alloc<u32>(M + 64);
-    part_tp = ar.alloc<u32>(M + 64);
-    part_tv = ar.alloc<u32>(M + 64);
+    part_rank = spos == pos_a ? pos_b : pos_a;
+    part_tp = key_a;
+    part_tv = key_b;
   }
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
              (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
@@ -769,18 +789,19 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
     const u64 m_next = read_scalar(ctx, d_scalars, 4);
-    const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
+    const size_t scatter_mark = ar.mark();
+    const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                  tile_active, sa, rank, ko, po,
                                                                                  slots_next, rank_shift,
                                                                                  ctx->d_hround, outcome->rounds,
-                                                                                 two_level ? part_rank : nullptr,
-                                                                                 0u)));
-    if (two_level)
+                                                                                 sc.rank_out, 0u)));
+    if (sc.rank_out != nullptr)
     {
-      scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+      scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
     }
+    ar.rewind(scatter_mark);
     dk_in = ko;
     dp_in = po;
     dk_out = ks;
@@ -1381,11 +1402,11 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u64 *dk_in = ar.alloc<u64>(mal);
   u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
   u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
-  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS && ar.high - ar.top > 12 * (M + 64) + 24 * mal + (64 << 20))
+  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
   {
-    part_rank = ar.alloc<u32>(M + 64);
-    part_tp = ar.alloc<u32>(M + 64);
-    part_tv = ar.alloc<u32>(M + 64);
+    part_rank = spos == pos_a ? pos_b : pos_a;  // scratch of the first scatter lives in the dead sort buffers
+    part_tp = key_a;
+    part_tv = key_b;
   }
   if (M > 0)
   {
@@ -1467,18 +1488,19 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       }
       if (m > 0)
       {
-        const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
+        const size_t scatter_mark = ar.mark();
+        const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
         ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                    (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                      tile_active, sa, rank, ko, po,
                                                                                      slots_next, rank_shift,
                                                                                      ctx->d_hround, outcome->rounds,
-                                                                                     two_level ? part_rank : nullptr,
-                                                                                     slot_base)));
-        if (two_level)
+                                                                                     sc.rank_out, slot_base)));
+        if (sc.rank_out != nullptr)
         {
-          scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+          scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
         }
+        ar.rewind(scatter_mark);
         dk_in = ko;
         dp_in = po;
         dk_out = ks;
@@ -1583,18 +1605,19 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                  (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
       m_next = read_scalar(ctx, d_scalars, 4);
-      const bool two_level = part_rank != nullptr && m >= PARTITIONED_SCATTER_MIN;
+      const size_t scatter_mark = ar.mark();
+      const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
       ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                  (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                    tile_active, sa, rank, ko, po,
                                                                                    slots_next, rank_shift,
                                                                                    ctx->d_hround, outcome->rounds,
-                                                                                   two_level ? part_rank : nullptr,
-                                                                                   slot_base)));
-      if (two_level)
+                                                                                   sc.rank_out, slot_base)));
+      if (sc.rank_out != nullptr)
       {
-        scatter_ranks_partitioned(ctx, ps, part_rank, m, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
+        scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
       }
+      ar.rewind(scatter_mark);
       dk_in = ko;
       dp_in = po;
       dk_out = ks;
