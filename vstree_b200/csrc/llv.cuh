@@ -14,17 +14,30 @@ constexpr int LLV_SCAN_THREADS = 1024;
 static __global__ void __launch_bounds__(LLV_SCAN_THREADS)
 large_scan_kernel(u32 *tile_large, u32 ntiles, unsigned long long *scalars)
 {
+  constexpr int ITEMS = 8;  // tiles per thread and step
   __shared__ u64 scratch[LLV_SCAN_THREADS / 32 + 1];
   u64 carry = 0;
-  for (u32 b = 0; b < ntiles; b += LLV_SCAN_THREADS)
+  for (u32 b = 0; b < ntiles; b += LLV_SCAN_THREADS * ITEMS)
   {
-    const u32 i = b + threadIdx.x;
-    const u64 val = i < ntiles ? tile_large[i] : 0;
-    u64 total;
-    const u64 ex = block_exclusive_sum<u64, LLV_SCAN_THREADS>(val, scratch, &total);
-    if (i < ntiles)
+    const u32 i0 = b + threadIdx.x * ITEMS;
+    u32 v[ITEMS];
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
     {
-      tile_large[i] = (u32) (carry + ex);
+      v[k] = i0 + k < ntiles ? tile_large[i0 + k] : 0u;
+      sum += v[k];
+    }
+    u64 total;
+    u64 run = carry + block_exclusive_sum<u64, LLV_SCAN_THREADS>(sum, scratch, &total);
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+    {
+      if (i0 + k < ntiles)
+      {
+        tile_large[i0 + k] = (u32) run;
+      }
+      run += v[k];
     }
     carry += total;
   }

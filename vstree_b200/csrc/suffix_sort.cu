@@ -84,41 +84,48 @@ classify_count_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end,
   }
 }
 
-// In-place exclusive sums of up to four per-tile count arrays, single CTA; totals go to scalars[first_scalar+a].
+// In-place exclusive sums of up to three per-tile count arrays, one CTA per array (blockIdx.x), eight tiles per thread
+// and step; totals go to scalars[first_scalar + a].  (One CTA looping over the arrays with one tile per thread took
+// 72 us for the 24 K tiles of 100 Mbp: three such single-CTA scans were 2 % of a build.)
 constexpr int SCAN1_THREADS = 1024;
+constexpr int SCAN1_ITEMS = 8;
 __global__ void __launch_bounds__(SCAN1_THREADS)
 tile_exclusive_sum_kernel(u32 *a0, u32 *a1, u32 *a2, u32 ntiles, u64 *scalars, int first_scalar)
 {
   __shared__ u64 scratch[SCAN1_THREADS / 32 + 1];
-  u32 *arrs[3] = {a0, a1, a2};
-  for (int a = 0; a < 3; a++)
+  u32 *arr = blockIdx.x == 0 ? a0 : blockIdx.x == 1 ? a1 : a2;
+  if (arr == nullptr)
   {
-    u32 *arr = arrs[a];
-    if (arr == nullptr)
-    {
-      continue;
-    }
-    u64 carry = 0;
-    for (u32 b = 0; b < ntiles; b += SCAN1_THREADS)
-    {
-      const u32 i = b + threadIdx.x;
-      const u64 v = i < ntiles ? arr[i] : 0;
-      u64 total;
-      const u64 ex = block_exclusive_sum<u64, SCAN1_THREADS>(v, scratch, &total);
-      if (i < ntiles)
-      {
-        arr[i] = (u32) (carry + ex);  // offsets stay below 2^32 because N does
-      }
-      carry += total;
-    }
-    if (threadIdx.x == 0)
-    {
-      scalars[first_scalar + a] = carry;
-    }
+    return;
   }
-  if (threadIdx.x == 0 && first_scalar == 0)
+  u64 carry = 0;
+  for (u32 b = 0; b < ntiles; b += SCAN1_THREADS * SCAN1_ITEMS)
   {
-    scalars[3] = scalars[0] + scalars[1];
+    const u32 i0 = b + threadIdx.x * SCAN1_ITEMS;
+    u32 v[SCAN1_ITEMS];
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++)
+    {
+      v[k] = i0 + k < ntiles ? arr[i0 + k] : 0u;
+      sum += v[k];
+    }
+    u64 total;
+    u64 run = carry + block_exclusive_sum<u64, SCAN1_THREADS>(sum, scratch, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++)
+    {
+      if (i0 + k < ntiles)
+      {
+        arr[i0 + k] = (u32) run;  // offsets stay below 2^32 because N does
+      }
+      run += v[k];
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0)
+  {
+    scalars[first_scalar + blockIdx.x] = carry;
   }
 }
 
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(KS_THREADS)
 classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, KmerParams kp,
                      const u32 *__restrict__ tile_full,
                      const u32 *__restrict__ tile_side, const u32 *__restrict__ tile_spec,
-                     const u64 *__restrict__ scalars, u32 *__restrict__ main_key, u32 *__restrict__ main_pos,
+                     u64 M /* full + side suffixes of the whole table */, u32 *__restrict__ main_key, u32 *__restrict__ main_pos,
                      u32 *__restrict__ side_key, u32 *__restrict__ side_pos, u32 *__restrict__ side_dj,
                      u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ spec_list)
 {
@@ -169,7 +176,6 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, 
   u32 rf = ex_fs & 0xffffu, rs = ex_fs >> 16, rp = ex_p;
   const u32 tfull = tot_fs & 0xffffu;
   const u64 off_full = tile_full[blockIdx.x], off_side = tile_side[blockIdx.x], off_spec = tile_spec[blockIdx.x];
-  const u64 M = scalars[3];
 #pragma unroll
   for (int i = 0; i < KS_ITEMS; i++)
   {
@@ -376,7 +382,7 @@ regroup_summary_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ sl
   }
 }
 
-// single CTA: tile_maxrank -> exclusive running max (the rank carried into the tile),
+// single CTA, eight tiles per thread and step: tile_maxrank -> exclusive running max (the rank carried into the tile),
 // tile_active -> exclusive sum (first output slot of the tile); scalars[4] = total active
 __global__ void __launch_bounds__(SCAN1_THREADS)
 regroup_scan_kernel(u32 *tile_maxrank, u32 *tile_active, u32 ntiles, u64 *scalars)
@@ -386,23 +392,38 @@ regroup_scan_kernel(u32 *tile_maxrank, u32 *tile_active, u32 ntiles, u64 *scalar
   __shared__ u32 sincl[SCAN1_THREADS];
   u64 carry_sum = 0;
   u32 carry_max = 0;
-  for (u32 b = 0; b < ntiles; b += SCAN1_THREADS)
+  for (u32 b = 0; b < ntiles; b += SCAN1_THREADS * SCAN1_ITEMS)
   {
-    const u32 i = b + threadIdx.x;
-    const u32 mv = i < ntiles ? tile_maxrank[i] : 0;
-    const u64 cv = i < ntiles ? tile_active[i] : 0;
+    const u32 i0 = b + threadIdx.x * SCAN1_ITEMS;
+    u32 mv[SCAN1_ITEMS], cv[SCAN1_ITEMS];
+    u64 sum = 0;
+    u32 mx = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++)
+    {
+      mv[k] = i0 + k < ntiles ? tile_maxrank[i0 + k] : 0u;
+      cv[k] = i0 + k < ntiles ? tile_active[i0 + k] : 0u;
+      sum += cv[k];
+      mx = max(mx, mv[k]);
+    }
     u64 total;
-    const u64 ex = block_exclusive_sum<u64, SCAN1_THREADS>(cv, scratch, &total);
-    const u32 incl = block_inclusive_max<u32, SCAN1_THREADS>(mv, mscratch);
+    u64 run = carry_sum + block_exclusive_sum<u64, SCAN1_THREADS>(sum, scratch, &total);
+    const u32 incl = block_inclusive_max<u32, SCAN1_THREADS>(mx, mscratch);
     sincl[threadIdx.x] = incl;
     __syncthreads();
-    const u32 exmax = max(carry_max, threadIdx.x > 0 ? sincl[threadIdx.x - 1] : 0u);
+    u32 runmax = max(carry_max, threadIdx.x > 0 ? sincl[threadIdx.x - 1] : 0u);
     const u32 chunk_max = sincl[SCAN1_THREADS - 1];
     __syncthreads();
-    if (i < ntiles)
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++)
     {
-      tile_maxrank[i] = exmax;
-      tile_active[i] = (u32) (carry_sum + ex);
+      if (i0 + k < ntiles)
+      {
+        tile_maxrank[i0 + k] = runmax;
+        tile_active[i0 + k] = (u32) run;
+      }
+      runmax = max(runmax, mv[k]);
+      run += cv[k];
     }
     carry_sum += total;
     carry_max = max(carry_max, chunk_max);
@@ -626,7 +647,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
              (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side,
                                                                    tile_spec)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-             (tile_exclusive_sum_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles, d_scalars,
+             (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles, d_scalars,
                                                                      0)));
   CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -648,7 +669,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 
   ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N + 8.0 * M + 8.0 * nspec,
              (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side, tile_spec,
-                                                                  d_scalars, key_a, pos_a, side_key, side_pos, side_dj,
+                                                                  M, key_a, pos_a, side_key, side_pos, side_dj,
                                                                   sa, rank, nullptr)));
   // side suffixes: stable sort by h0-j, written straight behind the full ones
   if (nside == 1)
@@ -1125,7 +1146,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
                (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
                                                                      tile_side, tile_spec)));
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-               (tile_exclusive_sum_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
+               (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
                                                                        d_scalars, 0)));
     CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1143,7 +1164,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   {
     ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin) + 8.0 * (nfull + nside) + 4.0 * nspec,
                (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
-                                                                    tile_side, tile_spec, d_scalars, key_l, pos_l,
+                                                                    tile_side, tile_spec, 0, key_l, pos_l,
                                                                     lside_key, lside_pos, lside_dj, nullptr, nullptr,
                                                                     lspec)));
   }
