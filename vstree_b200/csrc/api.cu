@@ -174,6 +174,7 @@ struct CtxExtra
   PinnedPool pool;
   HostWiden widen;
   bool fuse_download = false;  // set by esa_build around do_construct
+  u64 h2d_bytes = 0;           // what the last upload moved over PCIe on this rank
   cudaEvent_t ev_sorted = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
 };
@@ -278,12 +279,33 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
     ctx->arena.reserve(need);
   }
   ctx->arena.reset();
-  const u64 padded = ((n + 15) & ~(u64) 15) + 64;
-  ctx->d_tis = ctx->arena.alloc<u8>(padded);
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_tis + n, 255, padded - n, ctx->stream));
-  if (n > 0)
+  u64 padded = ((n + 15) & ~(u64) 15) + 64;
+  if (is_sharded(ctx) && n > 0)
   {
-    CUDA_CHECK(cudaMemcpyAsync(ctx->d_tis, tis, n, cudaMemcpyHostToDevice, ctx->stream));
+    // the text is replicated, but it crosses PCIe only once per box: every rank uploads its slice and the slices are
+    // all-gathered between the devices (NVLink)
+    esa_comm *comm = ctx->comm;
+    const u64 slice = div_up_u64(div_up_u64(n, (u64) comm->nranks), 256) * 256;
+    padded = std::max(padded, slice * comm->nranks + 64);
+    ctx->d_tis = ctx->arena.alloc<u8>(padded);
+    const u64 b = std::min(n, (u64) comm->rank * slice), e = std::min(n, (u64) (comm->rank + 1) * slice);
+    if (e > b)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(ctx->d_tis + b, tis + b, e - b, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->x.h2d_bytes = e - b;
+    ctx->prof.enabled = false;
+    comm_allgather_bytes(ctx, comm, ctx->d_tis, slice);
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_tis + n, 255, padded - n, ctx->stream));
+  } else
+  {
+    ctx->d_tis = ctx->arena.alloc<u8>(padded);
+    ctx->x.h2d_bytes = n;
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_tis + n, 255, padded - n, ctx->stream));
+    if (n > 0)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(ctx->d_tis, tis, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
   }
   ctx->n = n;
   ctx->sigma = numofchars;
@@ -864,7 +886,7 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
       CUDA_CHECK(cudaEventSynchronize(ctx->x.ev_e));
       CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->x.ev_d, ctx->x.ev_e));
       stats->ms_d2h = ms;
-      stats->h2d_bytes = n;
+      stats->h2d_bytes = ctx->x.h2d_bytes;
       stats->d2h_bytes = d2h;
     }
   });

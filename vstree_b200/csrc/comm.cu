@@ -513,6 +513,35 @@ void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, si
                                          (ncclComm_t) comm->nccl, ctx->stream)));
 }
 
+void comm_allgather_bytes(esa_ctx *ctx, esa_comm *comm, u8 *d_buf, size_t slice)
+{
+  if (comm->nranks == 1 || slice == 0)
+  {
+    return;
+  }
+  const int G = comm->nranks, me = comm->rank;
+  comm->bytes_sent += (u64) slice * (G - 1);
+  if (comm->group != nullptr)
+  {
+    group_round(ctx, comm, d_buf, nullptr, nullptr, [&](esa_group *g) {
+      ESA_LAUNCH(ctx, ESA_K_COMM, (double) slice * (G - 1), {
+        for (int r = 0; r < G; r++)
+        {
+          if (r != me)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(d_buf + (size_t) r * slice, (const u8 *) g->slot[r].ptr + (size_t) r * slice,
+                                       slice, cudaMemcpyDefault, ctx->stream));
+          }
+        }
+      });
+    });
+    return;
+  }
+  ESA_LAUNCH(ctx, ESA_K_COMM, (double) slice * (G - 1),
+             NCCL_CHECK(nccl().AllGather(d_buf + (size_t) me * slice, d_buf, slice, ncclUint8, (ncclComm_t) comm->nccl,
+                                         ctx->stream)));
+}
+
 void comm_allreduce_min_u32(esa_ctx *ctx, esa_comm *comm, u32 *d_buf, size_t count)
 {
   if (comm->nranks == 1 || count == 0)

@@ -80,6 +80,8 @@ void comm_exchange_host_u64(esa_ctx *ctx, esa_comm *comm, const u64 *mine, size_
 void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, size_t count, bool max_instead_of_sum);
 // in-place minimum over ranks of `count` 32-bit words (large arrays: the text-order plcp array of a sharded build)
 void comm_allreduce_min_u32(esa_ctx *ctx, esa_comm *comm, u32 *d_buf, size_t count);
+// in-place all-gather of equal byte slices: rank r's slice lives at d_buf + r*slice on every rank
+void comm_allgather_bytes(esa_ctx *ctx, esa_comm *comm, u8 *d_buf, size_t slice);
 // variable all-to-all of 32-bit words: counts/offsets are host arrays of nranks entries (in words);
 // recv_cnt[r] must equal what rank r sends here
 void comm_alltoallv_u32(esa_ctx *ctx, esa_comm *comm, const u32 *d_send, const u64 *send_off, const u64 *send_cnt,
