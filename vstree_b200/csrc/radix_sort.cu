@@ -169,6 +169,14 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   u32 *gbase = digit_start + RADIX;            // [RADIX] global index of slot 0 of the digit, minus digit_start
   u32 *misc = gbase + RADIX;                   // [0] tile ticket, [1..] scan scratch
   u32 *thist = misc + 16;                      // [RADIX] digit counts of the tile, published BEFORE the ranking
+  // REMOTE: the "digit" of a key is the rank that owns its bin (a look-up of the real digit), so that one tile's
+  // output consists of nranks long runs instead of 256 short ones -- long stores are what NVLink wants
+  __shared__ u8 sowner[RADIX];
+  if (REMOTE && threadIdx.x < RADIX)
+  {
+    sowner[threadIdx.x] = remote->owner[threadIdx.x];
+  }
+#define DIGIT(k) (REMOTE ? (u32) sowner[digit_of((k), shift, mask)] : digit_of((k), shift, mask))
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0)
@@ -212,7 +220,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
-    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 d = DIGIT(keys[i]);
     if (__all_sync(FULL_MASK, d == __shfl_sync(FULL_MASK, d, 0)))
     {
       if (lane == 0)
@@ -229,7 +237,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   if (tid < RADIX)
   {
     valid_count = thist[tid];
-    if ((u32) tid == mask)
+    if ((u32) tid == (REMOTE ? (u32) sowner[mask] : mask))
     {
       valid_count -= (u32) TILE - tile_count;  // padding keys carry the largest digit
     }
@@ -248,7 +256,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
-    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 d = DIGIT(keys[i]);
     atomicOr(&mymm[d], 1u << lane);
     __syncwarp();
     const u32 peers = mymm[d];
@@ -269,7 +277,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
-    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 d = DIGIT(keys[i]);
     u32 peers = FULL_MASK;
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; b++)
@@ -284,7 +292,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
-    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 d = DIGIT(keys[i]);
     const u32 peers = ranks[i];
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
@@ -325,7 +333,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   if (tid < RADIX)
   {
     u32 cnt = bcount;
-    if ((u32) tid == mask)
+    if ((u32) tid == (REMOTE ? (u32) sowner[mask] : mask))
     {
       cnt -= (u32) TILE - tile_count;  // padding keys carry the largest digit
     }
@@ -366,7 +374,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
-    const u32 d = digit_of(keys[i], shift, mask);
+    const u32 d = DIGIT(keys[i]);
     const u32 pos = mywc[d] + ranks[i];
     skeys[pos] = keys[i];
     if (HAS_VALS)
@@ -384,15 +392,14 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     if (p < tile_count)
     {
       const KeyT k = skeys[p];
-      const u32 d = digit_of(k, shift, mask);
+      const u32 d = DIGIT(k);
       const u32 g = gbase[d] + p;
       if (REMOTE)
       {
-        const u32 o = remote->owner[d];
-        reinterpret_cast<KeyT *>(remote->keys[o])[g] = k;
+        reinterpret_cast<KeyT *>(remote->keys[d])[g] = k;  // d is the owner rank
         if (HAS_VALS)
         {
-          remote->vals[o][g] = svals[p];
+          remote->vals[d][g] = svals[p];
         }
       } else
       {
@@ -408,6 +415,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   {
     __threadfence_system();  // the stores crossed NVLink: visible to the owner before this kernel counts as done
   }
+#undef DIGIT
 }
 
 template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
@@ -550,7 +558,8 @@ void radix_sort_init()
 
 // Stable partition of (key, value) pairs by the digit in key bits [begin_bit, end_bit) (at most 8 bits) whose output
 // goes to OTHER ranks' buffers: see the REMOTE note at radix_pass_kernel.  d_start[256] (device) holds, per digit, the
-// first index of this rank's run inside the owner's buffers.
+// first index of this rank's run inside the owner's buffers (entry r of d_start for owner rank r; the kernel
+// partitions by OWNER, the look-up of the digit, not by the digit itself).
 void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes)
 {
@@ -575,17 +584,11 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
   u64 *status = (u64 *) status_words;
   const u64 pim = part_items_max<u32>();
   cudaStream_t s = ctx->stream;
+  // one part (n < 2^32): the first destination index of every owner's run is given, no histogram pass is needed
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
-  for (u32 part = 0; part < L.parts; part++)
-  {
-    const u64 off = (u64) part * pim;
-    const u32 cnt = (u32) (n - off < pim ? n - off : pim);
-    const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(cnt, (u64) HIST_THREADS * HIST_ITEMS));
-    ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, (double) cnt * 4,
-               (radix_hist_kernel<u32><<<grid, HIST_THREADS, 0, s>>>(keys + off, cnt, begin_bit, end_bit, 1,
-                                                                       hist + (u64) part * RADIX)));
-  }
-  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<1, RADIX, 0, s>>>(hist, base, 1, L.parts, d_start)));
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0,
+             CUDA_CHECK(cudaMemcpyAsync(base, d_start, RADIX * sizeof(u32), cudaMemcpyDeviceToDevice, s)));
+  (void) hist;
   const u32 mask = (1u << (end_bit - begin_bit)) - 1;
   const size_t smem = pass_smem_bytes<u32>(true);
   for (u32 part = 0; part < L.parts; part++)

@@ -1295,8 +1295,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   if (comm->direct)
   {
     // fused partition + all-to-all: one pass over my (key, position) pairs whose output runs land directly in the
-    // owners' key_a / pos_a over NVLink.  Layout inside an owner: bin-major, then sender, then the sender's order
-    // (= text position order), so the owner receives its range already partitioned by the top key digit.
+    // owners' key_a / pos_a over NVLink.  Layout inside an owner: by sender, each sender's pairs in its own order
+    // (= text position order); the owner's LSD sort does not care.
     u64 my_off[2] = {(u64) ((char *) key_a - ar.base), (u64) ((char *) pos_a - ar.base)}, offs[2 * ESA_MAX_RANKS];
     comm_exchange_host_u64(ctx, comm, my_off, 2, offs);  // also: every rank has carved its receive buffers
     RadixRemoteDst h_dst;
@@ -1307,10 +1307,24 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       h_dst.vals[r] = comm_peer_ptr<u32>(ctx, comm, r, offs[2 * r + 1]);
     }
     memcpy(h_dst.owner, lut.owner, 256);
+    // the pass partitions by owner: rank r's runs lie in sender order inside its buffers
+    u32 owner_start[256] = {0};
+    for (int o = 0; o < G; o++)
+    {
+      u64 before_me = 0;
+      for (int r = 0; r < me; r++)
+      {
+        for (int b = 0; b < 256; b++)
+        {
+          before_me += lut.owner[b] == o ? hist_all[(size_t) r * HROW + b] : 0;
+        }
+      }
+      owner_start[o] = (u32) before_me;
+    }
     RadixRemoteDst *d_dst = reinterpret_cast<RadixRemoteDst *>(ar.alloc<char>(sizeof(RadixRemoteDst)));
     u32 *d_start = ar.alloc<u32>(256);
     CUDA_CHECK(cudaMemcpyAsync(d_dst, &h_dst, sizeof h_dst, cudaMemcpyHostToDevice, s));
-    CUDA_CHECK(cudaMemcpyAsync(d_start, h_start, sizeof h_start, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(d_start, owner_start, sizeof owner_start, cudaMemcpyHostToDevice, s));
     radix_partition_remote_u32(ctx, key_l, pos_l, nfull, lut.shift, key_bits > lut.shift ? key_bits : lut.shift + 1,
                                d_dst, d_start, sort_temp, temp_bytes);
     comm->bytes_sent += 8 * (nfull - send_cnt[me]);
