@@ -471,9 +471,9 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   ctx->d_spm = nullptr;
   ctx->d_hround = nullptr;
   ctx->lcp_work_estimate = 0;
-  if (ctx->sigma <= 4 && ((demand & (ESA_LCPTAB | ESA_BWTTAB)) || sharded))
+  if (ctx->sigma <= 4)
   {
-    pack_text(ctx);  // 2-bit text + special mask for the random suffix-start accesses of lcp and bwt
+    pack_text(ctx);  // 2-bit text + special mask: text keys of the sorter, suffix-start accesses of lcp and bwt
   }
   if (want_lcp && ctx->lcp_mode != 2 && !sharded)
   {
@@ -537,7 +537,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     ctx->d_plcpv = ar.alloc<u32>(N + 64);
     if (sharded)
     {
-      compute_plcp_sharded(ctx, ctx->comm, ctx->d_plcpv, so.h0, halo);
+      compute_plcp_sharded(ctx, ctx->comm, ctx->d_plcpv, halo);
     } else
     {
       compute_plcp(ctx, ctx->d_plcpv);
@@ -551,7 +551,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       finalize_tables(ctx, table_demand, ctx->d_plcpv, N, 0);
     } else
     {
-      finalize_tables_direct(ctx, table_demand, so.h0, N, 0, 0);
+      finalize_tables_direct(ctx, table_demand, N, 0, 0);
     }
   } else
   {
@@ -565,7 +565,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       finalize_tables(ctx, table_demand, ctx->d_plcpv, ctx->shard_count, ctx->shard_first);
     } else
     {
-      finalize_tables_direct(ctx, table_demand, so.h0, ctx->shard_count, ctx->shard_first, halo);
+      finalize_tables_direct(ctx, table_demand, ctx->shard_count, ctx->shard_first, halo);
     }
     // scalars of the whole table
     u64 sc[2] = {ctx->maxbranchdepth, ctx->longest}, all[2 * ESA_MAX_RANKS];

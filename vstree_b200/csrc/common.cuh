@@ -163,6 +163,25 @@ struct KernelProfiler
   }
 };
 
+// Depth schedule of the refinement rounds after the initial h0-mer sort: rounds 1..text_rounds extend the order by
+// text_len symbols read from the text itself (no rank array needed), later rounds double.  Round t starts from
+// groups that agree on round_start_depth(t) symbols (the lcp lower bound of a slot split off in round t).
+struct DepthSched
+{
+  u32 h0 = 0, text_len = 0, text_rounds = 0;
+};
+__host__ __device__ __forceinline__ u32 round_start_depth(const DepthSched &ds, u32 round /* >= 1 */)
+{
+  const u32 t = round - 1;
+  if (t <= ds.text_rounds)
+  {
+    return ds.h0 + t * ds.text_len;
+  }
+  const u32 sh = t - ds.text_rounds;
+  const u64 d = (u64) (ds.h0 + ds.text_rounds * ds.text_len) << (sh < 32 ? sh : 32);
+  return d > 0xffffffffull ? 0xffffffffu : (u32) d;
+}
+
 struct esa_comm;
 struct esa_ctx
 {
@@ -179,6 +198,9 @@ struct esa_ctx
   u64 *d_pk = nullptr;   // 2-bit packed text (sigma <= 4 only), see textcmp.cuh
   u32 *d_spm = nullptr;  // special mask of the packed text
   u8 *d_hround = nullptr;  // [N] doubling round in which slot r became a group head (lcp lower bound), 0 = initial sort
+  DepthSched sched;        // depth schedule of the last sort (turns d_hround entries into lcp lower bounds)
+  bool isa_valid = false;  // d_isa holds the inverse suffix array (a sort that ends inside the text rounds never
+                           // scatters ranks; consumers call ensure_isa)
   u64 lcp_work_estimate = 0;  // sum over rounds of active * depth / 32 (window compares of the direct lcp path)
   int lcp_mode = 0;           // 0 auto, 1 direct (suffix-array order), 2 plcp (text order)
   u64 n = 0;
@@ -294,10 +316,10 @@ struct RadixRemoteDst
 void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes);
 
-// doubling_sort.cu: the sort of one doubling round (list grouped by key >> shift; sorts by key bits [0, 2*shift));
-// same return convention as radix_sort_pairs_u64
-int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, void *sort_temp,
-                  size_t temp_bytes);
+// doubling_sort.cu: the sort of one refinement round (list grouped by key >> shift; sorts by key bits [0, end_bit),
+// end_bit > shift); same return convention as radix_sort_pairs_u64
+int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, u32 end_bit,
+                  void *sort_temp, size_t temp_bytes);
 
 // suffix_sort.cu: fills ctx->d_sa, ctx->d_isa (and ctx->d_bck when demanded) ; returns stats pieces
 struct SortOutcome
@@ -308,6 +330,8 @@ struct SortOutcome
   u64 num_sorted;   // suffixes that went through the sort (N - specials - 1)
 };
 void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *outcome, size_t scratch_mark);
+// d_isa[d_sa[r]] = r for the whole table unless the sort left it valid already (single-GPU contexts only)
+void ensure_isa(esa_ctx *ctx);
 // sharded variant (one rank of a communicator); sets ctx->d_sa / d_hround (shard-local, arena high side),
 // ctx->shard_first / shard_count, the replicated ctx->d_isa and ctx->d_bck
 void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
@@ -315,12 +339,12 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
 
 // lcp.cu: V[i] = i + PLCP[i] for all text positions (ctx->d_plcpv)
 void compute_plcp(esa_ctx *ctx, u32 *d_v);
-void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 h0, u32 halo_prev);
+void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev);
 
 // derive.cu
 void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base);
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu  // d_v == NULL with lcp demanded: direct lcp
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 void compute_skp(esa_ctx *ctx, const u32 *d_v, const u32 *d_lcpfull);  // skp.cu
 int run_checks(esa_ctx *ctx, std::string &msg);

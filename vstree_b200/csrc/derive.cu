@@ -320,6 +320,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 in
 void compute_sti1(esa_ctx *ctx, u32 prefixlength)
 {
   const u64 N = ctx->n + 1;
+  ensure_isa(ctx);
   ctx->d_sti1 = ctx->arena.alloc<u8>(N + KS_TILE);
   const KmerParams kp = make_kmer_params(ctx->sigma, prefixlength);
   const u32 tiles = (u32) div_up_u64(N, KS_TILE);
@@ -331,6 +332,7 @@ void compute_sti1(esa_ctx *ctx, u32 prefixlength)
 void widen_isa(esa_ctx *ctx)
 {
   const u64 N = ctx->n + 1;
+  ensure_isa(ctx);
   ctx->d_sti64 = ctx->arena.alloc<u64>(N);
   ESA_LAUNCH(ctx, ESA_K_FINALIZE, 12.0 * N,
              (widen_kernel<<<div_up_u32(N, 256), 256, 0, ctx->stream>>>(ctx->d_isa, ctx->d_sti64, N)));
@@ -340,6 +342,7 @@ int run_checks(esa_ctx *ctx, std::string &msg)
 {
   const u64 N = ctx->n + 1;
   cudaStream_t s = ctx->stream;
+  ensure_isa(ctx);
   const size_t mark = ctx->arena.mark();
   u32 *d_err = ctx->arena.alloc<u32>(8);
   CUDA_CHECK(cudaMemsetAsync(d_err, 0, 8 * sizeof(u32), s));

@@ -227,10 +227,11 @@ __global__ void __launch_bounds__(1024) ds_scan_kernel(u32 *counts, u32 ntiles, 
 
 }  // namespace
 
-// Sorts (keys_a, pos_a)[0..m) by key bits [0, 2*shift) given that the list is grouped by key >> shift.
+// Sorts (keys_a, pos_a)[0..m) by key bits [0, end_bit) given that the list is grouped by key >> shift (rank rounds:
+// end_bit = 2*shift; text rounds: shift + width of the text key).  Stable.
 // Returns 0 when the result is in (keys_a, pos_a), 1 when it is in (keys_b, pos_b).
-int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, void *sort_temp,
-                  size_t temp_bytes)
+int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, u32 end_bit,
+                  void *sort_temp, size_t temp_bytes)
 {
   static const bool disabled = getenv("ESA_NO_LOCAL_SORT") != nullptr;
   if (m <= 1)
@@ -239,7 +240,7 @@ int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b
   }
   if (disabled || m < 4096 || ctx->arena.high - ctx->arena.top < 16 * m + ((size_t) 4 << 20))
   {
-    return radix_sort_pairs_u64(ctx, keys_a, keys_b, pos_a, pos_b, m, 0, 2 * shift, sort_temp, temp_bytes);
+    return radix_sort_pairs_u64(ctx, keys_a, keys_b, pos_a, pos_b, m, 0, end_bit, sort_temp, temp_bytes);
   }
   cudaStream_t s = ctx->stream;
   Arena &ar = ctx->arena;
@@ -257,7 +258,7 @@ int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b
   if (2 * nspill > m)
   {
     ar.rewind(mark);
-    return radix_sort_pairs_u64(ctx, keys_a, keys_b, pos_a, pos_b, m, 0, 2 * shift, sort_temp, temp_bytes);
+    return radix_sort_pairs_u64(ctx, keys_a, keys_b, pos_a, pos_b, m, 0, end_bit, sort_temp, temp_bytes);
   }
   ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 24.0 * m,
              (ds_local_kernel<<<tiles, DS_THREADS, 0, s>>>(keys_a, pos_a, m, shift, keys_b, pos_b)));
@@ -267,7 +268,7 @@ int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b
     u32 *sp_a = ar.alloc<u32>(nspill + 8), *sp_b = ar.alloc<u32>(nspill + 8), *sidx = ar.alloc<u32>(nspill + 8);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, (double) m + 28.0 * nspill,
                (ds_collect_kernel<<<tiles, DS_THREADS, 0, s>>>(keys_a, pos_a, flags, m, tile_spill, sk_a, sp_a, sidx)));
-    const int w = radix_sort_pairs_u64(ctx, sk_a, sk_b, sp_a, sp_b, nspill, 0, 2 * shift, sort_temp, temp_bytes);
+    const int w = radix_sort_pairs_u64(ctx, sk_a, sk_b, sp_a, sp_b, nspill, 0, end_bit, sort_temp, temp_bytes);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 28.0 * nspill,
                (ds_scatter_back_kernel<<<div_up_u32(nspill, 256), 256, 0, s>>>(w ? sk_b : sk_a, w ? sp_b : sp_a, sidx,
                                                                                nspill, keys_b, pos_b)));

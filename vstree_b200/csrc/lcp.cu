@@ -203,7 +203,7 @@ plcp_fill_kernel(u32 *__restrict__ v, u64 N, const u32 *__restrict__ tile_carry)
 // split from its predecessor: the comparison starts there (lcp.cu header of lcp_direct.cu).
 template <typename Text>
 __global__ void __launch_bounds__(256)
-plcp_irreducible_shard_kernel(Text text, u64 count, const u32 *__restrict__ sa, const u8 *__restrict__ hround, u32 h0,
+plcp_irreducible_shard_kernel(Text text, u64 count, const u32 *__restrict__ sa, const u8 *__restrict__ hround, DepthSched sched,
                               u64 index_base, u32 halo_prev, u32 *__restrict__ v)
 {
   const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +224,7 @@ plcp_irreducible_shard_kernel(Text text, u64 count, const u32 *__restrict__ sa, 
     return;  // reducible: takes the value of its left neighbour in text order
   }
   const u32 hr = hround != nullptr ? hround[r] : 0u;
-  const u32 lb = hr ? (h0 << (hr - 1)) : 0u;
+  const u32 lb = hr ? round_start_depth(sched, hr) : 0u;
   v[i] = i + text.lcp(i, j, lb);
 }
 
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(PL_THREADS) plcp_tile_last_kernel(const u32 *_
 }  // namespace
 
 // sharded text-order plcp: every rank ends up with the complete V array
-void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 h0, u32 halo_prev)
+void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev)
 {
   const u64 n = ctx->n, N = n + 1;
   cudaStream_t s = ctx->stream;
@@ -299,13 +299,13 @@ void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 h0, u32 ha
       TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
       ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
                  (plcp_irreducible_shard_kernel<TextPacked2><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
-                                                                                   h0, ctx->shard_first, halo_prev, d_v)));
+                                                                                   ctx->sched, ctx->shard_first, halo_prev, d_v)));
     } else
     {
       TextBytes text{ctx->d_tis};
       ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
                  (plcp_irreducible_shard_kernel<TextBytes><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
-                                                                                 h0, ctx->shard_first, halo_prev, d_v)));
+                                                                                 ctx->sched, ctx->shard_first, halo_prev, d_v)));
     }
   }
   comm_allreduce_min_u32(ctx, comm, d_v, N);
@@ -318,6 +318,7 @@ void compute_plcp(esa_ctx *ctx, u32 *d_v)
 {
   const u64 n = ctx->n, N = n + 1;
   cudaStream_t s = ctx->stream;
+  ensure_isa(ctx);
   const u32 tiles = (u32) div_up_u64(N, PL_TILE);
   u32 *tile_last = ctx->arena.alloc<u32>(tiles);
   // algorithmic bytes: isa 4 + sa gather 4 + two symbols 2 + V write 4, plus the compared windows (data dependent)

@@ -4,7 +4,7 @@
 // The reference also compares neighbours directly at bucket borders (GETLCP, src/Mkvtree/bese.c:91-95) and gets the
 // rest from the depth at which its multikey quicksort split a group (SETLCP1, bese.c:827-846).  The same idea drives
 // this kernel: the prefix-doubling sorter records, per suffix-array slot, the round in which the slot became a group
-// head (ctx->d_hround).  Round t split groups that agreed on h = h0*2^(t-1) symbols and orders them by 2h symbols,
+// head (ctx->d_hround).  Round t split groups that agreed on round_start_depth(t) symbols (h0*2^(t-1) for pure doubling),
 // so lcp[r] lies in [h, 2h): the comparison starts at offset h and needs at most h/32 + 1 packed windows.
 // Everything is read in suffix-array order (coalesced), the only random accesses go to the text, which for DNA is
 // 2-bit packed and stays L2-resident up to ~300 Mbp.  No inverse suffix array and no plcp array are needed.
@@ -56,7 +56,7 @@ pack2_kernel(const u8 *__restrict__ tis, u64 n, u64 padded_len, u64 words, u64 *
 template <typename Text>
 __global__ void __launch_bounds__(FN_THREADS)
 finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *__restrict__ sa,
-                       const u8 *__restrict__ hround, u32 h0, bool want_lcp, u8 *__restrict__ lcp8,
+                       const u8 *__restrict__ hround, DepthSched sched, bool want_lcp, u8 *__restrict__ lcp8,
                        u32 *__restrict__ lcpfull, u8 *__restrict__ bwt, u64 *__restrict__ suf64,
                        u32 *__restrict__ tile_large, unsigned long long *__restrict__ scalars, u64 index_base,
                        u32 halo_prev)
@@ -122,7 +122,7 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
         }
         if (want_lcp && q < cnt && index_base + r0 + q > 0)
         {
-          const u32 lb = hr[q] ? (h0 << (hr[q] - 1)) : 0u;
+          const u32 lb = hr[q] ? round_start_depth(sched, hr[q]) : 0u;
           // pairs split by a doubling round agree on lb symbols: start there (at most lb/WINDOW + 1 steps)
           const u32 stop = lb == 0 ? Text::probe_stop(pr[q], pr[q + 1]) : text.step((u64) s[q] + lb, (u64) s[q + 1] + lb);
           l[q] = lb + stop;
@@ -229,7 +229,7 @@ void pack_text(esa_ctx *ctx)
 }
 
 // lcp (when demanded) by direct comparison; fills d_lcp, d_llv, d_bwt, d_suf64, maxbranchdepth, longest, nllv
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 index_base, u32 halo_prev)
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev)
 {
   // count entries of ctx->d_sa (the whole table on one GPU, this rank's shard otherwise)
   const u64 N = count;
@@ -263,14 +263,14 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u32 h0, u64 count, u64 ind
     TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextPacked2><<<tiles, FN_THREADS, 0, s>>>(
-                   text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, h0, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
+                   text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
                    ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
   } else
   {
     TextBytes text{ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextBytes><<<tiles, FN_THREADS, 0, s>>>(
-                   text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, h0, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
+                   text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
                    ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
   }
   if (want_lcp)

@@ -13,9 +13,15 @@
 //   3. .bck from the sorted keys (k <= h0 always holds): left = lower bound of the k-mer, mid = next left minus
 //      the number of suffixes of the bucket with a special inside the k-prefix (mkvprocess.c:251-327).
 //   4. regroup: equal keys form a group; rank[pos] = index of the group's first element; singletons are final.
-//   5. doubling rounds on the ACTIVE set only: sort by (rank[s], rank[s+h]) as one 64-bit key, regroup, h *= 2.
+//   5. refinement rounds on the ACTIVE set only: sort by (rank[s], key2) as one 64-bit key, regroup.
+//      Round 1 (ESA_TEXT_ROUNDS rounds, default 1) takes key2 straight from the text: the next L symbols behind the h
+//      the group agrees on, L as large as the free key bits allow (DNA: 16 symbols for n < 2^27), h += L.  Inputs
+//      without long repeats end here, and then no rank array was ever needed: the N-wide scatter rank[pos] = slot of
+//      the first regroup is DEFERRED (the ranks are kept in suffix-array order, a sequential write) and only carried
+//      out when a doubling round follows.  Later rounds: key2 = rank[s+h], h *= 2.
 #include "kmer_scan.cuh"
 #include "scan.cuh"
+#include "textcmp.cuh"
 
 void radix_sort_init();
 
@@ -289,7 +295,7 @@ constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
 template <typename KeyT, bool FIRST>
 __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m,
                                          u64 tile_base, KeyT *skey /* [RG_TILE+2] */, u32 *sslot, u8 *sflag,
-                                         u32 slot_base)
+                                         u32 slot_base, KeyT single_mask)
 {
 #pragma unroll
   for (int j = 0; j < RG_ITEMS; j++)
@@ -322,12 +328,11 @@ __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u3
       const KeyT k = skey[l + 1];
       bool head = (t == 0) || (k != skey[l]);
       bool next_head = (t + 1 == m) || (skey[l + 2] != k);
-      if (FIRST)
-      {
-        // a key with the flag bit is a suffix with a special inside its h0-prefix: unique by construction
-        head = head || ((k & 1) != 0);
-        next_head = next_head || ((t + 1 < m) && ((skey[l + 2] & 1) != 0));
-      }
+      // a key with flag bits set (initial sort: bit 0; text rounds: the low flag field) belongs to a suffix with a
+      // special inside the symbols the key covers: such suffixes are unique, and equal keys among them already stand
+      // in text order (every sort is stable), which is their final order (bese.c:26-55: specials compare by position)
+      head = head || ((k & single_mask) != 0);
+      next_head = next_head || ((t + 1 < m) && ((skey[l + 2] & single_mask) != 0));
       sflag[l] = (u8) ((head ? 1 : 0) | ((head && next_head) ? 0 : 2));
     } else
     {
@@ -340,14 +345,14 @@ __device__ __forceinline__ void rg_flags(const KeyT *__restrict__ keys, const u3
 template <typename KeyT, bool FIRST>
 __global__ void __launch_bounds__(RG_THREADS)
 regroup_summary_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m,
-                       u32 *__restrict__ tile_maxrank, u32 *__restrict__ tile_active, u32 slot_base)
+                       u32 *__restrict__ tile_maxrank, u32 *__restrict__ tile_active, u32 slot_base, KeyT single_mask)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
   __shared__ __align__(8) u8 sflag[RG_TILE];
   __shared__ u32 red[2][RG_THREADS / 32];
   const u64 tile_base = (u64) blockIdx.x * RG_TILE;
-  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base);
+  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base, single_mask);
   u32 mx = 0, cnt = 0;
 #pragma unroll
   for (int j = 0; j < RG_ITEMS; j++)
@@ -439,9 +444,13 @@ __global__ void __launch_bounds__(RG_THREADS)
 regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slots, u64 m,
                      const u32 *__restrict__ tile_maxrank, const u32 *__restrict__ tile_active, u32 *__restrict__ sa,
                      u32 *__restrict__ rank, u64 *__restrict__ next_key, u32 *__restrict__ next_pos,
-                     u32 *__restrict__ next_slots, u32 rank_shift, u8 *__restrict__ hround, u32 round,
+                     u32 *__restrict__ next_slots, u32 rank_shift /* of the keys read */,
+                     u32 next_shift /* of the keys written for the next round */, u8 *__restrict__ hround, u32 round,
                      u32 *__restrict__ rank_out /* if set: rank_out[t] = rank instead of the scatter rank[pos] */,
-                     u32 slot_base /* first global slot of this shard; sa and hround are shard-local arrays */)
+                     u32 slot_base /* first global slot of this shard; sa and hround are shard-local arrays */,
+                     KeyT single_mask,
+                     u32 *__restrict__ rank_slot /* if set: rank_slot[slot - slot_base] = rank and nothing else (the
+                                                    rank list in suffix-array order of a deferred scatter) */)
 {
   __shared__ KeyT skey[RG_TILE + 2];
   __shared__ u32 sslot[RG_TILE];
@@ -451,7 +460,7 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
   __shared__ u32 scratch[RG_THREADS / 32 + 1];
   __shared__ u32 sincl[RG_THREADS];
   const u64 tile_base = (u64) blockIdx.x * RG_TILE;
-  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base);
+  rg_flags<KeyT, FIRST>(keys, slots, m, tile_base, skey, sslot, sflag, slot_base, single_mask);
   // blocked phase: thread owns local items [tid*8, tid*8+8)
   const int b0 = threadIdx.x * RG_ITEMS;
   const u64 f8 = *reinterpret_cast<const u64 *>(sflag + b0);
@@ -502,7 +511,10 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
       {
         sa[slot - slot_base] = p;  // FIRST: the sorted position buffer already is sa[0..m)
       }
-      if (rank_out != nullptr)
+      if (rank_slot != nullptr)
+      {
+        rank_slot[slot - slot_base] = r;
+      } else if (rank_out != nullptr)
       {
         rank_out[t] = r;
       } else
@@ -511,7 +523,7 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
       }
       if (d != NONE32)
       {
-        next_key[d] = (u64) r << rank_shift;
+        next_key[d] = (u64) r << next_shift;
         next_pos[d] = p;
         next_slots[d] = slot;
       }
@@ -528,7 +540,111 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
   }
 }
 
-// 5. doubling key: low bits = rank of the suffix h symbols further
+// 5a. text round: low key bits = the next L symbols behind the h the group agrees on, as an order-preserving code.
+// Window of L letters: code (base sigma, first symbol in the top digit) << F.  A special (or the end of the text) at
+// offset d < L: the letters in front of it padded with the largest letter, flag field = L - d > 0 in the low F bits.
+// This orders exactly like the symbols do (bese.c:26-55: a special is larger than every letter): the padded code is
+// >= the code of every window with the same d letters in front, equal codes are split by the flag (full window
+// first, then the later special first), and equal flagged keys differ only in the POSITION of their special, i.e.
+// stand in text order already -- regroup makes every flagged key a singleton.
+struct TextKeyParams
+{
+  const u8 *tis;
+  TextPacked2 packed;  // packed.pk == nullptr: byte path
+  u32 len;             // L
+  u32 flag_bits;       // F = bits_for(L)
+  u32 sigma;
+};
+__global__ void __launch_bounds__(256)
+text_key_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h, TextKeyParams tk)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m)
+  {
+    return;
+  }
+  const u64 q = (u64) pos[t] + h;  // <= n: an active suffix has no special among its first h symbols
+  const u32 L = tk.len;
+  u64 code = 0;
+  u32 flag = 0;
+  if (tk.packed.pk != nullptr)
+  {
+    const u64 w = tk.packed.window(q);
+    const u32 msk = tk.packed.mask_window(q);
+    const u32 d = msk ? (u32) (__ffs((int) msk) - 1) : 32u;
+    u64 r = __brevll(w);
+    r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+    code = r >> (64 - 2 * L);
+    if (d < L)
+    {
+      code |= ((u64) 1 << (2 * (L - d))) - 1;
+      flag = L - d;
+    }
+  } else
+  {
+    for (u32 i = 0; i < L; i++)
+    {
+      const u32 a = tk.tis[q + i];  // tis is padded with 255 behind position n
+      if (a >= ESA_WILDCARD)
+      {
+        for (u32 j = i; j < L; j++)
+        {
+          code = code * tk.sigma + (tk.sigma - 1);
+        }
+        flag = L - i;
+        break;
+      }
+      code = code * tk.sigma + a;
+    }
+  }
+  key[t] |= (code << tk.flag_bits) | (u64) flag;
+}
+
+// number of symbols a text key can hold in `free_bits` bits, and the width of the key
+struct TextKeyShape
+{
+  u32 len, code_bits, flag_bits;
+};
+TextKeyShape text_key_shape(u32 sigma, u32 free_bits, bool packed)
+{
+  TextKeyShape best{0, 0, 0};
+  const u32 max_len = 28;
+  double pw = 1.0;
+  for (u32 L = 1; L <= max_len; L++)
+  {
+    pw *= (double) sigma;
+    u32 cb = 0;
+    if (packed || sigma == 4)
+    {
+      cb = 2 * L;
+    } else
+    {
+      if (pw > 72057594037927936.0)  // 2^56
+      {
+        break;
+      }
+      cb = bits_for((u64) pw - 1);
+    }
+    const u32 fb = bits_for(L);
+    if (cb + fb > free_bits || cb + fb > 56)
+    {
+      break;
+    }
+    best = TextKeyShape{L, cb, fb};
+  }
+  return best;
+}
+
+u32 text_rounds_setting()
+{
+  static const int v = [] {
+    const char *e = getenv("ESA_TEXT_ROUNDS");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return (u32) (v < 0 ? 0 : (v > 8 ? 8 : v));
+}
+
+// 5b. doubling key: low bits = rank of the suffix h symbols further
 __global__ void gather_rank_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h,
                                    const u32 *__restrict__ rank)
 {
@@ -601,6 +717,108 @@ ScatterScratch round_scatter_scratch(Arena &ar, u64 m, u32 pos_bits)
     sc.tv = ar.alloc<u32>(m + 64);
   }
   return sc;
+}
+
+__global__ void iota_kernel(u32 *__restrict__ v, u64 count)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    v[t] = (u32) t;
+  }
+}
+
+__global__ void scatter_iota_kernel(const u32 *__restrict__ sa, u64 count, u32 *__restrict__ isa)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    isa[sa[t]] = (u32) t;
+  }
+}
+
+// Shape of the refinement rounds of one build: which rounds take their secondary key from the text, how wide the
+// keys of a round are, and the state of the deferred rank scatter.
+struct RefinePlan
+{
+  u32 rank_shift = 0;   // bits of a rank: secondary-key width of the doubling rounds
+  u32 text_rounds = 0;  // rounds 1..text_rounds are text rounds
+  TextKeyShape tks{0, 0, 0};
+  TextKeyParams tk;
+  u32 *rank_sa = nullptr;  // ranks in suffix-array order (one entry per sorted suffix of this device)
+  bool pending = false;    // the scatter rank[sa[t]] = rank_sa[t] has not been carried out yet
+
+  bool is_text(u32 round) const { return round >= 1 && round <= text_rounds; }
+  // a round's key is rank << shift | secondary key
+  u32 shift_of(u32 round) const { return is_text(round) ? tks.code_bits + tks.flag_bits : rank_shift; }
+  u64 mask_of(u32 round) const { return is_text(round) ? ((u64) 1 << tks.flag_bits) - 1 : 0; }
+};
+
+RefinePlan make_refine_plan(esa_ctx *ctx, u32 rank_shift, u32 h0)
+{
+  RefinePlan plan;
+  plan.rank_shift = rank_shift;
+  const bool packed = ctx->d_pk != nullptr;
+  plan.tks = text_key_shape(ctx->sigma, 64 - rank_shift, packed);
+  plan.text_rounds = plan.tks.len > 0 ? text_rounds_setting() : 0;
+  plan.tk.tis = ctx->d_tis;
+  plan.tk.packed = TextPacked2{packed ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
+  plan.tk.len = plan.tks.len;
+  plan.tk.flag_bits = plan.tks.flag_bits;
+  plan.tk.sigma = ctx->sigma;
+  ctx->sched = DepthSched{h0, plan.text_rounds > 0 ? plan.tks.len : 0, plan.text_rounds};
+  return plan;
+}
+
+// The scatter of the first regroup is deferred when a text round follows it (or no round at all) and the arena has
+// room for the rank list; M = sorted suffixes of this device, m = active ones.
+void plan_deferred_scatter(esa_ctx *ctx, RefinePlan &plan, u64 M, u64 m)
+{
+  Arena &ar = ctx->arena;
+  plan.pending = false;
+  if (plan.text_rounds == 0 && m > 0)
+  {
+    return;
+  }
+  const size_t need = 4 * (M + 64) + 20 * (m + 64) + ((size_t) 64 << 20);
+  if (ar.high - ar.top < need)
+  {
+    return;
+  }
+  plan.rank_sa = ar.alloc<u32>(M + 64);
+  plan.pending = true;
+}
+
+// carries the deferred scatter out (before the first round that reads rank[]); sa = this device's suffix array
+void flush_deferred_scatter(esa_ctx *ctx, RefinePlan &plan, const u32 *sa, u64 M, u32 *rank, void *sort_temp,
+                            size_t temp_bytes)
+{
+  if (!plan.pending)
+  {
+    return;
+  }
+  plan.pending = false;
+  if (M == 0)
+  {
+    return;
+  }
+  Arena &ar = ctx->arena;
+  const size_t mark = ar.mark();
+  bool done = false;
+  if (M >= PARTITIONED_SCATTER_MIN && plan.rank_shift > SCATTER_WINDOW_BITS
+      && ar.high - ar.top > 8 * (M + 64) + ((size_t) 8 << 20))
+  {
+    u32 *tp = ar.alloc<u32>(M + 64), *tv = ar.alloc<u32>(M + 64);
+    done = scatter_ranks_partitioned(ctx, const_cast<u32 *>(sa), plan.rank_sa, M, plan.rank_shift, rank, tp, tv,
+                                     sort_temp, temp_bytes);
+  }
+  if (!done)
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * M,
+               (scatter_rank_kernel<<<div_up_u32(div_up_u64(M, 4), 256), 256, 0, ctx->stream>>>(sa, plan.rank_sa, M,
+                                                                                                   rank)));
+  }
+  ar.rewind(mark);
 }
 
 u64 read_scalar(esa_ctx *ctx, const u64 *d_scalars, int idx)
@@ -737,16 +955,19 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   outcome->active_sum = 0;
   outcome->active_first = 0;
   outcome->num_sorted = M;
+  ctx->isa_valid = true;
   if (M == 0)
   {
+    ctx->sched = DepthSched{h0, 0, 0};
     return;
   }
-  const u32 rank_shift = bits_for(N - 1);  // doubling key = rank << rank_shift | rank of the suffix h further
+  RefinePlan plan = make_refine_plan(ctx, bits_for(N - 1), h0);
+  const u32 rank_shift = plan.rank_shift;
   u32 rtiles = (u32) div_up_u64(M, RG_TILE);
   u32 *tile_maxrank = ar.alloc<u32>(rtiles), *tile_active = ar.alloc<u32>(rtiles);
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
              (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
-                                                                                tile_active, 0u)));
+                                                                                tile_active, 0u, 1u)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0,
              (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
   u64 m = read_scalar(ctx, d_scalars, 4);
@@ -757,11 +978,14 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   const u64 mal = m + 64;
   u64 *dk_in = ar.alloc<u64>(mal);
   u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
-  // two-level rank scatter of the first regroup: its scratch costs nothing -- the rank list in suffix-array order
-  // goes into the position buffer the sort did not end in, the partitioned copy into the two key buffers, which are
-  // dead once regroup_apply has read the sorted keys
+  // rank scatter of the first regroup: deferred when text rounds follow (or nothing follows): the rank list in
+  // suffix-array order is kept, the N-wide scatter happens only if a doubling round needs rank[].  Otherwise
+  // two-level, and its scratch costs nothing -- the rank list in suffix-array order goes into the position buffer the
+  // sort did not end in, the partitioned copy into the two key buffers, which are dead once regroup_apply has read
+  // the sorted keys
+  plan_deferred_scatter(ctx, plan, M, m);
   u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
-  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
+  if (!plan.pending && M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
   {
     part_rank = spos == pos_a ? pos_b : pos_a;
     part_tp = key_a;
@@ -770,33 +994,41 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
              (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
                                                                               tile_active, sa, rank, dk_in, dp_in,
-                                                                              slots_cur, rank_shift, nullptr, 0u,
-                                                                              part_rank, 0u)));
+                                                                              slots_cur, 0u, plan.shift_of(1), nullptr, 0u,
+                                                                              plan.pending ? plan.rank_sa : part_rank,
+                                                                              0u, 1u, nullptr)));
   if (part_rank != nullptr)
   {
     scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
-  }
-  if (m == 0)
-  {
-    return;
   }
   // partners carved out of region X (key_a .. pos_b are contiguous allocations of 4*Mal words = 16*Mal bytes)
   u64 *dk_out = reinterpret_cast<u64 *>(key_a);          // 8*mal bytes  <= 8*Mal  (key_a + key_b)
   u32 *dp_out = pos_a;                                    // 4*mal bytes
   u32 *slots_next = pos_b;                                // 4*mal bytes
 
-  // ---- 5. doubling
+  // ---- 5. refinement rounds
   u64 h = h0;
   while (m > 0)
   {
-    outcome->rounds++;
+    const u32 round = ++outcome->rounds;
+    const bool text_round = plan.is_text(round);
+    const u32 cur_shift = plan.shift_of(round);
     outcome->active_sum += m;
     ctx->lcp_work_estimate += m * (h / 32 + 1);
-    ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
-               (gather_rank_kernel<<<div_up_u32(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, rank)));
+    if (text_round)
+    {
+      ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 20.0 * m,
+                 (text_key_kernel<<<div_up_u32(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, plan.tk)));
+    } else
+    {
+      flush_deferred_scatter(ctx, plan, sa, M, rank, sort_temp, temp_bytes);
+      ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
+                 (gather_rank_kernel<<<div_up_u32(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, rank)));
+    }
     u64 *ks = dk_in, *ko = dk_out;
     u32 *ps = dp_in, *po = dp_out;
-    if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
+    if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, cur_shift, cur_shift + rank_shift, sort_temp,
+                               temp_bytes))
     {
       ks = dk_out;
       ko = dk_in;
@@ -806,18 +1038,21 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     rtiles = (u32) div_up_u64(m, RG_TILE);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
                (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                   tile_active, 0u)));
+                                                                                   tile_active, 0u,
+                                                                                   plan.mask_of(round))));
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
     const u64 m_next = read_scalar(ctx, d_scalars, 4);
     const size_t scatter_mark = ar.mark();
-    const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
+    const ScatterScratch sc = plan.pending ? ScatterScratch() : round_scatter_scratch(ar, m, rank_shift);
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
                (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
                                                                                  tile_active, sa, rank, ko, po,
-                                                                                 slots_next, rank_shift,
-                                                                                 ctx->d_hround, outcome->rounds,
-                                                                                 sc.rank_out, 0u)));
+                                                                                 slots_next, cur_shift,
+                                                                                 plan.shift_of(round + 1),
+                                                                                 ctx->d_hround, round, sc.rank_out, 0u,
+                                                                                 plan.mask_of(round),
+                                                                                 plan.pending ? plan.rank_sa : nullptr)));
     if (sc.rank_out != nullptr)
     {
       scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
@@ -831,12 +1066,46 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     slots_cur = slots_next;
     slots_next = t;
     m = m_next;
-    h *= 2;
+    h = text_round ? h + plan.tks.len : h * 2;
     if (outcome->rounds > 64)
     {
       esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
     }
   }
+  ctx->isa_valid = !plan.pending;  // a sort that ended inside the text rounds never needed rank[]: see ensure_isa
+}
+
+// the inverse suffix array for its consumers (plcp, sti1, .sti, esa_check) when the sorter did not leave it behind
+void ensure_isa(esa_ctx *ctx)
+{
+  if (ctx->isa_valid || ctx->d_sa == nullptr || ctx->d_isa == nullptr)
+  {
+    return;
+  }
+  const u64 N = ctx->n + 1;
+  Arena &ar = ctx->arena;
+  const size_t mark = ar.mark();
+  const u32 pos_bits = bits_for(N - 1);
+  bool done = false;
+  if (N >= PARTITIONED_SCATTER_MIN && pos_bits > SCATTER_WINDOW_BITS)
+  {
+    const size_t need = 12 * (N + 64) + radix_sort_temp_bytes(N, 4) + ((size_t) 8 << 20);
+    if (ar.high - ar.top > need)
+    {
+      u32 *val = ar.alloc<u32>(N + 64), *tp = ar.alloc<u32>(N + 64), *tv = ar.alloc<u32>(N + 64);
+      const size_t tb = radix_sort_temp_bytes(N, 4);
+      void *temp = ar.alloc<char>(tb);
+      ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * N, (iota_kernel<<<div_up_u32(N, 256), 256, 0, ctx->stream>>>(val, N)));
+      done = scatter_ranks_partitioned(ctx, ctx->d_sa, val, N, pos_bits, ctx->d_isa, tp, tv, temp, tb);
+    }
+  }
+  if (!done)
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * N,
+               (scatter_iota_kernel<<<div_up_u32(N, 256), 256, 0, ctx->stream>>>(ctx->d_sa, N, ctx->d_isa)));
+  }
+  ar.rewind(mark);
+  ctx->isa_valid = true;
 }
 
 // =========================================================================================================
@@ -855,7 +1124,6 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 //   All per-rank work is O(N/G) except the text upload; the exchange volume is 8 bytes per suffix once plus 8 bytes per
 //   active suffix and round.
 #include "comm.cuh"
-#include "textcmp.cuh"
 
 namespace
 {
@@ -1418,7 +1686,9 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   outcome->active_sum = 0;
   outcome->active_first = 0;
   outcome->num_sorted = M;
-  const u32 rank_shift = max(bits_for(N - 1), 8u);
+  ctx->isa_valid = false;  // rank[] of a sharded build only ever holds the entries of the suffixes a rank owns
+  RefinePlan plan = make_refine_plan(ctx, max(bits_for(N - 1), 8u), h0);
+  const u32 rank_shift = plan.rank_shift;
   const u32 owner_bits = bits_for((u64) G - 1);
   u32 rtiles = (u32) div_up_u64(M, RG_TILE);
   u32 *tile_maxrank = ar.alloc<u32>(rtiles + 1), *tile_active = ar.alloc<u32>(rtiles + 1);
@@ -1427,7 +1697,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   {
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
                (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
-                                                                                  tile_active, slot_base)));
+                                                                                  tile_active, slot_base, 1u)));
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
     m = read_scalar(ctx, d_scalars, 4);
@@ -1436,8 +1706,14 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   const u64 mal = m + 64;
   u64 *dk_in = ar.alloc<u64>(mal);
   u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
+  // the scatter of the first regroup is deferred like on one GPU; whether a doubling round follows the text rounds
+  // is a property of all ranks together (a rank without active suffixes still owns ranks others will ask for)
+  if (plan.text_rounds > 0)
+  {
+    plan_deferred_scatter(ctx, plan, M, m);
+  }
   u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
-  if (M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
+  if (!plan.pending && M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
   {
     part_rank = spos == pos_a ? pos_b : pos_a;  // scratch of the first scatter lives in the dead sort buffers
     part_tp = key_a;
@@ -1448,8 +1724,10 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
                (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
                                                                                 tile_active, sa, rank, dk_in, dp_in,
-                                                                                slots_cur, rank_shift, nullptr, 0u,
-                                                                                part_rank, slot_base)));
+                                                                                slots_cur, 0u, plan.shift_of(1), nullptr,
+                                                                                0u,
+                                                                                plan.pending ? plan.rank_sa : part_rank,
+                                                                                slot_base, 1u, nullptr)));
     if (part_rank != nullptr)
     {
       scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
@@ -1460,56 +1738,132 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u32 *dp_out = pos_a;
   u32 *slots_next = pos_b;
 
-  // ---- 5. doubling, all ranks in lock step until no rank has an active suffix left
+  // ---- 5. refinement rounds, all ranks in lock step until no rank has an active suffix left
   KeyFromText keyof;
   keyof.tis = ctx->d_tis;
   keyof.packed = TextPacked2{sigma == 4 ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
   keyof.kp = kp;
+  // sort + regroup of one round on this rank (the secondary keys are in place); returns the next active count
+  auto sort_and_regroup = [&](u32 round) -> u64 {
+    const u32 cur_shift = plan.shift_of(round);
+    u64 *ks = dk_in, *ko = dk_out;
+    u32 *ps = dp_in, *po = dp_out;
+    if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, cur_shift, cur_shift + rank_shift, sort_temp,
+                               temp_bytes))
+    {
+      ks = dk_out, ko = dk_in;
+      ps = dp_out, po = dp_in;
+    }
+    rtiles = (u32) div_up_u64(m, RG_TILE);
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
+               (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
+                                                                                   tile_active, slot_base,
+                                                                                   plan.mask_of(round))));
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+               (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
+    const u64 m_next = read_scalar(ctx, d_scalars, 4);
+    dk_in = ks, dk_out = ko;  // sorted lists; apply_round reads them
+    dp_in = ps, dp_out = po;
+    return m_next;
+  };
+  // new ranks, suffix array entries and the next active list of one round on this rank
+  auto apply_round = [&](u32 round, u64 m_next) {
+    const size_t scatter_mark = ar.mark();
+    const ScatterScratch sc = plan.pending ? ScatterScratch() : round_scatter_scratch(ar, m, rank_shift);
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
+               (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(dk_in, dp_in, slots_cur, m, tile_maxrank,
+                                                                                 tile_active, sa, rank, dk_out, dp_out,
+                                                                                 slots_next, plan.shift_of(round),
+                                                                                 plan.shift_of(round + 1),
+                                                                                 ctx->d_hround, round, sc.rank_out,
+                                                                                 slot_base, plan.mask_of(round),
+                                                                                 plan.pending ? plan.rank_sa : nullptr)));
+    if (sc.rank_out != nullptr)
+    {
+      scatter_ranks_partitioned(ctx, dp_in, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
+    }
+    ar.rewind(scatter_mark);
+    u64 *tk = dk_in;
+    dk_in = dk_out;
+    dk_out = tk;
+    u32 *tp = dp_in;
+    dp_in = dp_out;
+    dp_out = tp;
+    u32 *t = slots_cur;
+    slots_cur = slots_next;
+    slots_next = t;
+  };
+  // text rounds: the secondary keys come from the replicated text -- no communication but the active counts
+  u64 h = h0;
+  u64 m_world = 0;
+  {
+    u64 world[ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, comm, &m, 1, world);
+    for (int r = 0; r < G; r++)
+    {
+      m_world += world[r];
+    }
+  }
+  while (m_world > 0 && plan.is_text(outcome->rounds + 1))
+  {
+    const u32 round = ++outcome->rounds;
+    outcome->active_sum += m;
+    ctx->lcp_work_estimate += m * (h / 32 + 1);
+    u64 m_next = 0;
+    if (m > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 20.0 * m,
+                 (text_key_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, plan.tk)));
+      m_next = sort_and_regroup(round);
+      apply_round(round, m_next);
+    }
+    u64 world[ESA_MAX_RANKS];
+    comm_exchange_host_u64(ctx, comm, &m_next, 1, world);
+    m_world = 0;
+    for (int r = 0; r < G; r++)
+    {
+      m_world += world[r];
+    }
+    m = m_next;
+    h += plan.tks.len;
+  }
+  if (m_world == 0)
+  {
+    return;
+  }
+  // a doubling round follows: rank[] is needed now
+  flush_deferred_scatter(ctx, plan, sa, M, rank, sort_temp, temp_bytes);
   if (comm->direct && comm->direct_loads)
   {
     // peer-memory variant: two barriers per round keep the remote loads of rank[] apart from the owners' updates
     u64 my_off = (u64) ((char *) rank - ar.base), offs[ESA_MAX_RANKS];
-    CUDA_CHECK(cudaStreamSynchronize(s));  // my first regroup has written its ranks
+    CUDA_CHECK(cudaStreamSynchronize(s));  // my ranks are written
     u64 pair[2] = {my_off, m}, pairs[2 * ESA_MAX_RANKS];
     comm_exchange_host_u64(ctx, comm, pair, 2, pairs);
     PeerRanks peers;
-    u64 m_world = 0;
+    m_world = 0;
     for (int r = 0; r < G; r++)
     {
       offs[r] = pairs[2 * r];
       peers.rank[r] = comm_peer_ptr<const u32>(ctx, comm, r, offs[r]);
       m_world += pairs[2 * r + 1];
     }
-    u64 hh = h0;
     while (m_world > 0)
     {
-      outcome->rounds++;
+      const u32 round = ++outcome->rounds;
       outcome->active_sum += m;
-      ctx->lcp_work_estimate += m * (hh / 32 + 1);
+      ctx->lcp_work_estimate += m * (h / 32 + 1);
       if (outcome->rounds > 64)
       {
         esa_throw(ESA_ERR_CUDA, "prefix doubling did not converge");
       }
       u64 m_next = 0;
-      u64 *ks = dk_in, *ko = dk_out;
-      u32 *ps = dp_in, *po = dp_out;
       if (m > 0)
       {
         ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
-                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, hh, keyof, lut, peers)));
+                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut, peers)));
         comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
-        if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
-        {
-          ks = dk_out, ko = dk_in;
-          ps = dp_out, po = dp_in;
-        }
-        rtiles = (u32) div_up_u64(m, RG_TILE);
-        ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
-                   (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                       tile_active, slot_base)));
-        ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-                   (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-        m_next = read_scalar(ctx, d_scalars, 4);
+        m_next = sort_and_regroup(round);
       } else
       {
         CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1523,26 +1877,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       }
       if (m > 0)
       {
-        const size_t scatter_mark = ar.mark();
-        const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
-        ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
-                   (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
-                                                                                     tile_active, sa, rank, ko, po,
-                                                                                     slots_next, rank_shift,
-                                                                                     ctx->d_hround, outcome->rounds,
-                                                                                     sc.rank_out, slot_base)));
-        if (sc.rank_out != nullptr)
-        {
-          scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
-        }
-        ar.rewind(scatter_mark);
-        dk_in = ko;
-        dp_in = po;
-        dk_out = ks;
-        dp_out = ps;
-        u32 *t = slots_cur;
-        slots_cur = slots_next;
-        slots_next = t;
+        apply_round(round, m_next);
       }
       if (sum_next > 0)
       {
@@ -1553,11 +1888,10 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       }
       m = m_next;
       m_world = sum_next;
-      hh *= 2;
+      h *= 2;
     }
     return;
   }
-  u64 h = h0;
   while (true)
   {
     u64 req_cnt[ESA_MAX_RANKS] = {0}, req_off[ESA_MAX_RANKS], in_cnt[ESA_MAX_RANKS], in_off[ESA_MAX_RANKS];
@@ -1580,7 +1914,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     }
     mine[G] = m;
     comm_exchange_host_u64(ctx, comm, mine, (size_t) G + 1, all);
-    u64 m_world = 0, in_tot = 0, o2 = 0;
+    u64 in_tot = 0, o2 = 0;
+    m_world = 0;
     for (int r = 0; r < G; r++)
     {
       m_world += all[(size_t) r * (G + 1) + G];
@@ -1594,7 +1929,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     {
       break;
     }
-    outcome->rounds++;
+    const u32 round = ++outcome->rounds;
     outcome->active_sum += m;
     ctx->lcp_work_estimate += m * (h / 32 + 1);
     if (outcome->rounds > 64)
@@ -1626,40 +1961,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 20.0 * m,
                  (merge_answer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, idx, ans_in, m)));
       ar.rewind(round_mark);  // the round's exchange buffers are dead (later users are stream ordered)
-      u64 *ks = dk_in, *ko = dk_out;
-      u32 *ps = dp_in, *po = dp_out;
-      if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, rank_shift, sort_temp, temp_bytes))
-      {
-        ks = dk_out, ko = dk_in;
-        ps = dp_out, po = dp_in;
-      }
-      rtiles = (u32) div_up_u64(m, RG_TILE);
-      ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
-                 (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                     tile_active, slot_base)));
-      ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-                 (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-      m_next = read_scalar(ctx, d_scalars, 4);
-      const size_t scatter_mark = ar.mark();
-      const ScatterScratch sc = round_scatter_scratch(ar, m, rank_shift);
-      ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
-                 (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
-                                                                                   tile_active, sa, rank, ko, po,
-                                                                                   slots_next, rank_shift,
-                                                                                   ctx->d_hround, outcome->rounds,
-                                                                                   sc.rank_out, slot_base)));
-      if (sc.rank_out != nullptr)
-      {
-        scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
-      }
-      ar.rewind(scatter_mark);
-      dk_in = ko;
-      dp_in = po;
-      dk_out = ks;
-      dp_out = ps;
-      u32 *t = slots_cur;
-      slots_cur = slots_next;
-      slots_next = t;
+      m_next = sort_and_regroup(round);
+      apply_round(round, m_next);
     } else
     {
       ar.rewind(round_mark);
