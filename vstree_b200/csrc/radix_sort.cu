@@ -31,10 +31,25 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #define ESA_SORT_MINBLOCKS 2
 #endif
 #ifndef ESA_SORT_EARLY
-#define ESA_SORT_EARLY 1     // publish the tile's digit counts before the ranking phase
+#define ESA_SORT_EARLY 2     // publish the tile's digit counts before the ranking phase (2: plain popc-inc atomics)
+#endif
+#ifndef ESA_SORT_CHAIN
+#define ESA_SORT_CHAIN 1     // serial chain through the warp counters without shuffles
 #endif
 #ifndef ESA_SORT_MATCH
 #define ESA_SORT_MATCH 0  // 0: eight ballots per key, 1: shared-memory atomicOr lane masks
+#endif
+#ifndef ESA_SORT_OVERLAP
+#define ESA_SORT_OVERLAP 1  // look-back (warps 0-7) runs while the other warps already reorder their keys
+#endif
+#ifndef ESA_SORT_FULLTILE
+#define ESA_SORT_FULLTILE 1  // full tiles take a path without bounds checks
+#endif
+#ifndef ESA_SORT_XMASK
+#define ESA_SORT_XMASK 1  // ballot loop: peers &= ballot ^ (bit ? 0 : ~0), one LOP3 per bit
+#endif
+#ifndef ESA_SORT_SPIN_NS
+#define ESA_SORT_SPIN_NS 0  // nanosleep while a predecessor tile has not published yet (0: busy spin)
 #endif
 constexpr int SORT_THREADS = ESA_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
@@ -59,6 +74,28 @@ template <> struct SortTraits<u64>
 template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, u32 shift, u32 mask)
 {
   return (u32) (k >> shift) & mask;
+}
+
+// Lanes of the warp whose digit equals mine, one ballot per digit bit.  Per bit: test with an immediate mask (no shift),
+// select of the xor mask, ballot of the negated predicate, one three-input LOP3 -- four instructions where the plain
+// C++ forms compile to five (shift, and, negate, vote, lop3).  nd = ~digit.
+template <int B> __device__ __forceinline__ u32 match_digit_bits(u32 nd, u32 peers)
+{
+  if constexpr (B < RADIX_BITS)
+  {
+    u32 xm, bal;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %2, %3;\n\t"
+                 "setp.ne.u32 p, t, 0;\n\t"
+                 "selp.b32 %0, 0xffffffff, 0, p;\n\t"
+                 "vote.sync.ballot.b32 %1, !p, 0xffffffff;\n\t}"
+                 : "=r"(xm), "=r"(bal)
+                 : "r"(nd), "n"(1u << B));
+    return match_digit_bits<B + 1>(nd, peers & (bal ^ xm));
+  } else
+  {
+    return peers;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -205,11 +242,23 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   KeyT keys[ITEMS];
   u32 ranks[ITEMS];
   const u32 wbase = warp * (32 * ITEMS);
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++)
+  const bool full_tile = ESA_SORT_FULLTILE && tile_count == (u32) TILE;
+  if (full_tile)
   {
-    const u32 idx = wbase + i * 32 + lane;
-    keys[i] = idx < tile_count ? kin[tile_base + idx] : (KeyT) ~(KeyT) 0;  // padding sorts last
+    const KeyT *kp = kin + tile_base + wbase + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      keys[i] = kp[i * 32];
+    }
+  } else
+  {
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      const u32 idx = wbase + i * 32 + lane;
+      keys[i] = idx < tile_count ? kin[tile_base + idx] : (KeyT) ~(KeyT) 0;  // padding sorts last
+    }
   }
 #if ESA_SORT_EARLY
   // ---- early counts: the tile's digit histogram is published before the (long) ranking phase, so that the
@@ -221,6 +270,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   for (int i = 0; i < ITEMS; i++)
   {
     const u32 d = DIGIT(keys[i]);
+#if ESA_SORT_EARLY == 2
+    atomicAdd(&thist[d], 1u);  // ATOMS.POPC.INC: the hardware counts the lanes that hit the same word
+#else
     if (__all_sync(FULL_MASK, d == __shfl_sync(FULL_MASK, d, 0)))
     {
       if (lane == 0)
@@ -231,6 +283,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     {
       atomicAdd(&thist[d], 1u);
     }
+#endif
   }
   __syncthreads();
   u32 valid_count = 0;
@@ -246,6 +299,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #endif
   // ---- rank inside the warp: stable in (item, lane) order = memory order
   const u32 lt_mask = (1u << lane) - 1;
+  const u32 gt_mask = 0xfffffffeu << lane;  // lanes above mine
   // lanes holding the same digit, found with one ballot per digit bit.  MATCH.ANY does the same in one
   // instruction but its cost grows with the number of distinct values in the warp (ncu, round 1: the instruction
   // behind it held 35 % of all stall samples and splitting it from its use changed nothing).
@@ -279,6 +333,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   {
     const u32 d = DIGIT(keys[i]);
     u32 peers = FULL_MASK;
+#if ESA_SORT_XMASK
+    peers = match_digit_bits<0>(~d, peers);
+#else
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; b++)
     {
@@ -286,6 +343,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       const u32 bal = __ballot_sync(FULL_MASK, bit);
       peers &= bit ? bal : ~bal;
     }
+#endif
     ranks[i] = peers;
   }
   // then the short serial chain through the warp's shared counters
@@ -294,6 +352,19 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   {
     const u32 d = DIGIT(keys[i]);
     const u32 peers = ranks[i];
+#if ESA_SORT_CHAIN == 1
+    // every lane of a peer group reads the group's counter (one broadcast word), the highest lane of the group
+    // writes it back: no shuffle, no find-first-set
+    u32 *cp = mywc + d;
+    const u32 r = *cp + __popc(peers & lt_mask);
+    __syncwarp();  // all reads before the write
+    if ((peers & gt_mask) == 0)
+    {
+      *cp = r + 1;
+    }
+    __syncwarp();
+    ranks[i] = r;
+#else
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
     if (lane == leader)
@@ -304,6 +375,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     old = __shfl_sync(FULL_MASK, old, leader);
     ranks[i] = old + __popc(peers & lt_mask);
     __syncwarp();
+#endif
   }
 #endif
   __syncthreads();
@@ -317,7 +389,27 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       bcount += wc[w * RADIX + tid];
     }
   }
-  const u32 dstart = block_exclusive_sum<u32, RADIX>(bcount, misc + 1, nullptr);
+  // exclusive scan over the 256 digit counts with ONE barrier: warp scans, eight warp totals through shared memory
+  u32 dstart = 0;
+  {
+    const u32 incl = warp_inclusive_sum(bcount);
+    if (tid < RADIX && lane == 31)
+    {
+      misc[1 + warp] = incl;
+    }
+    __syncthreads();
+    if (tid < RADIX)
+    {
+      u32 before = 0;
+#pragma unroll
+      for (int w = 0; w < RADIX / 32; w++)
+      {
+        const u32 t = misc[1 + w];
+        before += w < warp ? t : 0u;
+      }
+      dstart = before + incl - bcount;
+    }
+  }
   if (tid < RADIX)
   {
     u32 run = dstart;
@@ -329,6 +421,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       run += c;
     }
   }
+#if ESA_SORT_OVERLAP
+  __syncthreads();  // warp offsets visible: warps 8.. reorder right away, warps 0-7 after their look-back
+#endif
   // ---- decoupled look-back, one thread per digit
   if (tid < RADIX)
   {
@@ -355,6 +450,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
         const u64 s = status[(u64) t * RADIX + tid];
         if ((s >> 62) == 0)
         {
+#if ESA_SORT_SPIN_NS > 0
+          __nanosleep(ESA_SORT_SPIN_NS);
+#endif
           continue;  // predecessor has not published yet
         }
         excl += (u32) (s & STATUS_VALUE_MASK);
@@ -369,18 +467,37 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     digit_start[tid] = dstart;
     gbase[tid] = base[tid] + excl - dstart;  // wraps modulo 2^32 by design
   }
+#if !ESA_SORT_OVERLAP
   __syncthreads();
+#endif
   // ---- reorder the tile in shared memory
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++)
+  if (full_tile)
   {
-    const u32 d = DIGIT(keys[i]);
-    const u32 pos = mywc[d] + ranks[i];
-    skeys[pos] = keys[i];
-    if (HAS_VALS)
+    const u32 *vp = vin + tile_base + wbase + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
     {
-      const u32 idx = wbase + i * 32 + lane;
-      svals[pos] = idx < tile_count ? vin[tile_base + idx] : 0u;
+      const u32 d = DIGIT(keys[i]);
+      const u32 pos = mywc[d] + ranks[i];
+      skeys[pos] = keys[i];
+      if (HAS_VALS)
+      {
+        svals[pos] = vp[i * 32];
+      }
+    }
+  } else
+  {
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      const u32 d = DIGIT(keys[i]);
+      const u32 pos = mywc[d] + ranks[i];
+      skeys[pos] = keys[i];
+      if (HAS_VALS)
+      {
+        const u32 idx = wbase + i * 32 + lane;
+        svals[pos] = idx < tile_count ? vin[tile_base + idx] : 0u;
+      }
     }
   }
   __syncthreads();
@@ -389,7 +506,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   for (int j = 0; j < ITEMS; j++)
   {
     const u32 p = j * SORT_THREADS + tid;
-    if (p < tile_count)
+    if (full_tile || p < tile_count)
     {
       const KeyT k = skeys[p];
       const u32 d = DIGIT(k);
