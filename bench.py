@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -315,7 +315,7 @@ def main():
         esa.check()  # the tables of the last timed step are consistent (device-side property checks)
 
     # ---- end-to-end leg: esa_build through the C ABI with host buffers --------------------------------------
-    e2e_ms, h2d, d2h = 0.0, 0, 0
+    e2e_ms, h2d, d2h, e2e_detail, e2e_steps_ms = 0.0, 0, 0, None, []
     for i in range(1 + args.e2e_steps):
         barrier()
         t1 = time.perf_counter()
@@ -332,7 +332,11 @@ def main():
         esa.free(tabs)
         if i > 0:
             e2e_ms += dt
+            e2e_steps_ms.append(round(dt, 2))
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+            e2e_detail = {"h2d_ms": round(st["ms_h2d"], 3), "device_ms": round(st["ms_total"], 3),
+                          "d2h_tail_ms": round(st["ms_d2h"], 3), "wall_ms": round(dt, 3),
+                          "host_cpus": st["host_cpus"], "host_widen_threads": st["host_widen_threads"]}
     e2e_ms_step = e2e_ms / args.e2e_steps
 
     t = torch.tensor([dev_ms, e2e_ms_step], dtype=torch.float64, device="cuda")
@@ -398,7 +402,8 @@ def main():
             "stages": stage,
             "cpu_baseline": cpu,
             "e2e": {"value": n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max, "steps": args.e2e_steps,
+                    "steps_ms_rank0": e2e_steps_ms, "last_step_rank0": e2e_detail},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -136,6 +136,9 @@ typedef struct
   /* sharded builds (0 otherwise) */
   uint64_t shard_first, shard_count; /* this rank's slice of the suffix array */
   uint64_t comm_bytes_sent;          /* payload this rank sent to other ranks */
+  /* esa_build: host side of the fused download */
+  uint32_t host_cpus;                /* CPUs usable by this process (affinity mask and cgroup quota) */
+  uint32_t host_widen_threads;       /* host threads that widened the 32-bit suffix array (0: widened on the device) */
 } esa_stats;
 
 /* ---- lifetime ---- */

@@ -34,7 +34,8 @@ class Stats(ctypes.Structure):
                 ("kernel", KernelStat * len(KERNEL_FAMILIES)), ("ms_h2d", ctypes.c_double),
                 ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("shard_first", ctypes.c_uint64), ("shard_count", ctypes.c_uint64),
-                ("comm_bytes_sent", ctypes.c_uint64)]
+                ("comm_bytes_sent", ctypes.c_uint64), ("host_cpus", ctypes.c_uint32),
+                ("host_widen_threads", ctypes.c_uint32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "kernel"}

@@ -6,10 +6,14 @@
 #include <emmintrin.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <time.h>
 
 #include "comm.cuh"
 
@@ -127,15 +131,22 @@ struct HostWiden
   u64 *dst = nullptr;      // pinned: the table handed out in esa_result
   u64 count = 0, chunk = 0;
   u32 nchunks = 0;
-  int nthreads = 0, device = 0;
-  std::vector<cudaEvent_t> events;
+  int nthreads_last = 0;  // workers of the last fused download (0: the widened table crossed PCIe)
+  // Progress of the chunked copy without any CUDA call on the worker side: behind chunk c the copy stream copies the
+  // word c+1 from a device table into *progress (pinned).  DMA writes of one stream land in order, so a worker that
+  // reads progress > c finds chunk c complete.  (Workers that waited in cudaEventSynchronize contended with the
+  // launching thread for the driver's locks: the lcp/bwt sweep of a fused build took 14 ms instead of 7.)
+  u32 *progress = nullptr;  // pinned word
+  u32 *d_ticks = nullptr;   // device: d_ticks[i] = i + 1
+  static constexpr u32 MAX_CHUNKS = 1024;
+  // persistent workers: created at the first fused download, parked on cv_job between builds
   std::vector<pthread_t> threads;
-  struct Arg
-  {
-    HostWiden *w;
-    int tid;
-  };
-  std::vector<Arg> args;
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_cond_t cv_job = PTHREAD_COND_INITIALIZER, cv_done = PTHREAD_COND_INITIALIZER;
+  u64 job_id = 0;  // under mu
+  bool stop = false;
+  std::atomic<u32> next_chunk{0}, chunks_done{0};
+  std::atomic<bool> abort{false};
 };
 
 void widen_range(const u32 *src, u64 *dst, u64 cnt)
@@ -155,18 +166,59 @@ void widen_range(const u32 *src, u64 *dst, u64 cnt)
   _mm_sfence();
 }
 
+// takes chunks off the job until none is left; called by the workers and, at the end, by the building thread
+void widen_drain(HostWiden *w)
+{
+  u32 c;
+  while ((c = w->next_chunk.fetch_add(1)) < w->nchunks)
+  {
+    u32 spins = 0;
+    while (__atomic_load_n(w->progress, __ATOMIC_ACQUIRE) <= c && !w->abort.load())
+    {
+      if (++spins < 256)
+      {
+        _mm_pause();
+      } else
+      {
+        spins = 0;
+        struct timespec ts = {0, 20000};
+        nanosleep(&ts, nullptr);
+      }
+    }
+    if (!w->abort.load())
+    {
+      const u64 b = (u64) c * w->chunk, e = std::min(w->count, b + w->chunk);
+      widen_range(w->staging + b, w->dst + b, e - b);
+    }
+    if (w->chunks_done.fetch_add(1) + 1 == w->nchunks)
+    {
+      pthread_mutex_lock(&w->mu);
+      pthread_cond_broadcast(&w->cv_done);
+      pthread_mutex_unlock(&w->mu);
+    }
+  }
+}
+
 void *widen_worker(void *p)
 {
-  HostWiden::Arg *a = (HostWiden::Arg *) p;
-  HostWiden *w = a->w;
-  cudaSetDevice(w->device);
-  for (u32 c = (u32) a->tid; c < w->nchunks; c += (u32) w->nthreads)
+  HostWiden *w = (HostWiden *) p;
+  u64 seen = 0;
+  while (true)
   {
-    cudaEventSynchronize(w->events[c]);
-    const u64 b = (u64) c * w->chunk, e = std::min(w->count, b + w->chunk);
-    widen_range(w->staging + b, w->dst + b, e - b);
+    pthread_mutex_lock(&w->mu);
+    while (!w->stop && w->job_id == seen)
+    {
+      pthread_cond_wait(&w->cv_job, &w->mu);
+    }
+    const bool stop = w->stop;
+    seen = w->job_id;
+    pthread_mutex_unlock(&w->mu);
+    if (stop)
+    {
+      return nullptr;
+    }
+    widen_drain(w);
   }
-  return nullptr;
 }
 
 struct CtxExtra
@@ -316,65 +368,130 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
 // host threads available to one rank for widening; measured on the B200 box (32 cores, 100 M entries): 2 threads
 // 37.8 ms end to end, 4: 27.8, 8: 24.5, 12: 24.1, against 30.6 ms when the widened table crosses PCIe -- so the
 // fused path is only taken with at least 6 threads per rank (ESA_WIDEN_THREADS overrides, 0 disables)
+// CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota (a container on a large host
+// sees every core in sysconf(_SC_NPROCESSORS_ONLN) but may be throttled to a few)
+int usable_cpus()
+{
+  long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof set, &set) == 0)
+  {
+    const int c = CPU_COUNT(&set);
+    if (c > 0 && c < cpus)
+    {
+      cpus = c;
+    }
+  }
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r"))  // cgroup v2: "<quota|max> <period>"
+  {
+    char q[32];
+    long period = 0;
+    if (fscanf(f, "%31s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0)
+    {
+      const long lim = (atol(q) + period - 1) / period;
+      if (lim > 0 && lim < cpus)
+      {
+        cpus = lim;
+      }
+    }
+    fclose(f);
+  } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r"))  // cgroup v1
+  {
+    long quota = -1, period = 0;
+    if (fscanf(g, "%ld", &quota) != 1)
+    {
+      quota = -1;
+    }
+    fclose(g);
+    if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r"))
+    {
+      if (fscanf(h, "%ld", &period) != 1)
+      {
+        period = 0;
+      }
+      fclose(h);
+    }
+    if (quota > 0 && period > 0 && (quota + period - 1) / period < cpus)
+    {
+      cpus = (quota + period - 1) / period;
+    }
+  }
+  return (int) std::max<long>(1, cpus);
+}
+
 int widen_threads(const FullCtx *ctx)
 {
   if (const char *e = getenv("ESA_WIDEN_THREADS"))
   {
     return atoi(e);
   }
-  const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  // one CPU per rank stays free for the thread that drives the build; fewer than 4 workers lose against shipping
+  // the widened table (measured above)
   const int ranks = ctx->comm != nullptr ? ctx->comm->nranks : 1;
-  const long per_rank = cores / (2 * ranks);
-  return per_rank >= 6 ? (int) std::min<long>(12, per_rank) : 0;
+  const int per_rank = usable_cpus() / ranks - 1;
+  return per_rank >= 4 ? std::min(12, per_rank) : 0;
 }
 
 void start_host_widen(FullCtx *ctx)
 {
   HostWiden &w = ctx->x.widen;
   w.count = ctx->shard_count;
-  w.device = ctx->device;
   w.staging = (u32 *) ctx->x.pool.get((w.count + 4) * sizeof(u32));
   w.dst = (u64 *) ctx->x.pool.get((w.count + 4) * sizeof(u64));
   w.chunk = std::max<u64>((u64) 1 << 21, div_up_u64(div_up_u64(w.count, 192), 4) * 4);  // multiples of 4 entries
   w.nchunks = (u32) div_up_u64(w.count, w.chunk);
-  w.nthreads = std::max(1, std::min(widen_threads(ctx), (int) std::max<u32>(1, w.nchunks)));
-  while (w.events.size() < w.nchunks)
+  if (w.nchunks > HostWiden::MAX_CHUNKS)
   {
-    cudaEvent_t e;
-    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    w.events.push_back(e);
+    w.chunk = div_up_u64(div_up_u64(w.count, HostWiden::MAX_CHUNKS), 4) * 4;
+    w.nchunks = (u32) div_up_u64(w.count, w.chunk);
   }
+  if (w.progress == nullptr)
+  {
+    CUDA_CHECK(cudaMallocHost((void **) &w.progress, 64));
+    CUDA_CHECK(cudaMalloc((void **) &w.d_ticks, HostWiden::MAX_CHUNKS * sizeof(u32)));
+    std::vector<u32> ticks(HostWiden::MAX_CHUNKS);
+    for (u32 i = 0; i < HostWiden::MAX_CHUNKS; i++)
+    {
+      ticks[i] = i + 1;
+    }
+    CUDA_CHECK(cudaMemcpy(w.d_ticks, ticks.data(), ticks.size() * sizeof(u32), cudaMemcpyHostToDevice));
+  }
+  if (w.threads.empty())
+  {
+    const int want = std::max(1, widen_threads(ctx));
+    for (int t = 0; t < want; t++)
+    {
+      pthread_t th;
+      if (pthread_create(&th, nullptr, widen_worker, &w) != 0)
+      {
+        break;  // fewer workers than planned: the building thread drains what is left in finish_host_widen
+      }
+      w.threads.push_back(th);
+    }
+  }
+  w.nthreads_last = (int) w.threads.size();
+  __atomic_store_n(w.progress, 0u, __ATOMIC_RELEASE);
+  w.next_chunk.store(0);
+  w.chunks_done.store(0);
+  w.abort.store(false);
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_sorted, ctx->stream));
   CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->x.ev_sorted, 0));
+  w.active = true;
   for (u32 c = 0; c < w.nchunks; c++)
   {
     const u64 b = (u64) c * w.chunk, e = std::min(w.count, b + w.chunk);
     CUDA_CHECK(cudaMemcpyAsync(w.staging + b, ctx->d_sa + b, (e - b) * sizeof(u32), cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
-    CUDA_CHECK(cudaEventRecord(w.events[c], ctx->copy_stream));
+    CUDA_CHECK(cudaMemcpyAsync(w.progress, w.d_ticks + c, sizeof(u32), cudaMemcpyDeviceToHost, ctx->copy_stream));
   }
-  w.threads.resize(w.nthreads);
-  w.args.resize(w.nthreads);
-  w.active = true;
-  for (int t = 0; t < w.nthreads; t++)
-  {
-    w.args[t] = {&w, t};
-    if (pthread_create(&w.threads[t], nullptr, widen_worker, &w.args[t]) != 0)
-    {
-      // fewer workers than planned: the started ones cover the chunks of the missing ones too
-      for (int u = 0; u < t; u++)
-      {
-        pthread_join(w.threads[u], nullptr);
-      }
-      w.nthreads = 0;
-      CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
-      widen_range(w.staging, w.dst, w.count);
-      break;
-    }
-  }
+  pthread_mutex_lock(&w.mu);
+  w.job_id++;
+  pthread_cond_broadcast(&w.cv_job);
+  pthread_mutex_unlock(&w.mu);
 }
 
-// waits for the workers; returns the widened table (owned by the pinned pool like every result table)
+// waits for the copy and the workers; returns the widened table (owned by the pinned pool like every result table)
 u64 *finish_host_widen(FullCtx *ctx, bool keep)
 {
   HostWiden &w = ctx->x.widen;
@@ -382,11 +499,26 @@ u64 *finish_host_widen(FullCtx *ctx, bool keep)
   {
     return nullptr;
   }
-  for (int t = 0; t < w.nthreads; t++)
+  if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess)
   {
-    pthread_join(w.threads[t], nullptr);
+    w.abort.store(true);  // the copy died: nobody waits for chunks that will never arrive
+    keep = false;
   }
-  cudaStreamSynchronize(ctx->copy_stream);
+  widen_drain(&w);  // the building thread takes what the workers have not started yet
+  pthread_mutex_lock(&w.mu);
+  while (w.chunks_done.load() < w.nchunks)
+  {
+    struct timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    ts.tv_nsec += 2000000;
+    if (ts.tv_nsec >= 1000000000)
+    {
+      ts.tv_sec++;
+      ts.tv_nsec -= 1000000000;
+    }
+    pthread_cond_timedwait(&w.cv_done, &w.mu, &ts);
+  }
+  pthread_mutex_unlock(&w.mu);
   w.active = false;
   ctx->x.pool.put(w.staging);
   w.staging = nullptr;
@@ -398,6 +530,28 @@ u64 *finish_host_widen(FullCtx *ctx, bool keep)
     return nullptr;
   }
   return r;
+}
+
+// esa_shutdown: parks no more
+void destroy_host_widen(FullCtx *ctx)
+{
+  HostWiden &w = ctx->x.widen;
+  pthread_mutex_lock(&w.mu);
+  w.stop = true;
+  pthread_cond_broadcast(&w.cv_job);
+  pthread_mutex_unlock(&w.mu);
+  for (pthread_t th : w.threads)
+  {
+    pthread_join(th, nullptr);
+  }
+  w.threads.clear();
+  if (w.progress != nullptr)
+  {
+    cudaFreeHost(w.progress);
+    cudaFree(w.d_ticks);
+    w.progress = nullptr;
+    w.d_ticks = nullptr;
+  }
 }
 
 void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
@@ -511,10 +665,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     u64 mine[3] = {ctx->shard_count, 0, ctx->lcp_work_estimate}, all[3 * ESA_MAX_RANKS];
     if (ctx->shard_count > 0)
     {
-      u32 last = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&last, ctx->d_sa + ctx->shard_count - 1, sizeof last, cudaMemcpyDeviceToHost, s));
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      mine[1] = last;
+      mine[1] = read_back_u32(ctx, ctx->d_sa + ctx->shard_count - 1);
     }
     comm_exchange_host_u64(ctx, comm, mine, 3, all);
     u64 work = 0;
@@ -774,10 +925,7 @@ void esa_shutdown(esa_ctx *c)
   ctx->prof.destroy();
   ctx->x.pool.destroy();
   finish_host_widen(ctx, false);
-  for (cudaEvent_t ev : ctx->x.widen.events)
-  {
-    cudaEventDestroy(ev);
-  }
+  destroy_host_widen(ctx);
   for (cudaEvent_t ev : {ctx->x.ev_a, ctx->x.ev_b, ctx->x.ev_c, ctx->x.ev_d, ctx->x.ev_e, ctx->x.ev_sorted})
   {
     if (ev != nullptr)
@@ -888,6 +1036,8 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
       stats->ms_d2h = ms;
       stats->h2d_bytes = ctx->x.h2d_bytes;
       stats->d2h_bytes = d2h;
+      stats->host_cpus = (uint32_t) usable_cpus();
+      stats->host_widen_threads = (uint32_t) ctx->x.widen.nthreads_last;
     }
   });
   if (rc != ESA_OK)

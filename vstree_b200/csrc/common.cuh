@@ -271,6 +271,13 @@ struct LaunchScope
     scope__.done();                                  \
   } while (0)
 
+// Small device -> host read-backs (counts, maxima) go through a one-warp kernel that stores into the MAPPED pinned
+// words ctx->h_scalars, not through the copy engine: a 24-byte cudaMemcpyAsync queues behind the hundreds of megabytes
+// the fused download of esa_build has in flight on that engine and stalled the lcp/bwt sweep for 8 ms.
+// Copies count 64-bit words from d_src to ctx->h_scalars + h_offset and synchronises the stream.
+void read_back_u64(esa_ctx *ctx, const void *d_src, u32 count, u32 h_offset = 0);
+u32 read_back_u32(esa_ctx *ctx, const u32 *d_src);  // one 32-bit word, same path
+
 static inline u32 div_up_u32(u64 a, u64 b) { return (u32) ((a + b - 1) / b); }
 static inline u64 div_up_u64(u64 a, u64 b) { return (a + b - 1) / b; }
 

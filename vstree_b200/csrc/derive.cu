@@ -303,8 +303,7 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 in
   {
     ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, LLV_SCAN_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
   }
-  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
+  read_back_u64(ctx, d_scalars, 3);
   ctx->maxbranchdepth = ctx->h_scalars[0];
   ctx->longest = ctx->h_scalars[1];
   ctx->nllv = want_lcp ? ctx->h_scalars[2] : 0;
@@ -315,6 +314,42 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 in
                (llv_emit_kernel<<<tiles, FN_THREADS, 0, s>>>(N, ctx->d_sa, d_v, nullptr, ctx->d_lcp, tile_large,
                                                               ctx->nllv, ctx->d_llv, index_base)));
   }
+}
+
+namespace
+{
+__global__ void readback_kernel(u64 *__restrict__ host_dst, const u64 *__restrict__ src, u32 count)
+{
+  if (threadIdx.x < count)
+  {
+    host_dst[threadIdx.x] = src[threadIdx.x];
+  }
+  __threadfence_system();
+}
+__global__ void readback32_kernel(u64 *__restrict__ host_dst, const u32 *__restrict__ src)
+{
+  host_dst[0] = src[0];
+  __threadfence_system();
+}
+}  // namespace
+
+void read_back_u64(esa_ctx *ctx, const void *d_src, u32 count, u32 h_offset)
+{
+  if (count == 0 || count + h_offset > 64)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "internal: read-back of %u words at %u", count, h_offset);
+  }
+  readback_kernel<<<1, 64, 0, ctx->stream>>>(ctx->h_scalars + h_offset, (const u64 *) d_src, count);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+u32 read_back_u32(esa_ctx *ctx, const u32 *d_src)
+{
+  readback32_kernel<<<1, 1, 0, ctx->stream>>>(ctx->h_scalars + 63, d_src);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return (u32) ctx->h_scalars[63];
 }
 
 void compute_sti1(esa_ctx *ctx, u32 prefixlength)

@@ -252,8 +252,7 @@ int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b
   ESA_LAUNCH(ctx, ESA_K_REGROUP, 9.0 * m,
              (ds_plan_kernel<<<tiles, DS_THREADS, 0, s>>>(keys_a, m, shift, flags, tile_spill)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0, (ds_scan_kernel<<<1, 1024, 0, s>>>(tile_spill, tiles, d_total)));
-  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars + 8, d_total, sizeof(u64), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
+  read_back_u64(ctx, d_total, 1, 8);
   const u64 nspill = ctx->h_scalars[8];
   if (2 * nspill > m)
   {

@@ -277,8 +277,7 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base,
   {
     ESA_LAUNCH(ctx, ESA_K_MISC, 0, (large_scan_kernel<<<1, LLV_SCAN_THREADS, 0, s>>>(tile_large, tiles, d_scalars)));
   }
-  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 3 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
+  read_back_u64(ctx, d_scalars, 3);
   ctx->maxbranchdepth = ctx->h_scalars[0];
   ctx->longest = ctx->h_scalars[1];
   ctx->nllv = want_lcp ? ctx->h_scalars[2] : 0;

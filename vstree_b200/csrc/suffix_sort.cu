@@ -823,8 +823,7 @@ void flush_deferred_scatter(esa_ctx *ctx, RefinePlan &plan, const u32 *sa, u64 M
 
 u64 read_scalar(esa_ctx *ctx, const u64 *d_scalars, int idx)
 {
-  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars + idx, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  read_back_u64(ctx, d_scalars + idx, 1);
   return ctx->h_scalars[0];
 }
 
@@ -867,8 +866,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   ESA_LAUNCH(ctx, ESA_K_MISC, 0,
              (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles, d_scalars,
                                                                      0)));
-  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
+  read_back_u64(ctx, d_scalars, 4);
   const u64 nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
   const u64 M = nfull + nside;  // suffixes that take part in the sort
   if (M + nspec != N)
@@ -1416,8 +1414,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     ESA_LAUNCH(ctx, ESA_K_MISC, 0,
                (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
                                                                        d_scalars, 0)));
-    CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, d_scalars, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    read_back_u64(ctx, d_scalars, 4);
     nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
   }
   if (nfull + nside + nspec != p_end - p_begin)
