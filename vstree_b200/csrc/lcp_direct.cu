@@ -16,6 +16,8 @@
 namespace
 {
 
+// one thread per record of the packed text (layout: textcmp.cuh): 60 symbols starting one in front of position 32w,
+// the 8 summary bits, and the 32-bit special mask of positions [32w, 32w + 32)
 __global__ void __launch_bounds__(256)
 pack2_kernel(const u8 *__restrict__ tis, u64 n, u64 padded_len, u64 words, u64 *__restrict__ pk,
              u32 *__restrict__ spm)
@@ -26,29 +28,71 @@ pack2_kernel(const u8 *__restrict__ tis, u64 n, u64 padded_len, u64 words, u64 *
     return;
   }
   const u64 p0 = w * 32;
-  u64 bits = 0;
-  u32 mask = 0;
-  if (p0 + 32 <= padded_len)
+  u64 lo = 0, hi = 0;
+  u32 mask = 0, summary = 0;
+  // record symbol 0 = the symbol in front of p0
   {
-    const uint4 a = *reinterpret_cast<const uint4 *>(tis + p0), b = *reinterpret_cast<const uint4 *>(tis + p0 + 16);
-    const u32 q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 32; i++)
+    const bool sp = p0 == 0 || p0 - 1 >= n || tis[p0 - 1] >= ESA_WILDCARD;
+    if (sp)
     {
-      const u32 c = (q[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-      if (c >= ESA_WILDCARD || p0 + i >= n)
+      summary |= 1u;
+    } else
+    {
+      lo |= (u64) (tis[p0 - 1] & 3u);
+    }
+  }
+  if (p0 + 64 <= padded_len)
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(tis + p0);
+    const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+    const u32 q[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 59; i++)
+    {
+      const u32 ch = (q[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+      const bool sp = ch >= ESA_WILDCARD || p0 + i >= n;
+      const int j = i + 1;  // record symbol index
+      if (sp)
       {
-        mask |= 1u << i;
+        summary |= 1u << (j >> 3);
+        if (i < 32)
+        {
+          mask |= 1u << i;
+        }
+      } else if (j < 32)
+      {
+        lo |= (u64) (ch & 3u) << (2 * j);
       } else
       {
-        bits |= (u64) (c & 3u) << (2 * i);
+        hi |= (u64) (ch & 3u) << (2 * (j - 32));
       }
     }
   } else
   {
-    mask = 0xffffffffu;
+    for (int i = 0; i < 59; i++)
+    {
+      const u64 pos = p0 + i;
+      const u32 ch = pos < n ? tis[pos] : 255u;
+      const bool sp = ch >= ESA_WILDCARD;
+      const int j = i + 1;
+      if (sp)
+      {
+        summary |= 1u << (j >> 3);
+        if (i < 32)
+        {
+          mask |= 1u << i;
+        }
+      } else if (j < 32)
+      {
+        lo |= (u64) (ch & 3u) << (2 * j);
+      } else
+      {
+        hi |= (u64) (ch & 3u) << (2 * (j - 32));
+      }
+    }
   }
-  pk[w] = bits;
+  pk[2 * w] = lo;
+  pk[2 * w + 1] = hi | ((u64) summary << 56);
   spm[w] = mask;
 }
 
@@ -222,7 +266,7 @@ void pack_text(esa_ctx *ctx)
   const u64 n = ctx->n, N = n + 1;
   const u64 words = (N + 31) / 32 + 4;
   const u64 padded = ((n + 15) & ~(u64) 15) + 64;
-  ctx->d_pk = ctx->arena.alloc<u64>(words);
+  ctx->d_pk = ctx->arena.alloc<u64>(2 * words);  // 16-byte records
   ctx->d_spm = ctx->arena.alloc<u32>(words);
   pack2_kernel<<<div_up_u32(words, 256), 256, 0, ctx->stream>>>(ctx->d_tis, n, padded, words, ctx->d_pk, ctx->d_spm);
   CUDA_CHECK(cudaGetLastError());

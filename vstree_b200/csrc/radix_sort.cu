@@ -33,6 +33,9 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #ifndef ESA_SORT_EARLY
 #define ESA_SORT_EARLY 2     // publish the tile's digit counts before the ranking phase (2: plain popc-inc atomics)
 #endif
+#ifndef ESA_HIST_PLAIN
+#define ESA_HIST_PLAIN 1     // histogram with plain shared-memory atomics (no warp-uniformity test)
+#endif
 #ifndef ESA_SORT_CHAIN
 #define ESA_SORT_CHAIN 1     // serial chain through the warp counters without shuffles
 #endif
@@ -135,6 +138,10 @@ radix_hist_kernel(const KeyT *__restrict__ keys, u32 count, u32 begin_bit, u32 e
           const u32 shift = begin_bit + p * RADIX_BITS;
           const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
           const u32 d = digit_of(k[i], shift, (1u << bits) - 1);
+#if ESA_HIST_PLAIN
+          atomicAdd(&sh[p * RADIX + d], 1u);  // ATOMS.POPC.INC counts the lanes that hit the same bin in one go
+          continue;
+#endif
           // a digit that is the same in the whole warp (constant high bits, runs of equal keys) would
           // serialise 32 ways on one bin: count it once
           if (__all_sync(vmask, d == __shfl_sync(vmask, d, first)))

@@ -569,8 +569,9 @@ text_key_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h
   u32 flag = 0;
   if (tk.packed.pk != nullptr)
   {
-    const u64 w = tk.packed.window(q);
-    const u32 msk = tk.packed.mask_window(q);
+    const TextPacked2::Win tw = tk.packed.win(q);  // 28 symbols >= L
+    const u64 w = tw.w;
+    const u32 msk = tw.m;
     const u32 d = msk ? (u32) (__ffs((int) msk) - 1) : 32u;
     u64 r = __brevll(w);
     r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
@@ -1164,8 +1165,9 @@ __device__ __forceinline__ u32 initial_key_at(const u8 *__restrict__ tis, u64 q,
 // byte loads (the packed window holds symbol i in bits [2i, 2i+2); the code wants symbol 0 in its top digit)
 __device__ __forceinline__ u32 initial_key_at_packed(const TextPacked2 &text, u64 q, u32 h)
 {
-  const u64 w = text.window(q);
-  const u32 m = text.mask_window(q);
+  const TextPacked2::Win tw = text.win(q);  // 28 symbols >= h
+  const u64 w = tw.w;
+  const u32 m = tw.m;
   const u32 d = m ? (u32) (__ffs((int) m) - 1) : 32u;
   if (d == 0)
   {

@@ -77,31 +77,95 @@ struct TextBytes
   __device__ __forceinline__ u32 before(u64 p) const { return p > 0 ? tis[p - 1] : 255u; }
 };
 
+// Record layout of the 2-bit text.  One 16-byte record per 32 symbols, but every record carries 60 symbols: record i
+// holds the text symbols [32i - 1, 32i + 59) (symbol j of the record in bits [2j, 2j+2) of the 128-bit word, specials
+// stored as 0) and, in its top 8 bits, a summary: bit g is set when a special (or a position outside [0, n)) lies among
+// the record symbols [8g, 8g + 8).  So ONE 16-byte load yields, for any position p, the symbol in front of p and a
+// window of 28 symbols behind it, and tells whether the special mask has to be consulted at all.  The random accesses
+// of the lcp/bwt sweep and of the text keys are bound by L1 wavefronts (one per distinct line and load instruction,
+// about 136 G/s on a B200), not by bytes: the previous layout (64-bit words + separate mask words) needed four loads
+// per suffix start, this one needs one.  Same footprint: 16 + 4 bytes per 32 symbols.
 struct TextPacked2
 {
-  const u64 *pk;   // 32 symbols per word, symbol i of the word in bits [2i, 2i+2); specials stored as 0
-  const u32 *spm;  // 1 bit per symbol: special, or at/behind position n
+  const u64 *pk;   // records, two words each (lo, hi)
+  const u32 *spm;  // 1 bit per symbol: special, or at/behind position n (consulted only when a summary bit says so)
   const u8 *tis;   // the bytes, only consulted to tell 254 from 255
 
-  __device__ __forceinline__ u64 window(u64 p) const
+  static constexpr u32 WINDOW = 28;  // symbols per comparison step
+  static constexpr u64 WINDOW_BITS_MASK = ((u64) 1 << (2 * WINDOW)) - 1;
+  static constexpr u32 WINDOW_MASK = (1u << WINDOW) - 1;
+
+  struct Rec
+  {
+    u64 lo, hi;
+    u32 o;  // index of position p inside the record: 1..32
+  };
+  __device__ __forceinline__ Rec load(u64 p) const
+  {
+    const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(pk) + (p >> 5));
+    Rec x;
+    x.lo = r.x;
+    x.hi = r.y;
+    x.o = (u32) (p & 31) + 1;
+    return x;
+  }
+  static __device__ __forceinline__ u64 rec_window(const Rec &x)
+  {
+    const u32 sh = 2 * x.o;  // 2..64
+    const u64 w = sh < 64 ? ((x.lo >> sh) | (x.hi << (64 - sh))) : x.hi;
+    return w & WINDOW_BITS_MASK;
+  }
+  // does a special lie among the record symbols [first, last]?
+  static __device__ __forceinline__ bool rec_has_special(const Rec &x, u32 first, u32 last)
+  {
+    const u32 summary = (u32) (x.hi >> 56);
+    const u32 g0 = first >> 3, g1 = last >> 3;
+    return ((summary >> g0) & ((2u << (g1 - g0)) - 1)) != 0;
+  }
+  __device__ __forceinline__ u32 mask_slow(u64 p) const
   {
     const u64 w = p >> 5;
-    const u32 sh = (u32) (p & 31) * 2;
-    const u64 lo = pk[w];
-    if (sh == 0)
-    {
-      return lo;
-    }
-    return (lo >> sh) | (pk[w + 1] << (64 - sh));
+    return __funnelshift_r(spm[w], spm[w + 1], (u32) (p & 31)) & WINDOW_MASK;
   }
+  // window of WINDOW symbols at p (symbol k in bits [2k, 2k+2), upper bits zero) and its special mask
+  struct Win
+  {
+    u64 w;
+    u32 m;
+  };
+  __device__ __forceinline__ Win win(u64 p) const
+  {
+    const Rec x = load(p);
+    Win r;
+    r.w = rec_window(x);
+    r.m = rec_has_special(x, x.o, x.o + WINDOW - 1) ? mask_slow(p) : 0u;
+    return r;
+  }
+  __device__ __forceinline__ u64 window(u64 p) const { return rec_window(load(p)); }
   __device__ __forceinline__ u32 mask_window(u64 p) const
   {
-    const u64 w = p >> 5;
-    return __funnelshift_r(spm[w], spm[w + 1], (u32) (p & 31));
+    const Rec x = load(p);
+    return rec_has_special(x, x.o, x.o + WINDOW - 1) ? mask_slow(p) : 0u;
+  }
+  __device__ __forceinline__ u32 before_of(const Rec &x, u64 p) const
+  {
+    if (p == 0)
+    {
+      return 255u;
+    }
+    const u32 j = x.o - 1;
+    if (rec_has_special(x, j, j))
+    {
+      const u64 q = p - 1;
+      if ((spm[q >> 5] >> (q & 31)) & 1u)
+      {
+        return tis[q];
+      }
+    }
+    return (u32) ((j < 32 ? x.lo >> (2 * j) : x.hi >> (2 * (j - 32))) & 3u);
   }
   // One suffix start, loaded once and used for both neighbour comparisons and for the bwt symbol: the first
-  // window, its special mask and the symbol in front of the suffix (the lcp/bwt sweep is bound by the number of
-  // L2 sector requests, not by bytes: 10 requests per suffix-array entry before this, about 3 with it).
+  // window, its special mask and the symbol in front of the suffix.
   struct Probe
   {
     u64 w;
@@ -110,43 +174,30 @@ struct TextPacked2
   };
   __device__ __forceinline__ Probe probe(u64 p) const
   {
+    const Rec x = load(p);
     Probe r;
-    const u64 wi = p >> 5;
-    const u32 o = (u32) (p & 31);
-    const u64 lo = pk[wi];
-    const u32 mlo = spm[wi];
-    if (o == 0)
-    {
-      r.w = lo;
-      r.m = mlo;
-      r.before = before(p);
-    } else
-    {
-      r.w = (lo >> (2 * o)) | (pk[wi + 1] << (64 - 2 * o));
-      r.m = __funnelshift_r(mlo, spm[wi + 1], o);
-      r.before = ((mlo >> (o - 1)) & 1u) ? (u32) tis[p - 1] : (u32) (lo >> (2 * (o - 1))) & 3u;
-    }
+    r.w = rec_window(x);
+    r.m = rec_has_special(x, x.o, x.o + WINDOW - 1) ? mask_slow(p) : 0u;
+    r.before = before_of(x, p);
     return r;
+  }
+  static __device__ __forceinline__ u32 stop_of(u64 wa, u64 wb, u32 sp)
+  {
+    const u64 diff = wa ^ wb;
+    const u64 mm = (diff | (diff >> 1)) & 0x5555555555555555ull;
+    const u32 stop_mis = mm ? (u32) (__ffsll((long long) mm) - 1) >> 1 : WINDOW;
+    const u32 stop_sp = sp ? (u32) (__ffs((int) sp) - 1) : WINDOW;
+    return min(stop_mis, stop_sp);
   }
   static __device__ __forceinline__ u32 probe_stop(const Probe &a, const Probe &b)
   {
-    const u64 diff = a.w ^ b.w;
-    const u64 mm = (diff | (diff >> 1)) & 0x5555555555555555ull;
-    const u32 sp = a.m | b.m;
-    const u32 stop_mis = mm ? (u32) (__ffsll((long long) mm) - 1) >> 1 : 32u;
-    const u32 stop_sp = sp ? (u32) (__ffs((int) sp) - 1) : 32u;
-    return min(stop_mis, stop_sp);
+    return stop_of(a.w, b.w, a.m | b.m);
   }
-  static constexpr u32 WINDOW = 32;  // symbols per comparison step
-  // equal leading letters inside one window pair: 0..32 (32 = no mismatch and no special in the window)
+  // equal leading letters inside one window pair: 0..WINDOW (WINDOW = no mismatch and no special in the window)
   __device__ __forceinline__ u32 step(u64 pa, u64 pb) const
   {
-    const u64 diff = window(pa) ^ window(pb);
-    const u64 mm = (diff | (diff >> 1)) & 0x5555555555555555ull;
-    const u32 sp = mask_window(pa) | mask_window(pb);
-    const u32 stop_mis = mm ? (u32) (__ffsll((long long) mm) - 1) >> 1 : 32u;
-    const u32 stop_sp = sp ? (u32) (__ffs((int) sp) - 1) : 32u;
-    return min(stop_mis, stop_sp);
+    const Win a = win(pa), b = win(pb);
+    return stop_of(a.w, b.w, a.m | b.m);
   }
   __device__ __forceinline__ u32 lcp(u64 a, u64 b, u32 start) const
   {
@@ -155,23 +206,11 @@ struct TextPacked2
     {
       const u32 stop = step(a + l, b + l);
       l += stop;
-      if (stop < 32)
+      if (stop < WINDOW)
       {
         return l;
       }
     }
   }
-  __device__ __forceinline__ u32 before(u64 p) const
-  {
-    if (p == 0)
-    {
-      return 255u;
-    }
-    const u64 q = p - 1;
-    if ((spm[q >> 5] >> (q & 31)) & 1u)
-    {
-      return tis[q];
-    }
-    return (u32) (pk[q >> 5] >> ((q & 31) * 2)) & 3u;
-  }
+  __device__ __forceinline__ u32 before(u64 p) const { return before_of(load(p), p); }
 };
