@@ -127,3 +127,4 @@ template <typename T> __device__ __forceinline__ T warp_reduce_max(T v)
   }
   return v;
 }
+

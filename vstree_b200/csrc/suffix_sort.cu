@@ -223,6 +223,233 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Classification for the 4-letter alphabet from the PACKED text (sigma == 4): every position is independent -- one
+// 16-byte record load (shared by the 32 consecutive positions of a warp) gives the h0 symbols and the distance to
+// the next special, where the generic kernels above roll a base-sigma code over 16 + h0 symbols per thread and run
+// twice (count, scan, emit).  The class totals are known beforehand from the special mask alone, the per-tile
+// offsets of the rare classes come from a chained scan, so the text is swept once.
+constexpr int CD_THREADS = 256;
+constexpr int CD_ITEMS = 16;
+constexpr int CD_TILE = CD_THREADS * CD_ITEMS;
+constexpr int CD_WARPS = CD_THREADS / 32;
+
+// One CTA per tile of CD_TILE positions (128 mask words), positions [p_begin, p_end), p_begin a multiple of CD_TILE.
+// special-initial = mask bit; side = no mask bit but one among the next h-1 positions.  Per tile the two counts
+// (packed: nside | nspec << 16), per group of 2^group_shift tiles their sums (packed: nside | nspec << 32, added
+// atomically), and the totals in scalars[0] (nside) and scalars[1] (nspec).
+__global__ void __launch_bounds__(CD_TILE / 32)
+classify_dna_count_kernel(const u32 *__restrict__ spm, u64 p_begin, u64 p_end, u32 h, u32 group_shift,
+                          u32 *__restrict__ tile_cnt, unsigned long long *__restrict__ group_cnt,
+                          unsigned long long *__restrict__ scalars)
+{
+  __shared__ u32 red[2][CD_TILE / 32 / 32];
+  const u64 w = (p_begin >> 5) + (u64) blockIdx.x * (CD_TILE / 32) + threadIdx.x;
+  const u64 p0 = w * 32;
+  u32 ns = 0, np = 0;
+  if (p0 < p_end)
+  {
+    const u64 W = (u64) spm[w] | ((u64) spm[w + 1] << 32);
+    const u32 valid = p_end - p0 >= 32 ? 0xffffffffu : ((1u << (u32) (p_end - p0)) - 1);
+    u64 S = 0;
+    for (u32 j = 1; j < h; j++)
+    {
+      S |= W >> j;
+    }
+    np = __popc((u32) W & valid);
+    ns = __popc((u32) (S & ~W) & valid);
+  }
+  ns = warp_reduce_sum(ns);
+  np = warp_reduce_sum(np);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+  {
+    red[0][warp] = ns;
+    red[1][warp] = np;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    u32 a = 0, b = 0;
+    for (int k = 0; k < CD_TILE / 32 / 32; k++)
+    {
+      a += red[0][k];
+      b += red[1][k];
+    }
+    tile_cnt[blockIdx.x] = a | (b << 16);
+    if ((a | b) != 0)
+    {
+      atomicAdd(&group_cnt[blockIdx.x >> group_shift], (unsigned long long) a | ((unsigned long long) b << 32));
+      atomicAdd(&scalars[0], (unsigned long long) a);
+      atomicAdd(&scalars[1], (unsigned long long) b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CD_THREADS, 4)
+classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M, u32 *__restrict__ main_key,
+                         u32 *__restrict__ main_pos, u32 *__restrict__ side_key, u32 *__restrict__ side_pos,
+                         u32 *__restrict__ side_dj, u32 *__restrict__ sa, u32 *__restrict__ rank,
+                         u32 *__restrict__ spec_list, u32 group_shift, const u32 *__restrict__ tile_cnt,
+                         const unsigned long long *__restrict__ group_cnt)
+{
+  __shared__ u32 cnt[3][CD_ITEMS * CD_WARPS];  // per (item, warp): members of the class; then exclusive offsets
+  __shared__ u64 base[3];
+  __shared__ u64 part[CD_WARPS];
+  __shared__ ulonglong2 srec[CD_TILE / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 tile = blockIdx.x;
+  const u64 tile_base = p_begin + (u64) tile * CD_TILE;
+  const u32 lt_mask = (1u << lane) - 1;
+  // the tile's 128 records, one coalesced 16-byte load per thread (the 32 positions of a warp share ONE record: loaded
+  // per position, a warp-wide load fetched 16 bytes and the sweep ran at 1 ms per 100 Mbp on memory latency alone)
+  if (tid < CD_TILE / 32 && ((tile_base >> 5) + tid) * 32 < p_end + 64)  // (records end 4 behind the last position)
+  {
+    srec[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(text.pk) + (tile_base >> 5) + tid);
+  }
+  // side and special suffixes in front of this tile: whole groups of tiles, then the tiles of my group (no chained
+  // scan: with some hundred tiles in flight a look-back walks back over all of them, 20 us per tile)
+  {
+    const u32 g = tile >> group_shift;
+    u64 acc = 0;  // nside | nspec << 32 (each below 2^32)
+    for (u32 i = tid; i < g; i += CD_THREADS)
+    {
+      acc += group_cnt[i];
+    }
+    for (u32 t = (g << group_shift) + tid; t < tile; t += CD_THREADS)
+    {
+      const u32 c = tile_cnt[t];
+      acc += (u64) (c & 0xffffu) | ((u64) (c >> 16) << 32);
+    }
+    acc = warp_reduce_sum(acc);
+    if (lane == 0)
+    {
+      part[warp] = acc;
+    }
+  }
+  __syncthreads();  // records staged
+  const u32 o_rec = (u32) lane + 1, bitoff = 2 * o_rec, wi = bitoff >> 5, bo = bitoff & 31;
+  const u32 gmask = ((2u << (((o_rec + h - 1) >> 3) - (o_rec >> 3))) - 1) << (o_rec >> 3);
+  u32 key[CD_ITEMS];
+  u64 dpk = 0;  // 4 bits per item: min(distance to the next special, h), h <= 15
+#pragma unroll
+  for (int i = 0; i < CD_ITEMS; i++)
+  {
+    const u64 p = tile_base + (u64) i * CD_THREADS + tid;
+    u32 d = 0, code = 0;
+    const bool valid = p < p_end;
+    if (valid)
+    {
+      // position p is symbol o = lane + 1 of its record (tiles start at multiples of 32): the h <= 15 symbols behind
+      // it are one 32-bit funnel shift out of the record's four words, at a per-thread constant offset
+      const ulonglong2 rr = srec[(i * CD_THREADS + tid) >> 5];
+      const u32 x0 = (u32) rr.x, x1 = (u32) (rr.x >> 32), x2 = (u32) rr.y, x3 = (u32) (rr.y >> 32);
+      const u32 lo32 = wi == 0 ? x0 : (wi == 1 ? x1 : x2), hi32 = wi == 0 ? x1 : (wi == 1 ? x2 : x3);
+      const u32 w32 = __funnelshift_r(lo32, hi32, bo);
+      d = 32;
+      if (((x3 >> 24) & gmask) != 0)  // a special among the record symbols [o, o + h): ask the mask
+      {
+        const u32 msk = text.mask_slow(p);
+        d = msk ? (u32) (__ffs((int) msk) - 1) : 32u;
+      }
+      d = min(d, h);
+      u32 r = __brev(w32);
+      r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);
+      code = r >> (32 - 2 * h);
+      if (d < h)
+      {
+        code |= (1u << (2 * (h - d))) - 1;  // padded with the largest letter behind the special
+      }
+    }
+    key[i] = (code << 1) | (d < h ? 1u : 0u);
+    dpk |= (u64) d << (4 * i);
+    const u32 bf = __ballot_sync(FULL_MASK, valid && d == h);
+    const u32 bs = __ballot_sync(FULL_MASK, valid && d > 0 && d < h);
+    const u32 bp = __ballot_sync(FULL_MASK, valid && d == 0);
+    if (lane == 0)
+    {
+      cnt[0][i * CD_WARPS + warp] = __popc(bf);
+      cnt[1][i * CD_WARPS + warp] = __popc(bs);
+      cnt[2][i * CD_WARPS + warp] = __popc(bp);
+    }
+  }
+  __syncthreads();
+  if (warp == 0)
+  {
+    // exclusive scan over the CD_ITEMS * CD_WARPS = 128 counters of every class, in position order (item, warp)
+    constexpr int PER = CD_ITEMS * CD_WARPS / 32;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+      u32 v[PER], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++)
+      {
+        v[k] = cnt[c][lane * PER + k];
+        sum += v[k];
+      }
+      const u32 incl = warp_inclusive_sum(sum);
+      u32 run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < PER; k++)
+      {
+        cnt[c][lane * PER + k] = run;
+        run += v[k];
+      }
+    }
+    if (lane == 0)
+    {
+      u64 acc = 0;
+      for (int k = 0; k < CD_WARPS; k++)
+      {
+        acc += part[k];
+      }
+      const u64 ex_side = acc & 0xffffffffull, ex_spec = acc >> 32;
+      base[0] = (tile_base - p_begin) - ex_side - ex_spec;  // every position in front of the tile has one class
+      base[1] = ex_side;
+      base[2] = ex_spec;
+    }
+  }
+  __syncthreads();
+  const u64 bfull = base[0], bside = base[1], bspec = base[2];
+#pragma unroll
+  for (int i = 0; i < CD_ITEMS; i++)
+  {
+    const u64 p = tile_base + (u64) i * CD_THREADS + tid;
+    const bool valid = p < p_end;
+    const u32 d = (u32) (dpk >> (4 * i)) & 15u;
+    const bool is_full = valid && d == h, is_side = valid && d > 0 && d < h, is_spec = valid && d == 0;
+    const u32 bf = __ballot_sync(FULL_MASK, is_full);
+    const u32 bs = __ballot_sync(FULL_MASK, is_side);
+    const u32 bp = __ballot_sync(FULL_MASK, is_spec);
+    const int e = i * CD_WARPS + warp;
+    if (is_full)
+    {
+      const u64 o = bfull + cnt[0][e] + __popc(bf & lt_mask);
+      main_key[o] = key[i];
+      main_pos[o] = (u32) p;
+    } else if (is_side)
+    {
+      const u64 o = bside + cnt[1][e] + __popc(bs & lt_mask);
+      side_key[o] = key[i];
+      side_pos[o] = (u32) p;
+      side_dj[o] = h - d;
+    } else if (is_spec)
+    {
+      const u64 o = bspec + cnt[2][e] + __popc(bp & lt_mask);
+      if (spec_list != nullptr)
+      {
+        spec_list[o] = (u32) p;  // sharded build: the tail is assembled after the exchange
+      } else
+      {
+        const u64 slot = M + o;  // tail of the table, position order
+        sa[slot] = (u32) p;
+        rank[p] = (u32) slot;
+      }
+    }
+  }
+}
+
 // per-bucket count of suffixes with a special inside the k-prefix (side suffixes with j < k)
 __global__ void side_bucket_count_kernel(const u32 *__restrict__ side_key, const u32 *__restrict__ side_dj, u64 nside,
                                          u32 h0, u32 k, u32 kdiv, u32 *__restrict__ cnt)
@@ -540,6 +767,248 @@ regroup_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Register-blocked regroup kernels (default).  Same contract and tile size as regroup_summary_kernel /
+// regroup_apply_kernel above, but every thread keeps its eight consecutive entries in registers (16-byte loads and
+// stores), takes the keys of its neighbours from a two-word shared-memory exchange and derives flags, ranks and
+// destinations without staging the tile in shared memory.  The staged kernels execute 55 (summary) and 97 (apply)
+// instructions per entry and are issue-bound (ncu: 80 % issue utilisation, 9e7 bank conflicts per 100 M entries).
+template <typename KeyT> struct RgVec;
+template <> struct RgVec<u32>
+{
+  static __device__ __forceinline__ void load8(const u32 *p, u32 *k)
+  {
+    const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+    k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y, k[6] = b.z, k[7] = b.w;
+  }
+};
+template <> struct RgVec<u64>
+{
+  static __device__ __forceinline__ void load8(const u64 *p, u64 *k)
+  {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(p)[j];
+      k[2 * j] = a.x;
+      k[2 * j + 1] = a.y;
+    }
+  }
+};
+__device__ __forceinline__ void rg_store8(u32 *p, const u32 *v)
+{
+  reinterpret_cast<uint4 *>(p)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<uint4 *>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+// Loads the thread's eight entries (keys, and slots unless FIRST) and derives heads / active as bit masks.
+// sx: shared exchange [2 * RG_THREADS] of KeyT.  Entries at or behind m get head = active = 0.
+template <typename KeyT, bool FIRST>
+__device__ __forceinline__ void rg2_flags(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m, u64 t0,
+                                          u32 slot_base, KeyT single_mask, KeyT *sx, KeyT *k, u32 *slot, KeyT &prev,
+                                          u32 &heads, u32 &act)
+{
+  const int tid = threadIdx.x;
+  const bool full = t0 + RG_ITEMS <= m;
+  if (full)
+  {
+    RgVec<KeyT>::load8(keys + t0, k);
+    if (!FIRST)
+    {
+      RgVec<u32>::load8(slots + t0, slot);
+    }
+  } else
+  {
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++)
+    {
+      k[i] = t0 + i < m ? keys[t0 + i] : (KeyT) 0;
+      if (!FIRST)
+      {
+        slot[i] = t0 + i < m ? slots[t0 + i] : 0u;
+      }
+    }
+  }
+  if (FIRST)
+  {
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++)
+    {
+      slot[i] = (u32) (t0 + i) + slot_base;  // slots are global suffix-array indices
+    }
+  }
+  sx[tid] = k[0];
+  sx[RG_THREADS + tid] = k[RG_ITEMS - 1];
+  __syncthreads();
+  KeyT next;
+  if (tid > 0)
+  {
+    prev = sx[RG_THREADS + tid - 1];
+  } else
+  {
+    prev = t0 > 0 ? keys[t0 - 1] : (KeyT) 0;
+  }
+  if (tid < RG_THREADS - 1)
+  {
+    next = sx[tid + 1];
+  } else
+  {
+    next = t0 + RG_ITEMS < m ? keys[t0 + RG_ITEMS] : (KeyT) 0;
+  }
+  heads = 0;
+  act = 0;
+  u32 headbits = 0;  // bit i: entry i is a head; bit 8: the entry behind my last one is a head (or the end)
+#pragma unroll
+  for (int i = 0; i <= RG_ITEMS; i++)
+  {
+    const u64 t = t0 + i;
+    const KeyT cur = i < RG_ITEMS ? k[i] : next;
+    const KeyT before = i == 0 ? prev : k[i - 1];
+    // a key with flag bits set belongs to a suffix that is unique and already in its final place (see rg_flags)
+    const bool h = t >= m || t == 0 || cur != before || (cur & single_mask) != 0;
+    headbits |= h ? (1u << i) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < RG_ITEMS; i++)
+  {
+    if (t0 + i < m)
+    {
+      const bool h = (headbits >> i) & 1u, nh = (headbits >> (i + 1)) & 1u;
+      heads |= h ? (1u << i) : 0u;
+      act |= (h && nh) ? 0u : (1u << i);
+    }
+  }
+}
+
+template <typename KeyT, bool FIRST>
+__global__ void __launch_bounds__(RG_THREADS)
+regroup2_summary_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ slots, u64 m,
+                        u32 *__restrict__ tile_maxrank, u32 *__restrict__ tile_active, u32 slot_base, KeyT single_mask)
+{
+  __shared__ KeyT sx[2 * RG_THREADS];
+  __shared__ u32 red[2][RG_THREADS / 32];
+  const u64 t0 = (u64) blockIdx.x * RG_TILE + (u64) threadIdx.x * RG_ITEMS;
+  KeyT k[RG_ITEMS], prev;
+  u32 slot[RG_ITEMS], heads, act;
+  rg2_flags<KeyT, FIRST>(keys, slots, m, t0, slot_base, single_mask, sx, k, slot, prev, heads, act);
+  u32 mx = heads ? slot[31 - __clz((int) heads)] : 0u;  // slots increase: the last head carries the maximum
+  u32 cnt = __popc(act);
+  mx = warp_reduce_max(mx);
+  cnt = warp_reduce_sum(cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+  {
+    red[0][warp] = mx;
+    red[1][warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    u32 a = 0, b = 0;
+    for (int w = 0; w < RG_THREADS / 32; w++)
+    {
+      a = max(a, red[0][w]);
+      b += red[1][w];
+    }
+    tile_maxrank[blockIdx.x] = a;
+    tile_active[blockIdx.x] = b;
+  }
+}
+
+template <typename KeyT, bool FIRST>
+__global__ void __launch_bounds__(RG_THREADS)
+regroup2_apply_kernel(const KeyT *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slots, u64 m,
+                      const u32 *__restrict__ tile_maxrank, const u32 *__restrict__ tile_active, u32 *__restrict__ sa,
+                      u32 *__restrict__ rank, u64 *__restrict__ next_key, u32 *__restrict__ next_pos,
+                      u32 *__restrict__ next_slots, u32 rank_shift, u32 next_shift, u8 *__restrict__ hround, u32 round,
+                      u32 *__restrict__ rank_out, u32 slot_base, KeyT single_mask, u32 *__restrict__ rank_slot)
+{
+  __shared__ KeyT sx[2 * RG_THREADS];
+  __shared__ u32 scratch[RG_THREADS / 32 + 1];
+  __shared__ u32 sincl[RG_THREADS];
+  const u64 t0 = (u64) blockIdx.x * RG_TILE + (u64) threadIdx.x * RG_ITEMS;
+  KeyT k[RG_ITEMS], prev;
+  u32 slot[RG_ITEMS], heads, act;
+  rg2_flags<KeyT, FIRST>(keys, slots, m, t0, slot_base, single_mask, sx, k, slot, prev, heads, act);
+  const u32 lastrank = heads ? slot[31 - __clz((int) heads)] : 0u;
+  const u32 nact = __popc(act);
+  const u32 ex_act = block_exclusive_sum<u32, RG_THREADS>(nact, scratch, nullptr);
+  const u32 incl = block_inclusive_max<u32, RG_THREADS>(lastrank, scratch);
+  sincl[threadIdx.x] = incl;
+  __syncthreads();
+  u32 cur = max(tile_maxrank[blockIdx.x], threadIdx.x > 0 ? sincl[threadIdx.x - 1] : 0u);
+  u32 dst = tile_active[blockIdx.x] + ex_act;
+  const bool full = t0 + RG_ITEMS <= m;
+  u32 p[RG_ITEMS], r[RG_ITEMS];
+  if (full)
+  {
+    RgVec<u32>::load8(pos + t0, p);
+  } else
+  {
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++)
+    {
+      p[i] = t0 + i < m ? pos[t0 + i] : 0u;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RG_ITEMS; i++)
+  {
+    if ((heads >> i) & 1u)
+    {
+      cur = slot[i];
+    }
+    r[i] = cur;
+  }
+  // the ranks: in suffix-array order (vector store), by slot (deferred scatter list) or scattered by position
+  if (rank_slot == nullptr && rank_out != nullptr && full)
+  {
+    rg_store8(rank_out + t0, r);
+  }
+#pragma unroll
+  for (int i = 0; i < RG_ITEMS; i++)
+  {
+    const u64 t = t0 + i;
+    if (t < m)
+    {
+      if (!FIRST)
+      {
+        sa[slot[i] - slot_base] = p[i];  // FIRST: the sorted position buffer already is sa[0..m)
+      }
+      if (rank_slot != nullptr)
+      {
+        rank_slot[slot[i] - slot_base] = r[i];
+      } else if (rank_out != nullptr)
+      {
+        if (!full)
+        {
+          rank_out[t] = r[i];
+        }
+      } else
+      {
+        rank[p[i]] = r[i];
+      }
+      if ((act >> i) & 1u)
+      {
+        next_key[dst] = (u64) r[i] << next_shift;
+        next_pos[dst] = p[i];
+        next_slots[dst] = slot[i];
+        dst++;
+      }
+      if (!FIRST && hround != nullptr && t > 0 && ((heads >> i) & 1u))
+      {
+        // a head whose predecessor belongs to the same old group was split off in this round: the two
+        // suffixes agree on the depth of the round (lcp lower bound for the direct lcp kernel)
+        const KeyT before = i == 0 ? prev : k[i - 1];
+        if ((u64) (k[i] >> rank_shift) == (u64) (before >> rank_shift))
+        {
+          hround[slot[i] - slot_base] = (u8) round;
+        }
+      }
+    }
+  }
+}
+
 // 5a. text round: low key bits = the next L symbols behind the h the group agrees on, as an order-preserving code.
 // Window of L letters: code (base sigma, first symbol in the top digit) << F.  A special (or the end of the text) at
 // offset d < L: the letters in front of it padded with the largest letter, flag field = L - d > 0 in the low F bits.
@@ -828,6 +1297,98 @@ u64 read_scalar(esa_ctx *ctx, const u64 *d_scalars, int idx)
   return ctx->h_scalars[0];
 }
 
+// scratch of the regroup step: per-tile carries
+struct RegroupScratch
+{
+  u32 *tile_maxrank = nullptr, *tile_active = nullptr;
+};
+RegroupScratch alloc_regroup_scratch(Arena &ar, u64 max_items)
+{
+  const size_t tiles = (size_t) div_up_u64(max_items, RG_TILE) + 1;
+  RegroupScratch rs;
+  rs.tile_maxrank = ar.alloc<u32>(tiles);
+  rs.tile_active = ar.alloc<u32>(tiles);
+  return rs;
+}
+
+// One regroup step over m sorted (key, position[, slot]) entries: summary kernel, single-CTA scan over the tiles,
+// apply kernel; returns the number of active suffixes it left.
+// (A single-pass version -- the apply kernel with chained scans over the tiles instead of the summary kernel and the
+// scan -- was measured and dropped: with some hundred tiles of 2048 entries in flight every tile walks back over all
+// of them before it meets a prefix, and even with the whole CTA reading 256 predecessors per round trip the sweep
+// saved over the keys was lost again: 1.40 vs 1.41 ms per 100 Mbp, 33.9 vs 29.6 ms on the repeat-rich 250 Mbp.)
+// The register-blocked kernels serve the FIRST regroup (its rank list is one vector store per thread: 1.22 -> 1.06 ms
+// per 100 Mbp); the rounds keep the staged kernels, whose thread-striped stores by slot coalesce where the blocked
+// ones write with a stride of eight entries (repeat-rich 250 Mbp: 29.6 ms staged, 36.6 ms blocked).
+// ESA_REGROUP_STAGED=1 / ESA_REGROUP_BLOCKED=1 force one kind everywhere.
+template <bool FIRST> bool staged_regroup_for()
+{
+  static const bool staged = getenv("ESA_REGROUP_STAGED") != nullptr, blocked = getenv("ESA_REGROUP_BLOCKED") != nullptr;
+  return staged ? true : (blocked ? false : !FIRST);
+}
+
+// first half: per-tile carries and the number of active suffixes the step will leave
+template <typename KeyT, bool FIRST>
+u64 run_regroup_summary(esa_ctx *ctx, const RegroupScratch &rs, u64 *d_scalars, const KeyT *keys, const u32 *slots,
+                        u64 m, u32 slot_base, KeyT single_mask)
+{
+  cudaStream_t s = ctx->stream;
+  const u32 rtiles = (u32) div_up_u64(m, RG_TILE);
+  if (staged_regroup_for<FIRST>())
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, (FIRST ? 4.0 : 12.0) * m,
+               (regroup_summary_kernel<KeyT, FIRST><<<rtiles, RG_THREADS, 0, s>>>(keys, slots, m, rs.tile_maxrank,
+                                                                                   rs.tile_active, slot_base,
+                                                                                   single_mask)));
+  } else
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, (FIRST ? 4.0 : 12.0) * m,
+               (regroup2_summary_kernel<KeyT, FIRST><<<rtiles, RG_THREADS, 0, s>>>(keys, slots, m, rs.tile_maxrank,
+                                                                                    rs.tile_active, slot_base,
+                                                                                    single_mask)));
+  }
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+             (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(rs.tile_maxrank, rs.tile_active, rtiles, d_scalars)));
+  return read_scalar(ctx, d_scalars, 4);
+}
+
+// second half: ranks, suffix array entries, lcp lower bounds and the next active list (m_next entries)
+template <typename KeyT, bool FIRST>
+void run_regroup_apply(esa_ctx *ctx, const RegroupScratch &rs, u64 m_next, const KeyT *keys, const u32 *pos,
+                       const u32 *slots, u64 m, u32 *sa, u32 *rank, u64 *next_key, u32 *next_pos, u32 *next_slots,
+                       u32 cur_shift, u32 next_shift, u8 *hround, u32 round, u32 *rank_out, u32 slot_base,
+                       KeyT single_mask, u32 *rank_slot)
+{
+  cudaStream_t s = ctx->stream;
+  const u32 rtiles = (u32) div_up_u64(m, RG_TILE);
+  const double bytes = (FIRST ? 12.0 : 24.0) * m + 16.0 * m_next;
+  if (staged_regroup_for<FIRST>())
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, bytes,
+               (regroup_apply_kernel<KeyT, FIRST><<<rtiles, RG_THREADS, 0, s>>>(
+                   keys, pos, slots, m, rs.tile_maxrank, rs.tile_active, sa, rank, next_key, next_pos, next_slots,
+                   cur_shift, next_shift, hround, round, rank_out, slot_base, single_mask, rank_slot)));
+  } else
+  {
+    ESA_LAUNCH(ctx, ESA_K_REGROUP, bytes,
+               (regroup2_apply_kernel<KeyT, FIRST><<<rtiles, RG_THREADS, 0, s>>>(
+                   keys, pos, slots, m, rs.tile_maxrank, rs.tile_active, sa, rank, next_key, next_pos, next_slots,
+                   cur_shift, next_shift, hround, round, rank_out, slot_base, single_mask, rank_slot)));
+  }
+}
+
+template <typename KeyT, bool FIRST>
+u64 run_regroup(esa_ctx *ctx, const RegroupScratch &rs, u64 *d_scalars, const KeyT *keys, const u32 *pos,
+                const u32 *slots, u64 m, u32 *sa, u32 *rank, u64 *next_key, u32 *next_pos, u32 *next_slots,
+                u32 cur_shift, u32 next_shift, u8 *hround, u32 round, u32 *rank_out, u32 slot_base, KeyT single_mask,
+                u32 *rank_slot)
+{
+  const u64 m_next = run_regroup_summary<KeyT, FIRST>(ctx, rs, d_scalars, keys, slots, m, slot_base, single_mask);
+  run_regroup_apply<KeyT, FIRST>(ctx, rs, m_next, keys, pos, slots, m, sa, rank, next_key, next_pos, next_slots,
+                                 cur_shift, next_shift, hround, round, rank_out, slot_base, single_mask, rank_slot);
+  return m_next;
+}
+
 }  // namespace
 
 // choose h0: the largest h <= 31 with sigma^h <= 2^31
@@ -859,15 +1420,42 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_scalars, 0, 16 * sizeof(u64), s)));
 
   // ---- 1. classification
+  static const bool no_dna_classify = getenv("ESA_NO_DNA_CLASSIFY") != nullptr;
+  const bool dna_classify = sigma == 4 && ctx->d_pk != nullptr && !no_dna_classify;
   const u32 ktiles = (u32) div_up_u64(N, KS_TILE);
-  u32 *tile_full = ar.alloc<u32>(ktiles), *tile_side = ar.alloc<u32>(ktiles), *tile_spec = ar.alloc<u32>(ktiles);
-  ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N,
-             (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side,
-                                                                   tile_spec)));
-  ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-             (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles, d_scalars,
-                                                                     0)));
-  read_back_u64(ctx, d_scalars, 4);
+  u32 *tile_full = nullptr, *tile_side = nullptr, *tile_spec = nullptr;
+  const u32 dtiles = (u32) div_up_u64(N, CD_TILE);
+  u32 dna_group_shift = 0, *dna_tile_cnt = nullptr;
+  unsigned long long *dna_group_cnt = nullptr;
+  if (dna_classify)
+  {
+    // class counts per tile, per group of tiles and in total from the special mask alone (12.5 MB per 100 Mbp)
+    dna_group_shift = 0;
+    while (((u64) 1 << (2 * dna_group_shift)) < dtiles)
+    {
+      dna_group_shift++;  // groups of about sqrt(tiles) tiles
+    }
+    dna_tile_cnt = ar.alloc<u32>(dtiles + 1);
+    dna_group_cnt = reinterpret_cast<unsigned long long *>(ar.alloc<u64>((dtiles >> dna_group_shift) + 2));
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0,
+               CUDA_CHECK(cudaMemsetAsync(dna_group_cnt, 0, ((dtiles >> dna_group_shift) + 2) * sizeof(u64), s)));
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N / 8,
+               (classify_dna_count_kernel<<<dtiles, CD_TILE / 32, 0, s>>>(
+                   ctx->d_spm, 0, N, h0, dna_group_shift, dna_tile_cnt, dna_group_cnt,
+                   reinterpret_cast<unsigned long long *>(d_scalars + 1))));
+    read_back_u64(ctx, d_scalars, 4);
+    ctx->h_scalars[0] = N - ctx->h_scalars[1] - ctx->h_scalars[2];
+  } else
+  {
+    tile_full = ar.alloc<u32>(ktiles), tile_side = ar.alloc<u32>(ktiles), tile_spec = ar.alloc<u32>(ktiles);
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N,
+               (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side,
+                                                                     tile_spec)));
+    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+               (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
+                                                                       d_scalars, 0)));
+    read_back_u64(ctx, d_scalars, 4);
+  }
   const u64 nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
   const u64 M = nfull + nside;  // suffixes that take part in the sort
   if (M + nspec != N)
@@ -878,16 +1466,27 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 
   // region X: ping-pong buffers of the initial 32-bit sort (16 bytes per sorted suffix)
   const u64 Mal = M + 64;
-  u32 *key_a = ar.alloc<u32>(Mal), *key_b = ar.alloc<u32>(Mal), *pos_a = ar.alloc<u32>(Mal), *pos_b = ar.alloc<u32>(Mal);
+  // the position buffer the four-pass sort ends in IS the suffix array (no copy afterwards)
+  u32 *key_a = ar.alloc<u32>(Mal), *key_b = ar.alloc<u32>(Mal), *pos_a = sa, *pos_b = ar.alloc<u32>(Mal);
   u32 *side_key = ar.alloc<u32>(nside + 1), *side_pos = ar.alloc<u32>(nside + 1), *side_dj = ar.alloc<u32>(nside + 1),
       *side_tmp = ar.alloc<u32>(nside + 1);
   const size_t temp_bytes = max(radix_sort_temp_bytes(M, 4), radix_sort_temp_bytes(M, 8));
   void *sort_temp = ar.alloc<char>(temp_bytes);
 
-  ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N + 8.0 * M + 8.0 * nspec,
-             (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side, tile_spec,
-                                                                  M, key_a, pos_a, side_key, side_pos, side_dj,
-                                                                  sa, rank, nullptr)));
+  if (dna_classify)
+  {
+    const TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, 0.5 * N + 8.0 * M + 8.0 * nspec,
+               (classify_dna_emit_kernel<<<dtiles, CD_THREADS, 0, s>>>(text, 0, N, h0, M, key_a, pos_a, side_key,
+                                                                        side_pos, side_dj, sa, rank, nullptr,
+                                                                        dna_group_shift, dna_tile_cnt, dna_group_cnt)));
+  } else
+  {
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) N + 8.0 * M + 8.0 * nspec,
+               (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, 0, N, kp, tile_full, tile_side,
+                                                                    tile_spec, M, key_a, pos_a, side_key, side_pos,
+                                                                    side_dj, sa, rank, nullptr)));
+  }
   // side suffixes: stable sort by h0-j, written straight behind the full ones
   if (nside == 1)
   {
@@ -933,7 +1532,7 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
     }
   }
   // the sorted positions are sa[0..M)
-  if (M > 0)
+  if (M > 0 && spos != sa)
   {
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 8.0 * M, CUDA_CHECK(cudaMemcpyAsync(sa, spos, M * sizeof(u32), cudaMemcpyDeviceToDevice, s)));
   }
@@ -962,21 +1561,13 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   }
   RefinePlan plan = make_refine_plan(ctx, bits_for(N - 1), h0);
   const u32 rank_shift = plan.rank_shift;
-  u32 rtiles = (u32) div_up_u64(M, RG_TILE);
-  u32 *tile_maxrank = ar.alloc<u32>(rtiles), *tile_active = ar.alloc<u32>(rtiles);
-  ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
-             (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
-                                                                                tile_active, 0u, 1u)));
-  ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-             (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-  u64 m = read_scalar(ctx, d_scalars, 4);
-  outcome->active_first = m;
-
+  const RegroupScratch rs = alloc_regroup_scratch(ar, M);
+  u64 m = run_regroup_summary<u32, true>(ctx, rs, d_scalars, skey, nullptr, M, 0u, 1u);
   // region Y: fresh buffers for the first doubling input; their ping-pong partners alias region X, which is
   // dead once the first regroup has consumed the sorted 32-bit keys
-  const u64 mal = m + 64;
-  u64 *dk_in = ar.alloc<u64>(mal);
-  u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
+  const u64 mcap = m + 64;
+  u64 *dk_in = ar.alloc<u64>(mcap);
+  u32 *dp_in = ar.alloc<u32>(mcap), *slots_cur = ar.alloc<u32>(mcap);
   // rank scatter of the first regroup: deferred when text rounds follow (or nothing follows): the rank list in
   // suffix-array order is kept, the N-wide scatter happens only if a doubling round needs rank[].  Otherwise
   // two-level, and its scratch costs nothing -- the rank list in suffix-array order goes into the position buffer the
@@ -986,23 +1577,21 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   u32 *part_rank = nullptr, *part_tp = nullptr, *part_tv = nullptr;
   if (!plan.pending && M >= PARTITIONED_SCATTER_MIN && rank_shift > SCATTER_WINDOW_BITS)
   {
-    part_rank = spos == pos_a ? pos_b : pos_a;
+    part_rank = spos == sa ? pos_b : ar.alloc<u32>(Mal);  // the position buffer the sort did not end in
     part_tp = key_a;
     part_tv = key_b;
   }
-  ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
-             (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
-                                                                              tile_active, sa, rank, dk_in, dp_in,
-                                                                              slots_cur, 0u, plan.shift_of(1), nullptr, 0u,
-                                                                              plan.pending ? plan.rank_sa : part_rank,
-                                                                              0u, 1u, nullptr)));
+  run_regroup_apply<u32, true>(ctx, rs, m, skey, spos, nullptr, M, sa, rank, dk_in, dp_in, slots_cur, 0u,
+                               plan.shift_of(1), nullptr, 0u, plan.pending ? plan.rank_sa : part_rank, 0u, 1u, nullptr);
+  outcome->active_first = m;
   if (part_rank != nullptr)
   {
     scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
   }
   // partners carved out of region X (key_a .. pos_b are contiguous allocations of 4*Mal words = 16*Mal bytes)
+  const u64 mal = m + 64;
   u64 *dk_out = reinterpret_cast<u64 *>(key_a);          // 8*mal bytes  <= 8*Mal  (key_a + key_b)
-  u32 *dp_out = pos_a;                                    // 4*mal bytes
+  u32 *dp_out = ar.alloc<u32>(mal);                       // (pos_a is the suffix array itself)
   u32 *slots_next = pos_b;                                // 4*mal bytes
 
   // ---- 5. refinement rounds
@@ -1034,24 +1623,12 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
       ps = dp_out;
       po = dp_in;
     }
-    rtiles = (u32) div_up_u64(m, RG_TILE);
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
-               (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                   tile_active, 0u,
-                                                                                   plan.mask_of(round))));
-    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-               (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-    const u64 m_next = read_scalar(ctx, d_scalars, 4);
     const size_t scatter_mark = ar.mark();
     const ScatterScratch sc = plan.pending ? ScatterScratch() : round_scatter_scratch(ar, m, rank_shift);
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
-               (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, ps, slots_cur, m, tile_maxrank,
-                                                                                 tile_active, sa, rank, ko, po,
-                                                                                 slots_next, cur_shift,
-                                                                                 plan.shift_of(round + 1),
-                                                                                 ctx->d_hround, round, sc.rank_out, 0u,
-                                                                                 plan.mask_of(round),
-                                                                                 plan.pending ? plan.rank_sa : nullptr)));
+    const u64 m_next = run_regroup<u64, false>(ctx, rs, d_scalars, ks, ps, slots_cur, m, sa, rank, ko, po,
+                                               slots_next, cur_shift, plan.shift_of(round + 1), ctx->d_hround, round,
+                                               sc.rank_out, 0u, plan.mask_of(round),
+                                               plan.pending ? plan.rank_sa : nullptr);
     if (sc.rank_out != nullptr)
     {
       scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
@@ -1689,22 +2266,15 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   RefinePlan plan = make_refine_plan(ctx, max(bits_for(N - 1), 8u), h0);
   const u32 rank_shift = plan.rank_shift;
   const u32 owner_bits = bits_for((u64) G - 1);
-  u32 rtiles = (u32) div_up_u64(M, RG_TILE);
-  u32 *tile_maxrank = ar.alloc<u32>(rtiles + 1), *tile_active = ar.alloc<u32>(rtiles + 1);
+  const RegroupScratch rs = alloc_regroup_scratch(ar, M);
   u64 m = 0;
   if (M > 0)
   {
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 4.0 * M,
-               (regroup_summary_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, nullptr, M, tile_maxrank,
-                                                                                  tile_active, slot_base, 1u)));
-    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-               (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-    m = read_scalar(ctx, d_scalars, 4);
+    m = run_regroup_summary<u32, true>(ctx, rs, d_scalars, skey, nullptr, M, slot_base, 1u);
   }
-  outcome->active_first = m;
-  const u64 mal = m + 64;
-  u64 *dk_in = ar.alloc<u64>(mal);
-  u32 *dp_in = ar.alloc<u32>(mal), *slots_cur = ar.alloc<u32>(mal);
+  const u64 mcap = m + 64;
+  u64 *dk_in = ar.alloc<u64>(mcap);
+  u32 *dp_in = ar.alloc<u32>(mcap), *slots_cur = ar.alloc<u32>(mcap);
   // the scatter of the first regroup is deferred like on one GPU; whether a doubling round follows the text rounds
   // is a property of all ranks together (a rank without active suffixes still owns ranks others will ask for)
   if (plan.text_rounds > 0)
@@ -1720,18 +2290,15 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   }
   if (M > 0)
   {
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 8.0 * M + 4.0 * M + 16.0 * m,
-               (regroup_apply_kernel<u32, true><<<rtiles, RG_THREADS, 0, s>>>(skey, spos, nullptr, M, tile_maxrank,
-                                                                                tile_active, sa, rank, dk_in, dp_in,
-                                                                                slots_cur, 0u, plan.shift_of(1), nullptr,
-                                                                                0u,
-                                                                                plan.pending ? plan.rank_sa : part_rank,
-                                                                                slot_base, 1u, nullptr)));
+    run_regroup_apply<u32, true>(ctx, rs, m, skey, spos, nullptr, M, sa, rank, dk_in, dp_in, slots_cur, 0u,
+                                 plan.shift_of(1), nullptr, 0u, plan.pending ? plan.rank_sa : part_rank, slot_base, 1u,
+                                 nullptr);
     if (part_rank != nullptr)
     {
       scatter_ranks_partitioned(ctx, spos, part_rank, M, rank_shift, rank, part_tp, part_tv, sort_temp, temp_bytes);
     }
   }
+  outcome->active_first = m;
   // ping-pong partners of the doubling buffers alias the 32-bit sort region (dead after the first regroup)
   u64 *dk_out = reinterpret_cast<u64 *>(key_a);
   u32 *dp_out = pos_a;
@@ -1742,41 +2309,28 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   keyof.tis = ctx->d_tis;
   keyof.packed = TextPacked2{sigma == 4 ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
   keyof.kp = kp;
-  // sort + regroup of one round on this rank (the secondary keys are in place); returns the next active count
-  auto sort_and_regroup = [&](u32 round) -> u64 {
+  // the sort of one round on this rank (the secondary keys are in place): afterwards (dk_in, dp_in) is sorted
+  auto sort_round = [&](u32 round) {
     const u32 cur_shift = plan.shift_of(round);
-    u64 *ks = dk_in, *ko = dk_out;
-    u32 *ps = dp_in, *po = dp_out;
     if (m > 1 && doubling_sort(ctx, dk_in, dk_out, dp_in, dp_out, m, cur_shift, cur_shift + rank_shift, sort_temp,
                                temp_bytes))
     {
-      ks = dk_out, ko = dk_in;
-      ps = dp_out, po = dp_in;
+      u64 *tk = dk_in;
+      dk_in = dk_out;
+      dk_out = tk;
+      u32 *tp = dp_in;
+      dp_in = dp_out;
+      dp_out = tp;
     }
-    rtiles = (u32) div_up_u64(m, RG_TILE);
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 12.0 * m,
-               (regroup_summary_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(ks, slots_cur, m, tile_maxrank,
-                                                                                   tile_active, slot_base,
-                                                                                   plan.mask_of(round))));
-    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-               (regroup_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_maxrank, tile_active, rtiles, d_scalars)));
-    const u64 m_next = read_scalar(ctx, d_scalars, 4);
-    dk_in = ks, dk_out = ko;  // sorted lists; apply_round reads them
-    dp_in = ps, dp_out = po;
-    return m_next;
   };
-  // new ranks, suffix array entries and the next active list of one round on this rank
-  auto apply_round = [&](u32 round, u64 m_next) {
+  // new ranks, suffix array entries and the next active list of one round on this rank; returns its size
+  auto regroup_round = [&](u32 round) -> u64 {
     const size_t scatter_mark = ar.mark();
     const ScatterScratch sc = plan.pending ? ScatterScratch() : round_scatter_scratch(ar, m, rank_shift);
-    ESA_LAUNCH(ctx, ESA_K_REGROUP, 24.0 * m + 16.0 * m_next,
-               (regroup_apply_kernel<u64, false><<<rtiles, RG_THREADS, 0, s>>>(dk_in, dp_in, slots_cur, m, tile_maxrank,
-                                                                                 tile_active, sa, rank, dk_out, dp_out,
-                                                                                 slots_next, plan.shift_of(round),
-                                                                                 plan.shift_of(round + 1),
-                                                                                 ctx->d_hround, round, sc.rank_out,
-                                                                                 slot_base, plan.mask_of(round),
-                                                                                 plan.pending ? plan.rank_sa : nullptr)));
+    const u64 m_next = run_regroup<u64, false>(ctx, rs, d_scalars, dk_in, dp_in, slots_cur, m, sa, rank,
+                                               dk_out, dp_out, slots_next, plan.shift_of(round),
+                                               plan.shift_of(round + 1), ctx->d_hround, round, sc.rank_out, slot_base,
+                                               plan.mask_of(round), plan.pending ? plan.rank_sa : nullptr);
     if (sc.rank_out != nullptr)
     {
       scatter_ranks_partitioned(ctx, dp_in, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
@@ -1791,6 +2345,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     u32 *t = slots_cur;
     slots_cur = slots_next;
     slots_next = t;
+    return m_next;
   };
   // text rounds: the secondary keys come from the replicated text -- no communication but the active counts
   u64 h = h0;
@@ -1813,8 +2368,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     {
       ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 20.0 * m,
                  (text_key_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, plan.tk)));
-      m_next = sort_and_regroup(round);
-      apply_round(round, m_next);
+      sort_round(round);
+      m_next = regroup_round(round);
     }
     u64 world[ESA_MAX_RANKS];
     comm_exchange_host_u64(ctx, comm, &m_next, 1, world);
@@ -1862,28 +2417,25 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
         ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
                    (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut, peers)));
         comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
-        m_next = sort_and_regroup(round);
-      } else
-      {
-        CUDA_CHECK(cudaStreamSynchronize(s));
+        sort_round(round);
       }
       // barrier 1: every rank has finished reading rank[] (its gather precedes this point on its stream)
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      {
+        u64 zero = 0, dummy[ESA_MAX_RANKS];
+        comm_exchange_host_u64(ctx, comm, &zero, 1, dummy);
+      }
+      if (m > 0)
+      {
+        m_next = regroup_round(round);  // updates rank[]; synchronises the stream (read-back of the active count)
+      }
+      // barrier 2 (carries the active counts): every rank has finished updating rank[] before anybody gathers again
       u64 world_next[ESA_MAX_RANKS], sum_next = 0;
+      CUDA_CHECK(cudaStreamSynchronize(s));
       comm_exchange_host_u64(ctx, comm, &m_next, 1, world_next);
       for (int r = 0; r < G; r++)
       {
         sum_next += world_next[r];
-      }
-      if (m > 0)
-      {
-        apply_round(round, m_next);
-      }
-      if (sum_next > 0)
-      {
-        // barrier 2: every rank has finished updating rank[] before anybody gathers again
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        u64 zero = 0, dummy[ESA_MAX_RANKS];
-        comm_exchange_host_u64(ctx, comm, &zero, 1, dummy);
       }
       m = m_next;
       m_world = sum_next;
@@ -1960,8 +2512,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 20.0 * m,
                  (merge_answer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, idx, ans_in, m)));
       ar.rewind(round_mark);  // the round's exchange buffers are dead (later users are stream ordered)
-      m_next = sort_and_regroup(round);
-      apply_round(round, m_next);
+      sort_round(round);
+      m_next = regroup_round(round);
     } else
     {
       ar.rewind(round_mark);

@@ -30,6 +30,13 @@ struct TextBytes
     u64 w;
     u32 before;
   };
+  static __device__ __forceinline__ Probe probe_from_lane_below(u32 mask, const Probe &x)
+  {
+    Probe r;
+    r.w = __shfl_up_sync(mask, x.w, 1);
+    r.before = __shfl_up_sync(mask, x.before, 1);
+    return r;
+  }
   __device__ __forceinline__ Probe probe(u64 p) const
   {
     Probe r;
@@ -172,6 +179,14 @@ struct TextPacked2
     u32 m;
     u32 before;
   };
+  static __device__ __forceinline__ Probe probe_from_lane_below(u32 mask, const Probe &x)
+  {
+    Probe r;
+    r.w = __shfl_up_sync(mask, x.w, 1);
+    r.m = __shfl_up_sync(mask, x.m, 1);
+    r.before = __shfl_up_sync(mask, x.before, 1);
+    return r;
+  }
   __device__ __forceinline__ Probe probe(u64 p) const
   {
     const Rec x = load(p);
