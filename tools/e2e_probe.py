@@ -16,6 +16,20 @@ tis = bench.make_tis("c2")[0]
 pinned = torch.from_numpy(tis).pin_memory().numpy()
 k = int(load_library().esa_recommended_prefixlength(sigma, n))
 with Esa(0) as esa:
+    mode = os.environ.get("PROBE_PRE", "")
+    if mode:
+        # what bench.py does in front of its end-to-end leg: staged builds, optionally under the NVML clock sampler
+        esa.upload(pinned, sigma)
+        sampler = None
+        if "nvml" in mode:
+            sampler = bench.ClockSampler(0)
+            sampler.start()
+        for _ in range(8):
+            esa.construct(k, bench.TABLES)
+        if sampler is not None:
+            print("sampler", sampler.stop(), flush=True)
+        if "check" in mode:
+            esa.check()
     for i in range(steps):
         t0 = time.perf_counter()
         tabs, st = esa.build(pinned, sigma, k, bench.TABLES, want_stats=True, copy=False)

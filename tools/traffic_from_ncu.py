@@ -1,5 +1,5 @@
 """profiles/radix_pass_traffic.json from an ncu report that captured every radix_pass launch of ONE build
-(ncu --set full -k regex:radix_pass_kernel -s <launches of the first build> -c <launches per build>):
+(ncu --set full -k "regex:radix_pass_kernel|ds_local_kernel" -c <launches per build>):
 DRAM bytes (read + write) per launch, averaged over the launches like bench.py's `achieved`.
     python tools/traffic_from_ncu.py report.ncu-rep out.json"""
 import csv
@@ -23,8 +23,8 @@ def val(d, name):
 
 launches = []
 for d in data:
-    if "radix_pass_kernel" not in d[ix["Kernel Name"]]:
-        continue
+    if "radix_pass_kernel" not in d[ix["Kernel Name"]] and "ds_local_kernel" not in d[ix["Kernel Name"]]:
+        continue  # the launches of the ESA_K_RADIX_PASS family (ds_local_kernel is the in-tile sort of a round)
     launches.append({"grid": d[ix["Grid Size"]], "kernel": d[ix["Kernel Name"]][:80],
                      "dram_bytes": val(d, "dram__bytes_read.sum") + val(d, "dram__bytes_write.sum"),
                      "time_us": float(d[ix["gpu__time_duration.sum"]].replace(",", "")) *
