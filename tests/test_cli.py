@@ -90,6 +90,39 @@ def test_host_tables_dna(tmp_path, args):
 
 
 @needs_ref
+@pytest.mark.parametrize("args", [
+    ["-db", "in.fna", "-dna", "-tis", "-ois", "-rev", "-v"],
+    ["-db", "in.fna", "-dna", "-tis", "-ois", "-cpl", "-v"],
+    ["-db", "in.fna", "-dna", "-tis", "-ois", "-rev", "-cpl", "-v"],
+    ["-db", "in.fna", "-dna", "-cpl", "-rev", "-tis", "-indexname", "named", "-v"],
+    ["-db", "in.fna", "-dna", "-tis", "-pl", "-rev"],
+])
+def test_reverse_and_complement_host_tables(tmp_path, args):
+    """-rev / -cpl transform the sequence only (.ois, .des, .sds, .ssp and the project counts stay) and name the index
+    <name>.rev / .cpl / .rcp (src/Mkvtree/mkvinput.c:273-309, mkvtree.c:143-161)."""
+    ra, rb = compare(tmp_path, {"in.fna": DNA}, args)
+    assert any(k.split(".")[-2] in ("rev", "cpl", "rcp") for k in rb[3])
+
+
+@needs_ref
+def test_reverse_of_odd_and_single_symbol_inputs(tmp_path):
+    compare(tmp_path, {"a.fna": b">x\nACGTN\n"}, ["-db", "a.fna", "-dna", "-tis", "-rev", "-cpl"])
+    (tmp_path / "two").mkdir()
+    compare(tmp_path / "two", {"a.fna": b">x\nG\n"}, ["-db", "a.fna", "-dna", "-tis", "-cpl"])
+
+
+@needs_ref
+@pytest.mark.parametrize("extra", [["-cpl"], ["-rev", "-cpl"]])
+def test_complement_of_protein_is_the_reference_error(tmp_path, extra):
+    compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis"] + extra, expect_rc=1)
+
+
+@needs_ref
+def test_reverse_of_protein(tmp_path):
+    compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-rev", "-v"])
+
+
+@needs_ref
 def test_host_tables_protein(tmp_path):
     compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-pl", "1", "-v"])
 
@@ -202,6 +235,10 @@ def test_host_tables_on_reference_fixtures(tmp_path, refdata):
     (["-db", "in.fna", "-dna", "-suf", "-lcp", "-skp"], DNA),                      # without -pl
     (["-db", "in.fna", "-dna", "-pl", "-allout", "-v"], DNA),
     (["-db", "in.fna", "-protein", "-pl", "1", "-allout", "-v"], PROT),
+    (["-db", "in.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois", "-rev", "-v"], DNA),
+    (["-db", "in.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-rev", "-cpl", "-v"], DNA),   # <name>.rcp.*
+    (["-db", "in.fna", "-dna", "-pl", "2", "-allout", "-cpl"], DNA),
+    (["-db", "in.fna", "-protein", "-pl", "-suf", "-lcp", "-bwt", "-rev", "-v"], PROT),
 ])
 def test_full_cli_small(tmp_path, args, data):
     compare(tmp_path, {"in.fna": data}, args)

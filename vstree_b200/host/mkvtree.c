@@ -11,7 +11,9 @@
  * The host keeps alphabet transformation and file I/O; there is no CPU implementation of the sort behind it:
  * without a GPU the program fails.
  *
- * Not supported (reported as errors): -q, -rev, -cpl, -maxdepth, GenBank/EMBL/SwissProt input,
+ *   -rev / -cpl           src/Mkvtree/mkvinput.c:273-309, src/kurtz/reverse.c:9-70, src/Mkvtree/mkvtree.c:143-161
+ *
+ * Not supported (reported as errors): -q, -maxdepth, GenBank/EMBL/SwissProt input,
  * input without one of -dna/-protein/-smap.
  */
 #define _GNU_SOURCE
@@ -312,7 +314,7 @@ static int parseoptions(Options *o, int argc, char **argv)
   }
   /* what this build does not do (see the header comment) */
   {
-    static const int unsupported[] = {OPTQ, OPTREV, OPTCPL, OPTMAXDEPTH};
+    static const int unsupported[] = {OPTQ, OPTMAXDEPTH};
     for (size_t i = 0; i < sizeof unsupported / sizeof unsupported[0]; i++)
     {
       if (o->isset[unsupported[i]])
@@ -345,6 +347,81 @@ static int parseoptions(Options *o, int argc, char **argv)
       return -2;
     }
     strcpy(o->indexname, base);
+  }
+  if ((o->demand & OUTPUTTABS) && (o->isset[OPTREV] || o->isset[OPTCPL]))
+  {
+    /* addindexsuffix, src/Mkvtree/mkvtree.c:143-161: the index of a transformed sequence gets its own name */
+    const char *suffix = o->isset[OPTREV] ? (o->isset[OPTCPL] ? ".rcp" : ".rev") : ".cpl";
+    if (strlen(o->indexname) + strlen(suffix) > PATH_MAX)
+    {
+      fail("string \"%s\" is too long, cannot copy", o->indexname);
+      return -2;
+    }
+    strcat(o->indexname, suffix);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* -rev / -cpl: the TRANSFORMED sequence (and nothing else: .ois, .des, .sds, .ssp and the counts of the project file
+   describe the sequence as it was read) is reversed and/or complemented in place, separators and wildcards included
+   (src/Mkvtree/mkvinput.c:273-309, src/kurtz/reverse.c:9-70).  Complement: code c of 0..3 becomes 3 - c, specials
+   stay; any other code is an error. */
+static int complementcode(uint8_t cc, uint8_t *out)
+{
+  if (ISSPECIAL(cc))
+  {
+    *out = cc;
+    return 0;
+  }
+  if (cc > 3)
+  {
+    return fail("complement of %lu undefined", (unsigned long) cc);
+  }
+  *out = (uint8_t) (3 - cc);
+  return 0;
+}
+
+static int transformsequence(uint8_t *seq, uint64_t len, int rev, int cpl)
+{
+  if (len == 0)
+  {
+    return 0;
+  }
+  if (rev && cpl)
+  {
+    uint8_t *front = seq, *back = seq + len - 1;
+    say("reverse complement sequence");
+    for (; front <= back; front++, back--)
+    {
+      uint8_t tmp = 0, other = 0;
+      if (complementcode(*front, &tmp) != 0 || complementcode(*back, &other) != 0)
+      {
+        return -1;
+      }
+      *front = other;
+      *back = tmp;
+    }
+  } else if (rev)
+  {
+    uint8_t *front = seq, *back = seq + len - 1;
+    say("reverse sequence");
+    for (; front < back; front++, back--)
+    {
+      const uint8_t tmp = *front;
+      *front = *back;
+      *back = tmp;
+    }
+  } else if (cpl)
+  {
+    say("complement sequence");
+    for (uint64_t i = 0; i < len; i++)
+    {
+      if (complementcode(seq[i], &seq[i]) != 0)
+      {
+        return -1;
+      }
+    }
   }
   return 0;
 }
@@ -1163,6 +1240,10 @@ int main(int argc, char **argv)
   if (ms.totallength == 0)
   {
     fail("input sequences are all empty");
+    goto failure;
+  }
+  if (transformsequence(ms.tis, ms.totallength, opt.isset[OPTREV], opt.isset[OPTCPL]) != 0)
+  {
     goto failure;
   }
   numofchars = alpha.mapsize - 1;
