@@ -122,6 +122,34 @@ def test_reverse_of_protein(tmp_path):
     compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-rev", "-v"])
 
 
+QUERY = b">q1 query\nGGGTTTACGTNNAC\n>q2\nACNNA\n>q3 last\nTTTTACGT\n"
+
+
+@needs_ref
+@pytest.mark.parametrize("args", [
+    ["-db", "in.fna", "-q", "q.fna", "-dna", "-tis", "-ois", "-indexname", "both", "-v"],
+    ["-q", "q.fna", "q2.fna", "-db", "in.fna", "b.fna", "-dna", "-tis", "-ois", "-pl", "-indexname", "both", "-v"],
+    ["-db", "in.fna", "-q", "q.fna", "-dna", "-tis", "-rev", "-indexname", "both"],
+])
+def test_query_files_follow_the_database_files(tmp_path, args):
+    """-q: the query sequences are appended behind the database sequences; the project file names the files
+    `queryfile=` and splits numofsequences (src/Mkvtree/mkvtree.c:438-452,502-515; mkvprocess.c:403-503)."""
+    ra, rb = compare(tmp_path, {"in.fna": DNA, "q.fna": QUERY, "q2.fna": b">only\nACGTACGTTT\n",
+                                "b.fna": b">b1\nTTGGCCAA\n>b2\nNNNACGT\n"}, args)
+    prj = [v for k, v in rb[3].items() if k.endswith(".prj")][0].decode()
+    assert "queryfile=" in prj and "numofquerysequences=0" not in prj
+
+
+@needs_ref
+@pytest.mark.parametrize("args", [
+    ["-q", "q.fna", "-dna", "-tis"],                               # no database file
+    ["-db", "in.fna", "-q", "q.fna", "-dna", "-tis"],              # several files need -indexname
+    ["-db", "in.fna", "-q", "-dna", "-tis", "-indexname", "x"],    # -q without a file
+])
+def test_query_option_errors(tmp_path, args):
+    compare(tmp_path, {"in.fna": DNA, "q.fna": QUERY}, args, expect_rc=None)
+
+
 @needs_ref
 def test_host_tables_protein(tmp_path):
     compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-pl", "1", "-v"])
@@ -242,6 +270,14 @@ def test_host_tables_on_reference_fixtures(tmp_path, refdata):
 ])
 def test_full_cli_small(tmp_path, args, data):
     compare(tmp_path, {"in.fna": data}, args)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_full_cli_query_files(tmp_path):
+    compare(tmp_path, {"in.fna": DNA, "q.fna": QUERY},
+            ["-db", "in.fna", "-q", "q.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-ois",
+             "-indexname", "dbq", "-v"])
 
 
 @needs_ref

@@ -13,7 +13,7 @@
  *
  *   -rev / -cpl           src/Mkvtree/mkvinput.c:273-309, src/kurtz/reverse.c:9-70, src/Mkvtree/mkvtree.c:143-161
  *
- * Not supported (reported as errors): -q, -maxdepth, GenBank/EMBL/SwissProt input,
+ * Not supported (reported as errors): -maxdepth, GenBank/EMBL/SwissProt input,
  * input without one of -dna/-protein/-smap.
  */
 #define _GNU_SOURCE
@@ -99,8 +99,10 @@ typedef struct
   uint32_t demand;
   uint32_t prefixlength;
   const char *smapfile;
-  const char *files[MAXNUMBEROFFILES];
-  unsigned numoffiles;
+  const char *files[MAXNUMBEROFFILES];   /* database files, then query files (option -q) */
+  unsigned numoffiles;                   /* all of them */
+  unsigned numofqueryfiles;
+  const char *queryfiles[MAXNUMBEROFFILES];
   char indexname[PATH_MAX + 1];
 } Options;
 
@@ -275,6 +277,14 @@ static int parseoptions(Options *o, int argc, char **argv)
           {
             o->numoffiles++;
           }
+          if (opt == OPTQ && o->numofqueryfiles < MAXNUMBEROFFILES)
+          {
+            o->queryfiles[o->numofqueryfiles] = argv[argnum];
+          }
+          if (opt == OPTQ)
+          {
+            o->numofqueryfiles++;
+          }
           argnum++;
         }
         break;
@@ -307,14 +317,20 @@ static int parseoptions(Options *o, int argc, char **argv)
     fail("option %s is mandatory", optname[OPTDB]);
     return -2;
   }
-  if (o->numoffiles >= MAXNUMBEROFFILES)
+  if (o->numoffiles + o->numofqueryfiles >= MAXNUMBEROFFILES)
   {
     fail("too many input files, maximum is %lu", (unsigned long) MAXNUMBEROFFILES);
     return -2;
   }
+  /* the query files follow the database files (src/Mkvtree/mkvtree.c:502-515); from here on they are input files
+     like the others, only the project file tells them apart */
+  for (unsigned i = 0; i < o->numofqueryfiles; i++)
+  {
+    o->files[o->numoffiles++] = o->queryfiles[i];
+  }
   /* what this build does not do (see the header comment) */
   {
-    static const int unsupported[] = {OPTQ, OPTMAXDEPTH};
+    static const int unsupported[] = {OPTMAXDEPTH};
     for (size_t i = 0; i < sizeof unsupported / sizeof unsupported[0]; i++)
     {
       if (o->isset[unsupported[i]])
@@ -1447,7 +1463,8 @@ int main(int argc, char **argv)
     }
     for (unsigned f = 0; f < opt.numoffiles; f++)
     {
-      fprintf(fp, "dbfile=%s %lu ", opt.files[f], (unsigned long) ms.filelength[f]);
+      fprintf(fp, "%s=%s %lu ", f < opt.numoffiles - opt.numofqueryfiles ? "dbfile" : "queryfile", opt.files[f],
+              (unsigned long) ms.filelength[f]);
       if (f == opt.numoffiles - 1)
       {
         fprintf(fp, "%lu\n", (unsigned long) (ms.totallength - startseq));
@@ -1463,8 +1480,22 @@ int main(int argc, char **argv)
     fprintf(fp, "lengthofspecialprefix=%lu\n", (unsigned long) ms.lengthofspecialprefix);
     fprintf(fp, "lengthofspecialsuffix=%lu\n", (unsigned long) ms.lengthofspecialsuffix);
     fprintf(fp, "numofsequences=%lu\n", (unsigned long) ms.numofsequences);
-    fprintf(fp, "numofdbsequences=%lu\n", (unsigned long) ms.numofsequences);
-    fprintf(fp, "numofquerysequences=0\n");
+    {
+      /* the sequences in front of the separator that ends the last database file are database sequences */
+      uint64_t numofdbsequences = ms.numofsequences;
+      if (opt.numofqueryfiles > 0)
+      {
+        const uint64_t lastdbsep = ms.filesep[opt.numoffiles - opt.numofqueryfiles - 1];
+        numofdbsequences = 0;
+        while (numofdbsequences + 1 < ms.numofsequences && ms.markpos[numofdbsequences] < lastdbsep)
+        {
+          numofdbsequences++;
+        }
+        numofdbsequences++;
+      }
+      fprintf(fp, "numofdbsequences=%lu\n", (unsigned long) numofdbsequences);
+      fprintf(fp, "numofquerysequences=%lu\n", (unsigned long) (ms.numofsequences - numofdbsequences));
+    }
     if (dosort)
     {
       fprintf(fp, "longest=%lu\n", (unsigned long) res.longest);
