@@ -150,6 +150,55 @@ def test_query_option_errors(tmp_path, args):
     compare(tmp_path, {"in.fna": DNA, "q.fna": QUERY}, args, expect_rc=None)
 
 
+EMBL = (b"ID   AB000001   standard; DNA; FUN; 60 BP.\nXX\nAC   AB000001;\nXX\n"
+        b"DE   Made-up spacer sequence one, partial\nDE   second description line.\nXX\n"
+        b"SQ   Sequence 60 BP; 15 A; 15 C; 15 G; 15 T; 0 other;\n"
+        b"     acgtacgtac gtacgtacgn nacgtacgta cgtacgtacg tacgtacgta cgtacgtacg        60\n//\n"
+        b"ID   AB000002   standard; DNA; FUN; 24 BP.\nXX\nDE   Second record\nXX\n"
+        b"SQ   Sequence 24 BP;\n     ttttggggcc ccaaaarykm acgt        24\n//\n")
+GENBANK = (b"LOCUS       TST00001      48 bp    DNA             PLN       01-JAN-2000\n"
+           b"DEFINITION  Synthetic test locus one,\n            continued.\nACCESSION   TST00001\n"
+           b"ORIGIN      \n        1 acgtacgtnn acgtacgtac gtacgtacgt acgtacgtac gtacgtac\n//\n"
+           b"LOCUS       TST00002      20 bp    DNA             PLN       01-JAN-2000\n"
+           b"DEFINITION  Locus two.\nORIGIN\n        1 ggggccccaa aattttacgt\n//\n")
+SWISS = (b"ID   TEST_HUMAN     STANDARD;      PRT;    30 AA.\nAC   P00001;\n"
+         b"DE   MADE-UP PROTEIN (TEST).\nSQ   SEQUENCE   30 AA;  3000 MW;  ABCDEF CRC32;\n"
+         b"     MKVLAAGIVG LLLAQWERTY PLKHGFDSAC\n//\n")
+
+
+@needs_ref
+@pytest.mark.parametrize("name,data,flag", [("e.embl", EMBL, "-dna"), ("g.gb", GENBANK, "-dna"),
+                                            ("s.sp", SWISS, "-protein")])
+def test_flat_file_formats(tmp_path, name, data, flag):
+    """GenBank, EMBL and SwissProt records are read as FASTA records ">ID description" (parsemultiform.c:225-385)."""
+    compare(tmp_path, {name: data}, ["-db", name, flag, "-tis", "-ois", "-pl", "-v"])
+    (tmp_path / "gz").mkdir()
+    compare(tmp_path / "gz", {name + ".gz": gzip.compress(data)}, ["-db", name + ".gz", flag, "-tis", "-ois"])
+
+
+@needs_ref
+@pytest.mark.parametrize("data", [
+    EMBL.replace(b"60 BP.\n", b"60 BASES\n", 1),                      # first line does not tell the type
+    EMBL.replace(b"\nDE   ", b"\nDX   "),                              # no description key
+    EMBL.replace(b"\nSQ   ", b"\nSX   "),                              # no sequence key
+    GENBANK.replace(b"\nORIGIN", b"\nORIGEN"),
+    GENBANK.replace(b"\n//\n", b"\n/ \n", 1),                         # no second slash
+    b"\n \n" + GENBANK, b" " + EMBL, b"\t\n" + GENBANK,              # a flat file has to start with its key
+])
+def test_flat_file_errors(tmp_path, data):
+    compare(tmp_path, {"x.txt": data}, ["-db", "x.txt", "-dna", "-tis"], expect_rc=1)
+
+
+@needs_ref
+@pytest.mark.parametrize("fixture", ["Emblfile", "GenBankfile", "Emblfile.gz", "GenBankfile.gz"])
+def test_flat_file_fixtures_of_the_reference(tmp_path, fixture):
+    path = os.path.join("/root/reference/src/Mkvtree/DATA", fixture)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    with open(path, "rb") as f:
+        compare(tmp_path, {fixture: f.read()}, ["-db", fixture, "-dna", "-tis", "-ois", "-v"])
+
+
 @needs_ref
 def test_host_tables_protein(tmp_path):
     compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-pl", "1", "-v"])

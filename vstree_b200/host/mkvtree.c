@@ -13,8 +13,9 @@
  *
  *   -rev / -cpl           src/Mkvtree/mkvinput.c:273-309, src/kurtz/reverse.c:9-70, src/Mkvtree/mkvtree.c:143-161
  *
- * Not supported (reported as errors): -maxdepth, GenBank/EMBL/SwissProt input,
- * input without one of -dna/-protein/-smap.
+ *   GenBank/EMBL/SwissProt  src/kurtz-basic/parsemultiform.c:225-385 (single input file)
+ *
+ * Not supported (reported as errors): -maxdepth, input without one of -dna/-protein/-smap.
  */
 #define _GNU_SOURCE
 #include <ctype.h>
@@ -1054,6 +1055,105 @@ static int parseplain(Multiseq *ms, const Alphabet *alpha, const uint8_t *input,
 /* ------------------------------------------------------------------------------------------------------ */
 /* output */
 
+/* ------------------------------------------------------------------------------------------------------ */
+/* GenBank, EMBL and SwissProt flat files (src/kurtz-basic/parsemultiform.c:225-385): every record becomes a FASTA
+   record ">ID DEFINITION-line\nSEQUENCE\n", and the FASTA reader takes it from there.
+   A record starts with `first` ("LOCUS" / "ID   "), its identifier is the next blank-delimited word, its description
+   the rest of the first line that starts with `second` ("\nDEFINITION" / "\nDE   "), its sequence everything behind
+   the line of `third` ("\nORIGIN" / "\nSQ   ") up to "//" without blanks, newlines and digits.
+   Returns the length of the FASTA text in `out`, 0 when the buffer does not start with `first`, -1 on error. */
+static const uint8_t *findbytes(const uint8_t *text, uint64_t textlen, const char *pattern)
+{
+  const size_t plen = strlen(pattern);
+  if (plen == 0 || textlen < plen)
+  {
+    return NULL;
+  }
+  return (const uint8_t *) memmem(text, textlen, pattern, plen);
+}
+
+static int64_t flatfiletofasta(uint8_t *out, const uint8_t *db, uint64_t dblen, int checktype, const char *first,
+                               const char *second, const char *third)
+{
+  const uint8_t *end = db + dblen, *rec = db;
+  const size_t firstlen = strlen(first);
+  uint64_t written = 0;
+  while (rec < end)
+  {
+    const uint8_t *p, *q;
+    if ((uint64_t) (end - rec) < firstlen || memcmp(rec, first, firstlen) != 0)
+    {
+      return 0;  /* (also when a later record does not start with the key: the reference gives up on the format) */
+    }
+    if (checktype)
+    {
+      /* EMBL ("... BP.") or SwissProt ("... AA."): the first line tells, and must */
+      for (p = rec; p < end && *p != '\n'; p++)
+      {
+      }
+      if (p - rec < 3 || p[-1] != '.'
+          || !((tolower(p[-3]) == 'b' && tolower(p[-2]) == 'p') || (tolower(p[-3]) == 'a' && tolower(p[-2]) == 'a')))
+      {
+        fail("cannot detect sequence type:  first line must end with \"aa.\" or \"bp.\" in lower or upper case");
+        return -1;
+      }
+    }
+    for (p = rec + firstlen; p < end && isspace(*p); p++)  /* the identifier */
+    {
+    }
+    q = findbytes(rec, (uint64_t) (end - rec), second);
+    if (q == NULL)
+    {
+      fail("missing \"%s\" in database file", second);
+      return -1;
+    }
+    for (q += strlen(second); q < end && *q == ' '; q++)
+    {
+    }
+    out[written++] = '>';
+    for (; p < end && !isspace(*p); p++)
+    {
+      out[written++] = *p;
+    }
+    out[written++] = ' ';
+    for (p = q; p < end && *p != '\n'; p++)
+    {
+      out[written++] = *p;
+    }
+    out[written++] = '\n';
+    q = findbytes(q, (uint64_t) (end - q), third);
+    if (q == NULL)
+    {
+      fail("missing \"%s\" in GenBank file", third);
+      return -1;
+    }
+    for (q += strlen(third); q < end && *q != '\n'; q++)  /* the rest of the key's line */
+    {
+    }
+    for (; q < end && *q != '/'; q++)
+    {
+      if (*q != ' ' && *q != '\n' && !isdigit(*q))
+      {
+        out[written++] = *q;
+      }
+    }
+    out[written++] = '\n';
+    if (q + 1 >= end || q[1] != '/')
+    {
+      fail("input sequence does no contain second '/'");
+      return -1;
+    }
+    for (; q < end && *q != '\n'; q++)
+    {
+    }
+    for (q = q < end ? q + 1 : end; q < end && isspace(*q); q++)
+    {
+    }
+    rec = q;
+  }
+  return (int64_t) written;
+}
+
 static const char *tabsuffixes[] = {"tis", "ois", "des", "ssp", "bwt", "suf", "lcp", "bck", "sti1", "skp", "cld", "cld1",
                                     "iso", "sti", "cfr", "crf", "lsf", "sds", "llv", "al1", "al2", "prj"};
 
@@ -1241,16 +1341,43 @@ int main(int argc, char **argv)
     {
       goto failure;
     }
-  } else if (rawlen - skip >= 5 && (memcmp(raw + skip, "LOCUS", 5) == 0 || memcmp(raw + skip, "ID   ", 5) == 0))
-  {
-    fail("GenBank/EMBL/SwissProt input is not supported by the GPU build of mkvtree; convert it to FASTA");
-    goto failure;
   } else
   {
-    if (parseplain(&ms, &alpha, raw, rawlen, (opt.demand & ESA_OISTAB) != 0) != 0)
+    /* A flat file has to start with its key: behind leading white space the reference recognises neither format
+       properly (EMBL is looked for at the very start of the file, a GenBank conversion is read from the very start,
+       src/kurtz-basic/parsemultiform.c:352-385, mkvinput.c:232-256) and ends up rejecting the white space like the
+       plain reader below does.  Several input files are FASTA or plain. */
+    uint8_t *fasta = NULL;
+    int64_t flen = 0;
+    if (opt.numoffiles == 1 && rawlen > 0 && skip == 0)
+    {
+      fasta = malloc(rawlen + 16);
+      if (fasta == NULL)
+      {
+        fail("not enough memory for %lu bytes", (unsigned long) rawlen);
+        goto failure;
+      }
+      flen = flatfiletofasta(fasta, raw + skip, rawlen - skip, 0, "LOCUS", "\nDEFINITION", "\nORIGIN");
+      if (flen == 0)
+      {
+        flen = flatfiletofasta(fasta, raw, rawlen, 1, "ID   ", "\nDE   ", "\nSQ   ");
+      }
+      if (flen < 0)
+      {
+        goto failure;
+      }
+    }
+    if (flen > 0)
+    {
+      if (parsefasta(&ms, &alpha, &opt, fasta, (uint64_t) flen, concatfilesep, (opt.demand & ESA_OISTAB) != 0) != 0)
+      {
+        goto failure;
+      }
+    } else if (parseplain(&ms, &alpha, raw, rawlen, (opt.demand & ESA_OISTAB) != 0) != 0)
     {
       goto failure;
     }
+    free(fasta);
   }
   free(raw);
   if (ms.totallength == 0)
