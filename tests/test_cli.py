@@ -199,6 +199,33 @@ def test_flat_file_fixtures_of_the_reference(tmp_path, fixture):
         compare(tmp_path, {fixture: f.read()}, ["-db", fixture, "-dna", "-tis", "-ois", "-v"])
 
 
+TEXT = b"Hello World xyz abcabcabc, said the text; and the text said hello again.\n"
+
+
+@needs_ref
+@pytest.mark.parametrize("data,args", [
+    (TEXT, ["-tis", "-ois", "-v"]),                       # no alphabet option, no -pl: the bytes themselves
+    (TEXT, ["-tis", "-ois", "-pl", "1", "-v"]),           # bytes numbered in byte order, .al2
+    (TEXT, ["-tis", "-pl", "2", "-indexname", "t"]),
+    (bytes([65, 66, 255, 65, 254, 66, 0, 1, 65]), ["-tis", "-pl", "1", "-v"]),
+    (bytes([65, 66, 255, 65, 254, 66, 0, 1, 65]), ["-tis", "-v"]),
+    (TEXT, ["-tis", "-pl", "-v"]),                        # error: -pl needs a number when the alphabet is unknown
+    (TEXT, ["-tis", "-pl", "9"]),                         # error: too large for this text and alphabet
+    (DNA, ["-tis", "-v"]),                                # error: FASTA needs an alphabet option
+    (EMBL, ["-tis"]), (GENBANK, ["-tis"]),
+])
+def test_without_alphabet_option(tmp_path, data, args):
+    """No -dna/-protein/-smap: plain text whose alphabet is the set of its bytes (src/Mkvtree/mkvinput.c:100-170,
+    findalphabet alphabet.c:456-487, .al2 mkvprocess.c:554-577)."""
+    compare(tmp_path, {"p.txt": data}, ["-db", "p.txt"] + args, expect_rc=None)
+
+
+@needs_ref
+def test_without_alphabet_option_several_files(tmp_path):
+    compare(tmp_path, {"a.txt": TEXT, "b.txt": TEXT}, ["-db", "a.txt", "b.txt", "-tis", "-indexname", "x"],
+            expect_rc=1)
+
+
 @needs_ref
 def test_host_tables_protein(tmp_path):
     compare(tmp_path, {"in.faa": PROT}, ["-db", "in.faa", "-protein", "-tis", "-ois", "-pl", "1", "-v"])
@@ -319,6 +346,19 @@ def test_host_tables_on_reference_fixtures(tmp_path, refdata):
 ])
 def test_full_cli_small(tmp_path, args, data):
     compare(tmp_path, {"in.fna": data}, args)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("data,args", [
+    (TEXT * 3, ["-pl", "1", "-suf", "-lcp", "-bwt", "-bck", "-sti1", "-tis", "-v"]),
+    (TEXT * 60, ["-pl", "2", "-allout", "-v"]),
+    (TEXT * 3, ["-suf", "-lcp", "-bwt", "-tis", "-v"]),                                   # raw bytes, one global sort
+    (bytes([65, 66, 255, 65, 254, 66, 0, 1, 65, 66, 65]) * 5, ["-pl", "1", "-suf", "-lcp", "-bwt", "-tis"]),
+    (bytes([65, 66, 255, 65, 254, 66, 0, 1, 65, 66, 65]) * 5, ["-suf", "-lcp", "-bwt", "-tis"]),  # all bytes are letters here too
+])
+def test_full_cli_without_alphabet_option(tmp_path, data, args):
+    compare(tmp_path, {"p.txt": data}, ["-db", "p.txt"] + args)
 
 
 @needs_ref

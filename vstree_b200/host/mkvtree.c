@@ -15,7 +15,9 @@
  *
  *   GenBank/EMBL/SwissProt  src/kurtz-basic/parsemultiform.c:225-385 (single input file)
  *
- * Not supported (reported as errors): -maxdepth, input without one of -dna/-protein/-smap.
+ *   no alphabet option      src/Mkvtree/mkvinput.c:100-170, findalphabet src/kurtz-basic/alphabet.c:456-487, .al2
+ *
+ * Not supported (reported as an error): -maxdepth.
  */
 #define _GNU_SOURCE
 #include <ctype.h>
@@ -452,6 +454,8 @@ typedef struct
   unsigned char mapdomain[UCHAR_MAX + 1];
   unsigned char characters[UCHAR_MAX + 1];
   unsigned domainsize, mapsize;
+  int fromtext;  /* no -dna/-protein/-smap: the alphabet is the set of bytes of the (plain) input, findalphabet,
+                    src/kurtz-basic/alphabet.c:456-487; there are no wildcards then, mapsize = alphabet size */
 } Alphabet;
 
 static void assign_builtin(Alphabet *a, const char *letters, int pairs, const char *wildcards, const char *domain)
@@ -640,13 +644,38 @@ static int make_alphabet(Alphabet *a, const Options *o)
   {
     return read_symbolmap(a, o->smapfile);
   }
-  return fail("input requires one of the options -smap, -dna, or -protein");
+  a->fromtext = 1;  /* plain input only; decided when the input has been read (mkvinput.c:100-170) */
+  return 0;
 }
 
 static void verbosealphabet(const Alphabet *a)
 {
   if (!verbose)
   {
+    return;
+  }
+  if (a->fromtext)
+  {
+    /* the reference prints this alphabet through the arrays of a symbol-map alphabet it never filled: the domain is
+       all zero bytes, and the place of the last character shows the (unset) wildcard character */
+    printf("alphabet \"");
+    for (unsigned i = 0; i < a->mapsize; i++)
+    {
+      printf("\\0");
+    }
+    printf("\" (size %lu) mapped to \"", (unsigned long) a->mapsize);
+    for (unsigned i = 0; i + 1 < a->mapsize; i++)
+    {
+      unsigned char c = a->characters[i];
+      if (isprint(c) && !isspace(c))
+      {
+        putchar(c);
+      } else
+      {
+        printf("\\%lu", (unsigned long) c);
+      }
+    }
+    printf("\\0\" (size %lu)\n", (unsigned long) a->mapsize);
     return;
   }
   printf("alphabet \"");
@@ -682,6 +711,7 @@ static void verbosealphabet(const Alphabet *a)
 typedef struct
 {
   uint8_t *tis, *ois;            /* transformed / original sequence, totallength bytes */
+  uint8_t *sortseq;              /* what the sorter gets when that is not tis (raw text without an alphabet) */
   uint64_t totallength;
   uint8_t *desc;                 /* descriptions, each ending in '\n' */
   uint64_t desclen;
@@ -1052,6 +1082,57 @@ static int parseplain(Multiseq *ms, const Alphabet *alpha, const uint8_t *input,
   return 0;  /* the reference leaves the special statistics of plain input at zero */
 }
 
+/* Plain text without an alphabet option: every byte value is a letter, 254 and 255 included (the reference sorts such
+   input with its sorter for sequences without special symbols).  mapped: the bytes are replaced by their rank among
+   the bytes that occur.  Otherwise the table holds the bytes themselves and ms->sortseq the ranked copy for the
+   sorter (the order of the suffixes is the same). */
+static int parsetext(Multiseq *ms, Alphabet *alpha, const uint8_t *input, uint64_t inputlen, int mapped)
+{
+  int occurs[UCHAR_MAX + 1] = {0};
+  uint8_t rank[UCHAR_MAX + 1];
+  ms->tis = malloc(inputlen + 1);
+  if (ms->tis == NULL)
+  {
+    return fail("not enough memory for the sequence");
+  }
+  ms->numofsequences = 1;
+  ms->totallength = inputlen;
+  for (uint64_t i = 0; i < inputlen; i++)
+  {
+    occurs[input[i]] = 1;
+  }
+  alpha->mapsize = 0;
+  for (unsigned c = 0; c <= UCHAR_MAX; c++)
+  {
+    rank[c] = 0;
+    if (occurs[c])
+    {
+      alpha->characters[alpha->mapsize] = (unsigned char) c;
+      rank[c] = (uint8_t) alpha->mapsize++;
+    }
+  }
+  alpha->domainsize = alpha->mapsize;
+  if (mapped)
+  {
+    for (uint64_t i = 0; i < inputlen; i++)
+    {
+      ms->tis[i] = rank[input[i]];
+    }
+    return 0;
+  }
+  memcpy(ms->tis, input, inputlen);
+  ms->sortseq = malloc(inputlen + 1);
+  if (ms->sortseq == NULL)
+  {
+    return fail("not enough memory for the sequence");
+  }
+  for (uint64_t i = 0; i < inputlen; i++)
+  {
+    ms->sortseq[i] = rank[input[i]];
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* output */
 
@@ -1313,6 +1394,11 @@ int main(int argc, char **argv)
   }
   memset(&ms, 0, sizeof ms);
   memset(concatfilesep, 0, sizeof concatfilesep);
+  if (alpha.fromtext && opt.numoffiles > 1)
+  {
+    fail("multiple input files require one of the options -smap, -dna, or -protein");
+    goto failure;
+  }
   if (opt.numoffiles == 1)
   {
     raw = readwholefile(opt.files[0], &rawlen);
@@ -1333,7 +1419,26 @@ int main(int argc, char **argv)
   for (skip = 0; skip < rawlen && isspace(raw[skip]); skip++)
   {
   }
-  if (skip < rawlen && raw[skip] == '>')
+  if (alpha.fromtext)
+  {
+    /* no alphabet option: plain text only; with a prefix length its bytes are numbered in byte order (.al2), without
+       one they are sorted as they are (src/Mkvtree/mkvinput.c:100-170) */
+    if ((skip < rawlen && raw[skip] == '>') || (rawlen - skip >= 5 && memcmp(raw + skip, "LOCUS", 5) == 0)
+        || (rawlen >= 5 && memcmp(raw, "ID   ", 5) == 0))
+    {
+      fail("fasta, EMBL, and GenBank format requires one of the options -smap, -dna, or -protein");
+      goto failure;
+    }
+    if (opt.prefixlength == AUTOPREFIXLENGTH)
+    {
+      fail("option -pl requires positive integer as parameter since alphabet size is unknown");
+      goto failure;
+    }
+    if (parsetext(&ms, &alpha, raw, rawlen, opt.prefixlength > 0) != 0)
+    {
+      goto failure;
+    }
+  } else if (skip < rawlen && raw[skip] == '>')
   {
     /* the separator offsets of concatenated files refer to the unskipped buffer, but a concatenation never
        starts with white space */
@@ -1389,7 +1494,7 @@ int main(int argc, char **argv)
   {
     goto failure;
   }
-  numofchars = alpha.mapsize - 1;
+  numofchars = alpha.fromtext ? alpha.mapsize : alpha.mapsize - 1;
   k = opt.prefixlength;
   if (k == AUTOPREFIXLENGTH)
   {
@@ -1496,7 +1601,7 @@ int main(int argc, char **argv)
           fail("%s", err);
           goto failure;
         }
-        jobs[r].tis = ms.tis;
+        jobs[r].tis = ms.sortseq != NULL ? ms.sortseq : ms.tis;
         jobs[r].n = ms.totallength;
         jobs[r].numofchars = numofchars;
         jobs[r].prefixlength = k;
@@ -1537,6 +1642,21 @@ int main(int argc, char **argv)
         {
           fail("%s", jobs[r].err);
           goto failure;
+        }
+      }
+      if (ms.sortseq != NULL)
+      {
+        /* raw text without an alphabet: the sorter saw ranked bytes, the Burrows-Wheeler table holds text bytes */
+        for (r = 0; r < njobs; r++)
+        {
+          uint8_t *bwt = jobs[r].res.bwttab;
+          for (uint64_t i = 0; bwt != NULL && i < jobs[r].res.shard_count; i++)
+          {
+            if (bwt[i] < ESA_UNDEFBWTCHAR)
+            {
+              bwt[i] = alpha.characters[bwt[i]];
+            }
+          }
         }
       }
       ctx = jobs[0].ctx;
@@ -1642,6 +1762,23 @@ int main(int argc, char **argv)
       fail("cannot close file \"%s.prj\"", opt.indexname);
       goto failure;
     }
+    if (alpha.fromtext)
+    {
+      /* .al2: the size of the alphabet in one byte, then its characters (src/Mkvtree/mkvprocess.c:554-577); no
+         alphabet file at all without a prefix length */
+      if (k > 0)
+      {
+        fp = openthefile(opt.indexname, "al2", 1);
+        if (fp == NULL)
+        {
+          goto failure;
+        }
+        putc((int) (alpha.mapsize & 0xffu), fp);
+        fwrite(alpha.characters, 1, alpha.mapsize, fp);
+        fclose(fp);
+      }
+      goto alphabetwritten;
+    }
     fp = openthefile(opt.indexname, "al1", 1);
     if (fp == NULL)
     {
@@ -1668,6 +1805,7 @@ int main(int argc, char **argv)
       fputs("L\nV\nI\nF\nK\nR\nE\nD\nA\nG\nS\nT\nN\nQ\nY\nW\nP\nH\nM\nC\nXUBZ*-\n", fp);
     }
     fclose(fp);
+alphabetwritten:;
   }
   /* makeskptab runs last in the reference (src/Mkvtree/mkvprocess.c:767-815, called at :1075 after the project
      and alphabet files are out), so the -v transcript names .skp last */
