@@ -889,14 +889,55 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
   uint64_t out = 0, linenum = 1, desccap = 0, sdcap = 0, sdcnt = 0, mpcap = 0, mpcnt = 0;
   unsigned sepnum = 0;
   int indesc = 0, lastwasspecial = 0;
+  uint8_t letter[UCHAR_MAX + 1];  /* code of an ordinary letter, 255 for everything that needs a closer look */
+  uint8_t *ois = NULL;
   ms->tis = malloc(inputlen + 1);
   if (ms->tis == NULL)
   {
     return fail("not enough memory for the sequence");
   }
+  if (wantois)
+  {
+    /* the original sequence has an entry wherever the transformed one has: both are written in the same sweep */
+    ois = ms->ois = malloc(inputlen + 1);
+    if (ois == NULL)
+    {
+      return fail("not enough memory for the original sequence");
+    }
+  }
+  for (unsigned c = 0; c <= UCHAR_MAX; c++)
+  {
+    const unsigned acode = alpha->symbolmap[c];
+    letter[c] = (c != '>' && !isspace((int) c) && acode != UNDEFCHAR && !ISSPECIAL(acode)) ? (uint8_t) acode : 255;
+  }
   for (uint64_t i = 0; i < inputlen; i++)
   {
     const uint8_t current = input[i];
+    if (!indesc && letter[current] != 255)
+    {
+      /* a run of ordinary letters (the bulk of any input) */
+      uint8_t *t = ms->tis + out;
+      uint64_t j = i;
+      if (ois != NULL)
+      {
+        uint8_t *q = ois + out;
+        for (; j < inputlen && letter[input[j]] != 255; j++)
+        {
+          *t++ = letter[input[j]];
+          *q++ = input[j];
+        }
+      } else
+      {
+        for (; j < inputlen && letter[input[j]] != 255; j++)
+        {
+          *t++ = letter[input[j]];
+        }
+      }
+      out += j - i;
+      lastwasspecial = 0;
+      i = j - 1;
+      continue;
+    }
     if (indesc)
     {
       PUSH(ms->desc, ms->desclen, desccap, current);
@@ -927,6 +968,10 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
         }
         ms->specialcharacters++;
         lastwasspecial = 1;
+        if (ois != NULL)
+        {
+          ois[out] = SEPARATOR;
+        }
         ms->tis[out++] = SEPARATOR;
       }
       ms->numofsequences++;
@@ -956,6 +1001,10 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
       } else
       {
         lastwasspecial = 0;
+      }
+      if (ois != NULL)
+      {
+        ois[out] = current;
       }
       ms->tis[out++] = (uint8_t) acode;
     }
@@ -997,33 +1046,6 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
     if (ms->markpos[ms->numofsequences - 2] == out - 1)
     {
       return fail("sequence %lu is empty", (unsigned long) (ms->numofsequences - 1));
-    }
-  }
-  if (wantois)
-  {
-    uint64_t q = 0;
-    int d = 0;
-    ms->ois = malloc(out + 1);
-    if (ms->ois == NULL)
-    {
-      return fail("not enough memory for the original sequence");
-    }
-    for (uint64_t i = 0; i < inputlen && q < out; i++)
-    {
-      if (d)
-      {
-        d = input[i] != '\n';
-      } else if (input[i] == '>')
-      {
-        if (i > 0)
-        {
-          ms->ois[q++] = SEPARATOR;
-        }
-        d = 1;
-      } else if (!isspace(input[i]))
-      {
-        ms->ois[q++] = input[i];
-      }
     }
   }
   return 0;
