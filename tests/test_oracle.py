@@ -137,3 +137,51 @@ def test_against_committed_goldens(case):
     assert sha(skp) == case["sha"]["skp"], "skp"
     if "tables" in case:
         assert skp.tolist() == case["tables"]["skp"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_against_reference_on_random_inputs(seed, tmp_path):
+    """Seeded random inputs through the UNMODIFIED reference binary: every alphabet flag, dense and sparse specials,
+    repeats, identical records (ties that only the position of a separator breaks), every prefix length the input
+    admits.  Pins the C restatement where the fixtures and goldens are silent."""
+    if not ou.have_ref():
+        pytest.skip("oracle/_ref/mkvtree.x not built")
+    rng = np.random.default_rng(5000 + seed)
+    kind = ["dna", "protein"][seed % 2]
+    sigma, flag = (4, "-dna") if kind == "dna" else (20, "-protein")
+    n = int(rng.choice([40, 300, 2000, 9000, 40000]))
+    shape = seed % 6
+    if shape == 0:      # identical records
+        rec = rng.integers(0, sigma, size=int(rng.integers(5, 60)), dtype=np.uint8)
+        tis = np.concatenate([np.append(rec, np.uint8(255)) for _ in range(max(2, n // (len(rec) + 1)))])[:-1]
+    elif shape == 1:    # dense specials
+        tis = rng.integers(0, sigma, size=n, dtype=np.uint8)
+        sp = rng.random(n) < 0.25
+        tis[sp] = rng.choice([254, 255], size=int(sp.sum()), p=[0.8, 0.2])
+    elif shape == 2:    # long repeats with a few substitutions
+        base = rng.integers(0, sigma, size=max(8, n // 8), dtype=np.uint8)
+        tis = np.tile(base, 8)[:n].copy()
+        hit = rng.random(len(tis)) < 0.01
+        tis[hit] = rng.integers(0, sigma, size=int(hit.sum()), dtype=np.uint8)
+    elif shape == 3:    # low complexity
+        tis = rng.integers(0, 2, size=n, dtype=np.uint8)
+        tis[rng.random(n) < 0.002] = 255
+    else:               # plain random with sparse wildcards and separators
+        tis = rng.integers(0, sigma, size=n, dtype=np.uint8)
+        sp = rng.random(n) < 0.004
+        tis[sp] = rng.choice([254, 255], size=int(sp.sum()))
+    # no empty records: the reader rejects them
+    tis = tis[np.concatenate([[True], ~((tis[1:] == 255) & (tis[:-1] == 255))])]
+    while len(tis) and tis[0] == 255:
+        tis = tis[1:]
+    while len(tis) and tis[-1] == 255:
+        tis = tis[:-1]
+    if len(tis) < 8:
+        pytest.skip("degenerate input")
+    path = str(tmp_path / "in.fa")
+    with open(path, "wb") as f:
+        f.write(synth.to_fasta(tis, kind))
+    kmax = int(ou.oracle_lib().oracle_maximalprefixlength(sigma, len(tis)))
+    pl = [] if seed % 3 == 0 else [str(int(rng.integers(1, max(1, kmax) + 1)))]
+    ref = _compare_with_reference(path, flag, sigma, pl, tmp_path)
+    assert np.array_equal(ref["tis"], tis)
