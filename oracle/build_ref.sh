@@ -11,7 +11,46 @@ if [ ! -d "$S/Mkvtree" ]; then
   echo "build_ref.sh: reference sources not found at $S (fine on the GPU box: prebuilt oracle/_ref is used)" >&2
   exit 0
 fi
+# The UNMODIFIED vmatch, the consumer of the index (downstream acceptance test: tests/test_zz_vmatch_acceptance.py).
+# Recipe: src/Vmatch/Makefile:38-84 (LIBVMATCHOBJ + vmatch.mn.c), src/Vmengine/Makefile:40-56 and Vmatdef2.mf
+# (vmatfind.c / vmatcount.c once per alphabet size, plus the dynamic and the streaming variant), libmkvtree.
+build_vmatch() {
+  local O="$OUT/objvm"
+  mkdir -p "$O"
+  local CV="$CF -I$S/Vmengine -I$S/Vmatch"
+  local LIST="vmatch parsevm optstring procargs runself runquery mlendistrib mapdemand procmatch queryindex verifysub lrseq echomatch substpos markmat nomatch showmasked vmcluster assigndig explain detmatch opensel vmdbfunc parsedbms chncallparse chainvm chainof initpost matchlenparm xmlfunc vplugin-open vmotif-start cpridx-start parsepp parsequery parsedbcl keepflags parsemcl cluedist matchclust clpos allmclust threadchain procfinal mokay vmatch.mn"
+  ( for f in "$S"/kurtz-basic/*.c; do echo "gcc $CF -c $f -o $O/kb_$(basename "$f" .c).o"; done
+    for f in "$S"/kurtz/*.c;       do echo "gcc $CF -c $f -o $O/k_$(basename "$f" .c).o"; done
+    for f in mkvtree mkvprocess bese ppsort mkvinput cprsuf remainsort; do
+      echo "gcc $CF -DWITHLCP -c $S/Mkvtree/$f.c -o $O/m_$f.o"; done
+    echo "gcc $CF -DWITHLCP -DSPECIAL -c $S/Mkvtree/bese.c -o $O/m_besespecial.o"
+    for f in "$S"/Vmengine/*.c; do b=$(basename "$f" .c)
+      case $b in vmatfind|vmatcount|vmatgen) ;; *) echo "gcc $CV -c $f -o $O/e_$b.o";; esac; done
+    for a in 4 12 21 31 42 53 66; do
+      echo "gcc $CV -DALPHABETSIZE=$a -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind$a.o"
+      echo "gcc $CV -DALPHABETSIZE=$a -c $S/Vmengine/vmatcount.c -o $O/e_vmatcount$a.o"; done
+    echo "gcc $CV -DDYNAMICALPHABET -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind-dyn.o"
+    echo "gcc $CV -DDYNAMICALPHABET -DESASTREAMACCESS -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind-strm.o"
+    for b in $LIST; do echo "gcc $CV -c $S/Vmatch/$b.c -o $O/v_$b.o"; done
+    echo "gcc $CF -c $HERE/stub/bzstub.c -o $O/bzstub.o"
+  ) | xargs -P "$J" -I{} sh -c "{}"
+  ar rcs "$O/libkb.a" "$O"/kb_*.o
+  ar rcs "$O/libk.a" "$O"/k_*.o
+  ar rcs "$O/libm.a" "$O"/m_*.o
+  ar rcs "$O/libe.a" "$O"/e_*.o
+  mv "$O/v_vmatch.mn.o" "$O/main_vmatch.o"
+  ar rcs "$O/libv.a" "$O"/v_*.o
+  local L="$O/libv.a $O/libe.a $O/libm.a $O/libk.a $O/libkb.a"
+  gcc -o "$OUT/vmatch.x" "$O/main_vmatch.o" $L $L "$O/bzstub.o" -lz -lm -ldl -lpthread
+  rm -rf "$O"
+}
+CF="-D_LARGEFILE_SOURCE -D_FILE_OFFSET_BITS=64 -O3 -m64 -fno-stack-protector -U_FORTIFY_SOURCE -D_GNU_SOURCE -DWITHSYSCONF -I$HERE/stub -I$S/include -w"
+J=$(nproc)
 if [ -x "$OUT/mkvtree.x" ] && [ -x "$OUT/mkvtree.dbg.x" ] && [ "${1:-}" != "--force" ]; then
+  if [ ! -x "$OUT/vmatch.x" ]; then
+    mkdir -p "$OUT"
+    build_vmatch || echo "build_ref.sh: vmatch.x could not be built (the acceptance test will be skipped)" >&2
+  fi
   exit 0
 fi
 mkdir -p "$OUT/obj" "$OUT/objdbg"
@@ -37,4 +76,5 @@ build_variant() {   # $1 = objdir, $2 = extra flags, $3 = suffix of binaries
 build_variant "$OUT/obj" "" ".x"
 build_variant "$OUT/objdbg" "-DDEBUG" ".dbg.x"
 rm -rf "$OUT/obj" "$OUT/objdbg"
+build_vmatch || echo "build_ref.sh: vmatch.x could not be built (the acceptance test will be skipped)" >&2
 echo "built: $(ls "$OUT")"
