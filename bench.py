@@ -373,6 +373,18 @@ def main():
         stage = {name: {"launches": v["launches"] // args.steps, "ms": v["ms"] / args.steps,
                         "GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None)}
                  for name, v in kern.items() if v["launches"]}
+        # the whole build against the HBM roofline (north star): the algorithmic bytes of every kernel family of rank 0
+        # (DESIGN.md section 5 lists the per-unit figures) over the step time, against the measured copy peak per GPU
+        try:
+            build_bytes = sum(v["bytes"] for name_, v in kern.items() if name_ not in ("comm",)) / args.steps
+            step_s = dev_ms_max / args.steps * 1e-3
+            build_roofline = {"algorithmic_bytes_per_step_rank0": build_bytes,
+                              "bytes_per_symbol": build_bytes / max(1, last["shard_count"]),
+                              "achieved": build_bytes / step_s / 1e9 if step_s > 0 else None, "peak": peak,
+                              "unit": "GB/s per GPU",
+                              "frac": (build_bytes / step_s / 1e9 / peak) if (peak and step_s > 0) else None}
+        except Exception:  # a report next to the headline, never a reason to lose the line
+            build_roofline = None
         line = {
             "metric": "mkvtree index build throughput (suf+lcp+bwt)",
             "value": n * args.steps / (dev_ms_max * 1e-3) / 1e6,
@@ -403,6 +415,7 @@ def main():
                          "algorithmic_bytes_per_launch": rp["bytes"] / rp["launches"] if rp["launches"] else None,
                          "share_of_step": rp["ms"] / dev_ms if dev_ms else None},
             "stages": stage,
+            "build_roofline": build_roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max, "statistic": "median over steps",
