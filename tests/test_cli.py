@@ -3,7 +3,6 @@ same command line, same files byte for byte, same -v transcript, same error mess
 Cases that only write host-side tables (-tis/-ois) run on the CPU; the others need the GPU."""
 import gzip
 import os
-import re
 import shutil
 import subprocess
 
