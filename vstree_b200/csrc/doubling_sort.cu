@@ -1,6 +1,7 @@
-// doubling_sort.cu -- the sort step of one prefix-doubling round.
+// doubling_sort.cu -- the sort step of one refinement round.
 //
-// Input: the active suffixes in suffix-array order, key = rank(s) << shift | rank(s+h).  Because the list is in
+// Input: the active suffixes in suffix-array order, key = rank(s) << shift | secondary key (rank(s+h) in a doubling
+// round, the code of the next symbols in a text round).  Because the list is in
 // suffix-array order the high key part is already sorted: groups (equal rank(s)) are contiguous, and only the order
 // INSIDE each group is open.  A global LSD radix sort ignores that and pays 7 memory sweeps of 24 bytes per pair for a
 // 54-bit key.  Most groups are small (random DNA: 2-3 suffixes, 50 diverged copies of a repeat: about 50), so:
@@ -13,8 +14,8 @@
 //            the places they came from -- their groups are contiguous and in rank order, so the sorted run fits the
 //            same index set.
 // When more than half of the pairs would spill (huge groups: the first rounds of highly repetitive inputs) the
-// global sort takes everything, as before.  The result equals a sort by the full key up to the order of EQUAL keys,
-// which is immaterial: equal keys stay one group and are ordered by a later round.
+// global sort takes everything, as before.  Every path is STABLE: equal keys keep their order, which is text order
+// from the initial sort on -- the text rounds rely on it (equal keys with a special in their window are final).
 #include "scan.cuh"
 
 namespace

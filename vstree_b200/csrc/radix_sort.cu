@@ -2,14 +2,15 @@
 //
 // This is the dominant kernel family of the suffix sorter (north star: "LSD radix passes ... coalesced,
 // vectorised HBM loads, shared-memory histogramming and warp-shuffle scans").  Structure per sort:
-//   1. radix_hist_kernel   one read of the keys -> histograms of EVERY digit (shared-memory bins, one
-//                          warp-aggregated atomic per distinct digit and warp)
+//   1. radix_hist_kernel   one read of the keys -> histograms of EVERY digit (shared-memory bins, plain atomics:
+//                          ATOMS.POPC.INC counts the lanes of a warp that hit the same bin in one operation)
 //   2. radix_scan_kernel   exclusive scan of each digit histogram -> global bin bases
 //   3. radix_pass_kernel   per digit ONE read + ONE write of the pairs: each 512-thread CTA takes a tile
 //                          (dynamic ticket), ranks its keys with warp match/ballot, learns the number of equal
 //                          digits in all earlier tiles by decoupled look-back over a status array (single 64-bit
 //                          word = 2 flag bits + 62 value bits), reorders the tile in shared memory and writes
-//                          each digit run coalesced.  Stable.
+//                          each digit run coalesced.  Stable.  The pass is bound by instruction issue, not by HBM
+//                          (88 warp instructions per 32 pairs): see DESIGN.md section 5 for what was measured.
 // Algorithmic bytes: hist = n*sizeof(key); pass = 2*n*(sizeof(key)+sizeof(value)).
 #include "scan.cuh"
 

@@ -3,9 +3,9 @@
 // Comparison semantics are the reference's (src/Mkvtree/bese.c:26-55, GETLCP :91-95): letters match by code,
 // a special symbol (254/255, and everything behind position n) matches nothing, so an lcp stops there.
 //   TextBytes   any alphabet: the tis bytes themselves, 8 symbols per 64-bit window.
-//   TextPacked2 alphabets of at most 4 letters (DNA): 2 bits per symbol, 32 symbols per 64-bit window, plus a
-//               1-bit special mask; 0.375 B/symbol keeps a 300 Mbp text inside the 126 MB L2, which is what turns
-//               the random suffix-start accesses of the lcp and bwt kernels into L2 hits.
+//   TextPacked2 alphabets of at most 4 letters (DNA): 2 bits per symbol in 16-byte records of 60 symbols (one load
+//               per suffix start, 28 symbols per comparison step), plus a 1-bit special mask that is consulted only
+//               when a record's summary bits say so; 0.625 B/symbol keeps a 200 Mbp text inside the 126 MB L2.
 #pragma once
 
 #include "common.cuh"
