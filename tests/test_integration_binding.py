@@ -1,0 +1,40 @@
+"""The reference-side binding shown in INTEGRATION.md section B (integration/gpusuffixsort.c) compiles against the
+REFERENCE's own headers -- Virtualtree, Input, PairUint, the ERROR macros -- and references exactly the C-ABI entry
+points the library exports.  CPU only; needs the reference tree (skipped on the GPU box)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFSRC = "/root/reference/src"
+
+
+def test_binding_in_integration_md_is_the_compiled_one():
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        snippet = re.search(r"```c\n(#include \"vstree_b200.h\".*?)```", f.read(), re.S).group(1)
+    with open(os.path.join(ROOT, "integration", "gpusuffixsort.c")) as f:
+        assert snippet in f.read(), "INTEGRATION.md section B and integration/gpusuffixsort.c drifted apart"
+
+
+def test_binding_compiles_against_the_reference_headers(tmp_path):
+    if not os.path.isdir(os.path.join(REFSRC, "include")):
+        pytest.skip("reference tree not mounted")
+    obj = str(tmp_path / "gpusuffixsort.o")
+    cmd = ["gcc", "-c", "-Wall", "-Werror=incompatible-pointer-types", "-Werror=int-conversion",
+           "-Werror=implicit-function-declaration", "-Wno-unused-function", "-D_GNU_SOURCE",
+           "-I" + os.path.join(REFSRC, "include"), "-I" + os.path.join(REFSRC, "Mkvtree"),
+           "-I" + os.path.join(ROOT, "oracle", "stub"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "integration", "gpusuffixsort.c"), "-o", obj]
+    pr = subprocess.run(cmd, capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    syms = subprocess.run(["nm", obj], capture_output=True, text=True).stdout
+    undefined = {l.split()[-1] for l in syms.splitlines() if " U " in l}
+    assert {"esa_init", "esa_build"} <= undefined
+    import ctypes
+    import vstree_b200
+    lib = ctypes.CDLL(vstree_b200.library_path())
+    for name in undefined:
+        if name.startswith("esa_"):
+            assert hasattr(lib, name), f"the binding calls {name}, which the library does not export"
