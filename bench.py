@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- mkvtree index build throughput (suf+lcp+bwt) on B200, next to the reference mkvtree on the host.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|small]
 
 One "step" = one enhanced-suffix-array build (esa_construct: suffix array, inverse suffix array, lcp/llv, bwt,
 64-bit suftab) of the workload's transformed sequence.  `value` times the device-resident build (text already in
@@ -46,6 +46,60 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recommended_prefixlength(sigma, n):
+    """vm_recommendedprefixlength (src/kurtz/detpfxlen.c:31-61) in Python floats = the same libm doubles; used by the
+    reference arm, which must not load the product library."""
+    import math
+    v = n / 16.0
+    k = 1 if v <= sigma else int(math.floor(math.log(v) / math.log(float(sigma))))
+    return max(1, k)
+
+
+def survey_model_bytes(n, sigma, k, tables, rounds_active_sum, nllv, with_pack=True):
+    """SURVEY.md 8d's stage table: the algorithmic bytes of one device-resident build (4-byte indices), with the
+    implementation's own data-dependent figures (sum of active-set sizes over the refinement rounds, number of large lcp
+    values) plugged in.  Never contains replicated work or sector over-fetch."""
+    N = n + 1
+    b = 0.375 if sigma <= 4 else 0.625
+    st = {"S0_pack": n * (1 + b) if with_pack else 0.0,
+          "S1_bck": (n * b + 16.0 * sigma ** k) if "bck" in tables else 0.0,
+          "S2_initial_sort": 76.0 * N,
+          "S3_refinement_rounds": 92.0 * rounds_active_sum,
+          "S4_inverse_sa": 8.0 * N,
+          "S5_lcp": (25.0 * N + n * b + 16.0 * nllv) if "lcp" in tables else 0.0,
+          "S6_bwt": 6.0 * N if "bwt" in tables else 0.0,
+          "S7_sti1": 6.0 * N if "sti1" in tables else 0.0,
+          "S8_widen_suf": 12.0 * N if "suf" in tables else 0.0}
+    return st
+
+
+def table_checksum(first, suf, lcp, bwt, llv):
+    """Order-sensitive 64-bit checksums of a range of the tables: sums (mod 2^64) of a mix of (global index, value), so
+    that the ranges of a sharded build add up to the checksum of the whole table."""
+    import numpy as np
+    K1, K2, K3 = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xC2B2AE3D27D4EB4F), np.uint64(0x165667B19E3779F9)
+
+    def mix(idx, val):
+        x = idx * K1 + val * K2
+        x ^= x >> np.uint64(31)
+        x *= K3
+        x ^= x >> np.uint64(29)
+        return int(x.sum(dtype=np.uint64))
+
+    out = {"suf": 0, "lcp": 0, "bwt": 0, "llv": 0}
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for o in range(0, len(suf), step):
+            idx = np.arange(first + o, first + o + len(suf[o:o + step]), dtype=np.uint64)
+            out["suf"] = (out["suf"] + mix(idx, suf[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
+            out["lcp"] = (out["lcp"] + mix(idx, lcp[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
+            out["bwt"] = (out["bwt"] + mix(idx, bwt[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
+        pairs = np.asarray(llv, dtype=np.uint64).reshape(-1, 2)
+        if len(pairs):
+            out["llv"] = mix(pairs[:, 0].copy(), pairs[:, 1].copy()) & (2 ** 64 - 1)
+    return out
 
 
 def make_tis(workload, world=1):
@@ -153,69 +207,111 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def time_reference_cli(tis, sigma, flag, k, repeats=1):
+def write_fasta(tis, flag, path):
+    from vstree_b200 import synth
+    with open(path, "wb") as f:
+        f.write(synth.to_fasta(tis, "dna" if flag == "-dna" else "protein", width=1 << 20))
+
+
+def tmpfs_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+
+
+REF_MKVTREE = os.path.join(ROOT, "oracle", "_ref", "mkvtree.x")
+OUR_MKVTREE = os.path.join(ROOT, "vstree_b200", "bin", "mkvtree")
+
+
+def time_cli(binary, workdir, flag, k, repeats=1):
+    """Wall time, process start -> all files closed, of `mkvtree -db in.fna -indexname idx <flag> -pl k -suf -lcp -bwt`
+    in workdir (tmpfs), best of `repeats`."""
+    best = None
+    for _ in range(repeats):
+        for fn in os.listdir(workdir):
+            if fn.startswith("idx."):
+                os.unlink(os.path.join(workdir, fn))
+        t0 = time.perf_counter()
+        pr = subprocess.run([binary, "-db", "in.fna", "-indexname", "idx", flag, "-pl", str(k), "-suf", "-lcp", "-bwt"],
+                            cwd=workdir, capture_output=True)
+        dt = time.perf_counter() - t0
+        if pr.returncode != 0:
+            raise RuntimeError(f"{binary} failed: " + pr.stderr.decode(errors="replace"))
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def time_reference_cli(tis, sigma, flag, k, repeats=1, also_ours=False):
     """Wall time of the UNMODIFIED reference mkvtree (oracle/_ref/mkvtree.x) on a FASTA rendering of tis; falls back
-    to the C restatement (oracle port) when the binary did not travel.  Returns (seconds, kind, cores)."""
+    to the C restatement (oracle port) when the binary did not travel.  Returns (seconds, kind, cores[, ours_seconds])."""
+    if os.access(REF_MKVTREE, os.X_OK):
+        with tempfile.TemporaryDirectory(dir=tmpfs_dir()) as d:
+            write_fasta(tis, flag, os.path.join(d, "in.fna"))
+            best = time_cli(REF_MKVTREE, d, flag, k, repeats)
+            ours = None
+            if also_ours and os.access(OUR_MKVTREE, os.X_OK):
+                time_cli(OUR_MKVTREE, d, flag, k, 1)  # first run of the binary on this box: page cache, module load
+                ours = time_cli(OUR_MKVTREE, d, flag, k, 2)
+        return (best, "reference", 1, ours) if also_ours else (best, "reference", 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_util as ou
-    from vstree_b200 import synth
-    if ou.have_ref():
-        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-        with tempfile.TemporaryDirectory(dir=shm) as d:
-            path = os.path.join(d, "in.fna")
-            with open(path, "wb") as f:
-                f.write(synth.to_fasta(tis, "dna" if flag == "-dna" else "protein", width=1 << 20))
-            best = None
-            for _ in range(repeats):
-                for fn in os.listdir(d):
-                    if fn.startswith("idx."):
-                        os.unlink(os.path.join(d, fn))
-                t0 = time.perf_counter()
-                pr = subprocess.run([ou.REF_MKVTREE, "-db", "in.fna", "-indexname", "idx", flag, "-pl", str(k), "-suf",
-                                     "-lcp", "-bwt"], cwd=d, capture_output=True)
-                dt = time.perf_counter() - t0
-                if pr.returncode != 0:
-                    raise RuntimeError("reference mkvtree failed: " + pr.stderr.decode(errors="replace"))
-                best = dt if best is None else min(best, dt)
-        return best, "reference", 1
     t0 = time.perf_counter()
     ou.oracle_build(tis, sigma, k, bck=False, sti1=False)
-    return time.perf_counter() - t0, "port", 1
+    dt = time.perf_counter() - t0
+    return (dt, "port", 1, None) if also_ours else (dt, "port", 1)
 
 
 def run_reference_arm(args, rank, world):
-    """bench.py --impl reference: the reference's own CPU implementation of the path on the host cores."""
+    """bench.py --impl reference: the reference's own CPU implementation of the path on the host cores, on the SAME
+    workload as the product arm (same generator, seed, length and prefix length; the whole sequence every step).  The
+    product library is not loaded here.  The reference is single-threaded C: cores = 1."""
     if rank != 0:
         return
     desc, n, sigma, flag, gen, kw = WORKLOADS[args.workload]
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from vstree_b200 import load_library
-    lib = load_library()  # host-side scalar math only (no GPU call)
-    # bounded sample: the whole run should end within a few minutes at ~5 Msymbols/s on one core
-    budget = 150.0
-    sample = int(min(n, max(2_000_000, budget * 5e6 / (args.steps + args.warmup))))
-    from vstree_b200 import synth
-    tis = getattr(synth, gen)(sample, **kw)
-    k = lib.esa_recommended_prefixlength(sigma, sample)
-    times = []
-    kind, cores = "reference", 1
-    for i in range(args.warmup + args.steps):
-        dt, kind, cores = time_reference_cli(tis, sigma, flag, k)
-        if i >= args.warmup:
-            times.append(dt)
+    if args.workload not in STRONG:
+        n *= world
+    tis, _, _ = make_tis(args.workload, world)
+    k = recommended_prefixlength(sigma, n)
+    unit = "Mbp/s" if flag == "-dna" else "Mres/s"
+    # every step is the whole workload; when one step is so long that W + K of them would not end within the budget
+    # (the reference is superlinear: N x 100 Mbp at N = 8), warm-ups go first, then timed steps (never below one)
+    budget_s = float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "1200"))
+    times, kind, cores = [], "reference", 1
+    t_begin = time.perf_counter()
+    if os.access(REF_MKVTREE, os.X_OK):
+        with tempfile.TemporaryDirectory(dir=tmpfs_dir()) as d:
+            write_fasta(tis, flag, os.path.join(d, "in.fna"))
+            first = time_cli(REF_MKVTREE, d, flag, k)  # also the first warm-up
+            warm_left = max(0, args.warmup - 1)
+            if first * (args.warmup + args.steps) > budget_s:
+                warm_left = 0
+            for _ in range(warm_left):
+                time_cli(REF_MKVTREE, d, flag, k)
+            if args.warmup == 0:
+                times.append(first)
+            while len(times) < args.steps:
+                if times and (time.perf_counter() - t_begin) + times[-1] > budget_s:
+                    break
+                times.append(time_cli(REF_MKVTREE, d, flag, k))
+    else:
+        kind = "port"
+        for i in range(args.warmup + args.steps):
+            dt, kind, cores = time_reference_cli(tis, sigma, flag, k)
+            if i >= args.warmup:
+                times.append(dt)
     total = sum(times)
-    value = sample * len(times) / total / 1e6
+    value = n * len(times) / total / 1e6
     line = {"impl": "reference", "metric": "mkvtree index build throughput (suf+lcp+bwt)", "value": value,
-            "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "n_gpus": args.gpus, "steps": args.steps,
+            "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "sample": f"first-principles regeneration at n={sample} (same generator/seed)",
-                       "prefixlength": int(k), "tables": list(TABLES)},
-            "cpu_baseline": {"value": value, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "cores": cores,
-                             "kind": kind, "sample": f"{sample} symbols per step, CLI wall time incl. parse and file "
-                                                     "output to tmpfs"},
-            "e2e": {"value": value, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0},
+            "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": desc, "n": n, "prefixlength": int(k), "tables": list(TABLES),
+                       "steps_timed": len(times),
+                       "seam": "whole CLI process (FASTA parse, sort, table files on tmpfs): the reference has no "
+                               "in-memory entry that skips the parse"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind,
+                             "sample": f"the whole workload ({n} symbols) every step, {len(times)} timed steps, CLI wall "
+                                       "time incl. FASTA parse and file output to tmpfs"},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -228,7 +324,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default: --steps)")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="N > 1: skip the comparison of the sharded tables with a single-GPU build of the same text")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +335,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
+    if args.e2e_steps <= 0:
+        args.e2e_steps = args.steps
     # libraries (NCCL's version banner) write to fd 1: keep stdout for the ONE JSON line
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -316,6 +416,7 @@ def main():
 
     # ---- end-to-end leg: esa_build through the C ABI with host buffers --------------------------------------
     e2e_ms, h2d, d2h, e2e_detail, e2e_steps_ms = 0.0, 0, 0, None, []
+    verify = None
     for i in range(1 + args.e2e_steps):
         barrier()
         t1 = time.perf_counter()
@@ -329,6 +430,16 @@ def main():
             dist.all_reduce(part)
             N = n + 1
             assert int(part[1]) == N and int(part[0]) % (1 << 56) == (N * (N - 1) // 2) % (1 << 56), "sharded suftab is not a permutation"
+            if not args.no_verify:
+                # outside every timed region: the tables of the sharded build against ONE GPU building the same text.
+                # Order-sensitive checksums over (global index, value) add up over the ranges.
+                cs = table_checksum(tabs["shard_first"], tabs["suf"], tabs["lcp"], tabs["bwt"], tabs["llv"])
+                mine = [cs["suf"], cs["lcp"], cs["bwt"], cs["llv"], tabs["largelcpvalues"]]
+                gathered = [None] * world
+                dist.all_gather_object(gathered, mine)
+                if rank == 0:
+                    tot = [sum(g[j] for g in gathered) & (2 ** 64 - 1) for j in range(5)]
+                    verify = {"sharded": tot, "maxbranchdepth": tabs["maxbranchdepth"], "longest": tabs["longest"]}
         esa.free(tabs)
         if i > 0:
             e2e_ms += dt
@@ -337,23 +448,50 @@ def main():
             e2e_detail = {"h2d_ms": round(st["ms_h2d"], 3), "device_ms": round(st["ms_total"], 3),
                           "d2h_tail_ms": round(st["ms_d2h"], 3), "wall_ms": round(dt, 3),
                           "host_cpus": st["host_cpus"], "host_widen_threads": st["host_widen_threads"]}
-    # the box shows sporadic host-side stalls (upload or driver calls held up for tens of ms, also in runs that do
-    # nothing else): the headline is the MEDIAN step, the mean and every step are reported next to it
+    # headline: the MEAN over the timed steps; the median and every step are reported next to it (the box shows sporadic
+    # host-side stalls of tens of ms in upload or driver calls)
     e2e_mean_step = e2e_ms / args.e2e_steps
-    e2e_ms_step = float(np.median(e2e_steps_ms)) if e2e_steps_ms else e2e_mean_step
+    e2e_median_step = float(np.median(e2e_steps_ms)) if e2e_steps_ms else e2e_mean_step
 
-    t = torch.tensor([dev_ms, e2e_ms_step], dtype=torch.float64, device="cuda")
+    # model inputs that live on the ranks: large lcp values and active-set sums of the whole index
+    agg = torch.tensor([float(last["nllv"]), float(last["active_sum"]), float(last["active_first"]),
+                        float(sum(v["bytes"] for name_, v in kern.items() if name_ not in ("comm",)) / args.steps)],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+    nllv_all, active_sum_all, active_first_all, own_bytes_all = (float(x) for x in agg)
+
+    t = torch.tensor([dev_ms, e2e_mean_step, e2e_median_step], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    dev_ms_max, e2e_ms_max, e2e_median_max = float(t[0]), float(t[1]), float(t[2])
 
-    cpu = None
+    if verify is not None and rank == 0:
+        # the same text on this GPU alone (a second context without communicator); the sharded context stays alive
+        with Esa(local_rank) as one:
+            t_one, _ = one.build(pinned, sigma, k, TABLES, want_stats=False, copy=False)
+            cs = table_checksum(0, t_one["suf"], t_one["lcp"], t_one["bwt"], t_one["llv"])
+            want = [cs["suf"], cs["lcp"], cs["bwt"], cs["llv"], t_one["largelcpvalues"]]
+            same = (want == verify["sharded"] and t_one["maxbranchdepth"] == verify["maxbranchdepth"]
+                    and t_one["longest"] == verify["longest"])
+            one.free(t_one)
+        verify = {"against": "single-GPU build of the same text on rank 0 (outside the timed regions)",
+                  "checksums_suf_lcp_bwt_llv_nllv": ["%016x" % x for x in want[:4]] + [want[4]], "identical": bool(same)}
+        assert same, f"sharded tables differ from the single-GPU build: {verify}"
+
+    cpu, e2e_cli = None, None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            sec, kind, cores = time_reference_cli(tis, sigma, flag, k)
+            sec, kind, cores, ours_sec = time_reference_cli(tis, sigma, flag, k, also_ours=(world == 1))
             cpu = {"value": n / sec / 1e6, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "cores": cores,
                    "kind": kind, "sample": f"the whole workload once ({n} symbols), CLI wall time incl. FASTA parse and "
                                            f"file output to tmpfs: {sec:.2f} s"}
+            if ours_sec is not None:
+                # the like-for-like process seam: both binaries, same FASTA file and command line, process start -> files
+                # closed, tmpfs (the product's time is dominated by CUDA start-up, parse and file output, not the build)
+                e2e_cli = {"ours_s": round(ours_sec, 3), "reference_s": round(sec, 3), "ratio": round(sec / ours_sec, 2),
+                           "value": n / ours_sec / 1e6, "unit": "Mbp/s" if flag == "-dna" else "Mres/s",
+                           "command": f"mkvtree -db in.fna -indexname idx {flag} -pl {k} -suf -lcp -bwt"}
         except Exception as e:  # the baseline is a report, not a gate
             cpu = {"value": None, "unit": "Mbp/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -373,18 +511,25 @@ def main():
         stage = {name: {"launches": v["launches"] // args.steps, "ms": v["ms"] / args.steps,
                         "GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None)}
                  for name, v in kern.items() if v["launches"]}
-        # the whole build against the HBM roofline (north star): the algorithmic bytes of every kernel family of rank 0
-        # (DESIGN.md section 5 lists the per-unit figures) over the step time, against the measured copy peak per GPU
+        # the whole build against the HBM roofline (north star): SURVEY.md 8d's stage bytes of the WHOLE index (with this
+        # implementation's measured active-set sums and large-lcp count) over the step time, against the measured copy
+        # peak of all GPUs together; next to it the sum of the kernel families' own algorithmic bytes
         try:
-            build_bytes = sum(v["bytes"] for name_, v in kern.items() if name_ not in ("comm",)) / args.steps
             step_s = dev_ms_max / args.steps * 1e-3
-            build_roofline = {"algorithmic_bytes_per_step_rank0": build_bytes,
-                              "bytes_per_symbol": build_bytes / max(1, last["shard_count"]),
-                              "achieved": build_bytes / step_s / 1e9 if step_s > 0 else None, "peak": peak,
-                              "unit": "GB/s per GPU",
-                              "frac": (build_bytes / step_s / 1e9 / peak) if (peak and step_s > 0) else None}
-        except Exception:  # a report next to the headline, never a reason to lose the line
-            build_roofline = None
+            stages_model = survey_model_bytes(n, sigma, k, TABLES, active_sum_all, nllv_all)
+            model_bytes = sum(stages_model.values())
+            build_roofline = {"model": "SURVEY.md 8d stage table", "stage_bytes": stages_model,
+                              "model_bytes_per_step": model_bytes, "model_bytes_per_symbol": model_bytes / n,
+                              "achieved": model_bytes / step_s / 1e9, "peak": peak * world, "unit": "GB/s (all GPUs)",
+                              "frac": model_bytes / step_s / 1e9 / (peak * world),
+                              "frac_of_nominal_8TBs": model_bytes / step_s / 1e9 / (8000.0 * world),
+                              "own_algorithmic_bytes_per_step": own_bytes_all,
+                              "own_bytes_per_symbol": own_bytes_all / n,
+                              "own_frac": own_bytes_all / step_s / 1e9 / (peak * world),
+                              "refinement_rounds": last["rounds"], "active_sum": active_sum_all,
+                              "active_first": active_first_all, "largelcpvalues": nllv_all}
+        except Exception as e:  # a report next to the headline, never a reason to lose the line
+            build_roofline = {"error": str(e)}
         line = {
             "metric": "mkvtree index build throughput (suf+lcp+bwt)",
             "value": n * args.steps / (dev_ms_max * 1e-3) / 1e6,
@@ -418,9 +563,12 @@ def main():
             "build_roofline": build_roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": n / (e2e_ms_max * 1e-3) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max, "statistic": "median over steps",
-                    "mean_ms_per_step_rank0": round(e2e_mean_step, 3), "steps": args.e2e_steps,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max,
+                    "statistic": "mean over the timed steps (max over ranks)",
+                    "median_ms_per_step": round(e2e_median_max, 3), "steps": args.e2e_steps,
                     "steps_ms_rank0": e2e_steps_ms, "last_step_rank0": e2e_detail},
+            "e2e_cli": e2e_cli,
+            "verify": verify,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

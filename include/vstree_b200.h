@@ -139,6 +139,10 @@ typedef struct
   /* esa_build: host side of the fused download */
   uint32_t host_cpus;                /* CPUs usable by this process (affinity mask and cgroup quota) */
   uint32_t host_widen_threads;       /* host threads that widened the 32-bit suffix array (0: widened on the device) */
+  /* scalars of the tables left resident (this rank's range in a sharded build) */
+  uint64_t nllv;                     /* lcp values >= 255 (largelcpvalues) */
+  uint64_t maxbranchdepth;
+  uint64_t num_sorted;               /* suffixes that went through the sort (N - special-initial ones) */
 } esa_stats;
 
 /* ---- lifetime ---- */
@@ -194,8 +198,10 @@ int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, int me, uint
                    uint64_t *recv_cnt, uint32_t start[256]);
 
 /* ---- suffix-to-text checks on the device (reference DEBUG checks: bese.c:355-528, cprsuf.c:66-95,
- * mkvprocess.c:672-763).  Runs on the tables left resident by the last esa_construct.  Returns 0 when
- * consistent, ESA_ERR_CHECK with a message naming the violated property otherwise. ---- */
+ * mkvprocess.c:672-763).  Runs on the tables left resident by the last esa_construct: permutation, order of
+ * neighbours, lcp8, the EXACT values of the .llv pairs with largelcpvalues and maxbranchdepth, bwt, bck against the
+ * suffix array, bck.left + sti1.  Returns 0 when consistent, ESA_ERR_CHECK with a message naming the violated
+ * property otherwise. ---- */
 int esa_check(esa_ctx *ctx, char *errbuf, size_t errlen);
 
 /* ---- host-side scalar math that must match the reference bit for bit ---- */
@@ -210,6 +216,12 @@ uint32_t esa_maximal_prefixlength(uint32_t numofchars, uint64_t totallength);
  * key_bytes is 4 or 8; vals may be NULL.  Sorts by key bits [begin_bit, end_bit), stable. ---- */
 int esa_debug_radix_sort(esa_ctx *ctx, int key_bytes, void *keys, uint32_t *vals, uint64_t n, uint32_t begin_bit,
                          uint32_t end_bit, char *errbuf, size_t errlen);
+
+/* ---- testing hook for esa_check: XORs `xor_mask` into element `index` of a table left resident on the device by the
+ * last esa_construct (table = one ESA_*TAB bit; ESA_DEBUG_LLVTAB addresses the .llv words: 2*j index, 2*j+1 value), so
+ * that tests can prove esa_check notices a damaged table (the reference's DEBUG checks abort the same way). ---- */
+#define ESA_DEBUG_LLVTAB (1u << 31)
+int esa_debug_corrupt(esa_ctx *ctx, uint32_t table, uint64_t index, uint64_t xor_mask, char *errbuf, size_t errlen);
 
 /* Library identification: "vstree_b200 <version> sm_100a". */
 const char *esa_version(void);

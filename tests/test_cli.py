@@ -424,3 +424,85 @@ def test_at1mb_scale_cli_against_reference(tmp_path):
     tis = synth.dna_with_specials(800000, seed=17, nfrac=0.02, mean_run=8, records=1900)
     compare(tmp_path, {"at.fna": synth.to_fasta(tis, "dna")},
             ["-db", "at.fna", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-bck", "-sti1", "-v"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] on the reference's OWN fixture: src/testdata/at1MB (committed gzipped under tests/golden/,
+# with Grumbach/Wildcards.fna), command line of SURVEY.md 8d.  The sha256 prefixes are the ones SURVEY.md 8c recorded
+# from the reference build; the live reference binary is compared on top when it travelled.
+AT1MB_SHA = {"suf": "d35617c3307679b0", "lcp": "010a6436643f0908", "llv": "5bea62168cc44547", "bwt": "8ce08b07227a8a93",
+             "bck": "3d3d5e340324cebc", "sti1": "1b8f0b5f567ebebc", "tis": "0d91a7b28cfa0b7a", "ois": "02747886eee026fd",
+             "des": "8924f1da9e6ede03", "sds": "d245f9f21ed02b3f", "ssp": "8b7e1d182c7e701a", "al1": "07fca85c244e5b6a"}
+AT1MB_PRJ = {"totallength": 772376, "numofsequences": 1952, "specialcharacters": 18923, "specialranges": 18010,
+             "longest": 137851, "largelcpvalues": 2317, "maxbranchdepth": 517, "prefixlength": 7}
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def at1mb_bytes():
+    with gzip.open(os.path.join(GOLDEN_DIR, "at1MB.gz"), "rb") as f:
+        return f.read()
+
+
+def test_at1mb_fixture_is_the_reference_file():
+    import hashlib
+    data = at1mb_bytes()
+    assert len(data) == 999815 and hashlib.sha256(data).hexdigest()[:16] == "8cb0a609e8c559b6"
+
+
+@pytest.mark.gpu
+def test_config1_at1mb_survey_hashes(tmp_path):
+    """`mkvtree -db at1MB -dna -pl -suf -lcp -bwt -tis -ois` (+ -bck; .sti1 in a second run: -sti1 suppresses .suf)."""
+    import hashlib
+    (tmp_path / "at1MB").write_bytes(at1mb_bytes())
+    rc, out, err, files = run(OURS, ["-db", "at1MB", "-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-bck"],
+                              str(tmp_path))
+    assert rc == 0, err
+    rc, out, err, files2 = run(OURS, ["-db", "at1MB", "-indexname", "two", "-dna", "-pl", "-sti1"], str(tmp_path))
+    assert rc == 0, err
+    files["at1MB.sti1"] = files2["two.sti1"]
+    for suffix, want in AT1MB_SHA.items():
+        got = hashlib.sha256(files["at1MB." + suffix]).hexdigest()[:16]
+        assert got == want, f".{suffix}: {got} != {want} (SURVEY.md 8c)"
+    prj = ou.parse_prj(files["at1MB.prj"].decode())
+    for k, v in AT1MB_PRJ.items():
+        assert prj[k] == v, (k, prj[k], v)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,args", [
+    ("at1MB", ["-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-bck", "-v"]),
+    ("at1MB", ["-dna", "-pl", "-sti1", "-skp", "-suf", "-lcp"]),
+    ("Wildcards.fna", ["-dna", "-pl", "-suf", "-lcp", "-bwt", "-tis", "-ois", "-bck", "-sti1", "-v"]),
+    ("Wildcards.fna", ["-dna", "-suf", "-lcp", "-bwt"])])
+def test_reference_fixtures_cli_against_live_reference(tmp_path, fixture, args):
+    data = at1mb_bytes() if fixture == "at1MB" else open(os.path.join(GOLDEN_DIR, fixture), "rb").read()
+    compare(tmp_path, {fixture: data}, ["-db", fixture] + args, expect_rc=None)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_c2_cli_against_live_reference_at_full_size(tmp_path_factory):
+    """Process seam at BASELINE.json configs[1]: both binaries on the same 100 Mbp FASTA file, every file compared
+    (cmp), on tmpfs.  About 20 s of reference time."""
+    import tempfile
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tis = synth.random_dna(100_000_000, seed=42)
+    args = ["-db", "c2.fna", "-dna", "-pl", "-tis", "-ois", "-suf", "-lcp", "-bwt", "-bck"]
+    with tempfile.TemporaryDirectory(dir=shm) as d:
+        fasta = synth.to_fasta(tis, "dna", width=1 << 20)
+        del tis
+        for sub in ("ref", "ours"):
+            os.mkdir(os.path.join(d, sub))
+            with open(os.path.join(d, sub, "c2.fna"), "wb") as f:
+                f.write(fasta)
+        del fasta
+        pa = subprocess.run([ou.REF_MKVTREE] + args, cwd=os.path.join(d, "ref"), capture_output=True)
+        pb = subprocess.run([OURS] + args, cwd=os.path.join(d, "ours"), capture_output=True)
+        assert pa.returncode == 0 and pb.returncode == 0, (pa.stderr, pb.stderr)
+        names = sorted(fn for fn in os.listdir(os.path.join(d, "ref")) if fn != "c2.fna")
+        assert names == sorted(fn for fn in os.listdir(os.path.join(d, "ours")) if fn != "c2.fna")
+        assert {"c2.fna.suf", "c2.fna.lcp", "c2.fna.llv", "c2.fna.bwt", "c2.fna.bck", "c2.fna.prj"} <= set(names)
+        for fn in names:
+            pr = subprocess.run(["cmp", os.path.join(d, "ref", fn), os.path.join(d, "ours", fn)], capture_output=True)
+            assert pr.returncode == 0, f"{fn}: {pr.stdout.decode()}"

@@ -242,9 +242,10 @@ def test_against_live_reference_binary(esa, kind, tmp_path):
 
 # ---------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs): too big for the CPU oracle, so size-independent invariants
-def _properties(esa, tis, sigma, k, tables=ALL):
+def _properties(esa, tis, sigma, k, tables=ALL, check=True):
     got, st = esa.build(tis, sigma, k, tables=tables)
-    esa.check()  # permutation, order, lcp, bwt, sti1 on the device
+    if check:
+        esa.check()  # permutation, order, lcp (exact values, llv), bwt, bck, sti1 on the device
     N = len(tis) + 1
     suf = got["suf"]
     assert len(suf) == N
@@ -265,18 +266,96 @@ def _properties(esa, tis, sigma, k, tables=ALL):
     return got, st
 
 
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at FULL size against the reference: tests/golden/bench_golden.json holds the sha256 of
+# every table file the UNMODIFIED reference mkvtree wrote for the same seeded input (tests/golden/make_bench_golden.py,
+# run where /root/reference is present).  The file is committed; a missing file or entry FAILS the test.
+BENCH_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "bench_golden.json")
+
+
+def bench_golden(name):
+    assert os.path.exists(BENCH_GOLDEN), "tests/golden/bench_golden.json is missing (make_bench_golden.py makes it)"
+    with open(BENCH_GOLDEN) as f:
+        g = json.load(f)
+    assert name in g, f"bench_golden.json has no entry {name}"
+    return g[name]
+
+
+def assert_matches_reference_golden(got, g, what):
+    for t in ("suf", "lcp", "llv", "bwt", "bck"):
+        h = hashlib.sha256(np.ascontiguousarray(got[t]).tobytes()).hexdigest()
+        assert h == g["sha256"][t], f"{what}: {t} differs from the reference's file ({h[:16]} vs {g['sha'][t]})"
+    assert got["longest"] == g["prj"]["longest"], what
+    assert got["maxbranchdepth"] == g["prj"]["maxbranchdepth"], what
+    assert got["largelcpvalues"] == g["prj"]["largelcpvalues"], what
+
+
+FULL = ("suf", "lcp", "bwt", "bck")
+
+
+def full_size_case(esa, name, check=True):
+    g = bench_golden(name)
+    tis = getattr(synth, g["generator"])(g["n"], **g["kwargs"])
+    assert hashlib.sha256(tis.tobytes()).hexdigest() == g["tis_sha256"], f"{name}: the generator no longer makes the golden's input"
+    got, st = _properties(esa, tis, g["sigma"], g["prefixlength"], tables=FULL, check=check)
+    assert_matches_reference_golden(got, g, name)
+    return got, st
+
+
 def test_full_size_c2_100mbp_random_dna(esa):
-    """BASELINE.json configs[1]: 100 Mbp random DNA, byte-identical .suf/.lcp/.bwt (hashes made here by the reference
-    binary, tests/golden/bench_golden.json)."""
+    """BASELINE.json configs[1]: 100 Mbp random DNA, byte-identical .suf/.lcp/.llv/.bwt/.bck."""
+    full_size_case(esa, "c2_100mbp")
+
+
+def test_full_size_c2_twin_with_specials(esa):
+    """the C2 twin with 0.1 % N in runs and 1000 records (specials at scale)."""
+    full_size_case(esa, "c2n_100mbp")
+
+
+def test_full_size_c3_250mbp_repeat_rich(esa):
+    """BASELINE.json configs[2]: 250 Mbp repeat-rich DNA, 67 M lcp values >= 255 (exact values in .llv)."""
+    got, st = full_size_case(esa, "c3_250mbp")
+    assert st["rounds"] >= 5 and got["largelcpvalues"] > 60_000_000
+
+
+def test_full_size_c4_500m_protein(esa):
+    """BASELINE.json configs[3]: 500 M residues, 100 000 records."""
+    full_size_case(esa, "c4_500mres")
+
+
+def test_full_size_c5_sample_30mbp_human_like(esa):
+    """configs[4]'s generator at 30 Mbp (satellite arrays: lcp up to 233 222, the plcp path) against the reference."""
+    got, st = full_size_case(esa, "c5m_30mbp")
+    assert got["maxbranchdepth"] > 100_000
+
+
+def test_full_size_c5_sample_300mbp_human_like(esa):
+    """configs[4]'s generator at 300 Mbp against the reference (about an hour of reference time, made once).  The device
+    check is skipped here: its brute-force lcp recomputation needs minutes on the satellite arrays."""
+    full_size_case(esa, "c5s_300mbp", check=False)
+
+
+@pytest.mark.skipif(not ou.have_ref(), reason="oracle/_ref/mkvtree.x did not travel")
+def test_c2_against_the_live_reference_binary(esa, tmp_path_factory):
+    """The unmodified reference, run on THIS box on the 100 Mbp C2 input (about 10-20 s), table by table."""
     tis = synth.random_dna(100_000_000, seed=42)
-    got, st = _properties(esa, tis, 4, 11, tables=("suf", "lcp", "bwt"))
-    path = os.path.join(os.path.dirname(__file__), "golden", "bench_golden.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            g = json.load(f).get("c2_100mbp")
-        if g:
-            for t in ("suf", "lcp", "llv", "bwt"):
-                assert hashlib.sha256(got[t].tobytes()).hexdigest()[:16] == g["sha"][t], t
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    import tempfile
+    with tempfile.TemporaryDirectory(dir=shm) as d:
+        path = os.path.join(d, "in.fna")
+        with open(path, "wb") as f:
+            f.write(synth.to_fasta(tis, "dna", width=1 << 20))
+        rc, out, err, files = ou.run_mkvtree(ou.REF_MKVTREE, path, ["-dna", "-pl", "-suf", "-lcp", "-bwt", "-bck"],
+                                             keepdir=d)
+        assert rc == 0, err
+        ref = ou.tables_from_files(files)
+        del files
+    k = ref["prj"]["prefixlength"]
+    assert k == 11
+    got, _ = esa.build(tis, 4, k, tables=FULL)
+    for t in ("suf", "lcp", "llv", "bwt", "bck"):
+        assert len(got[t]) == len(ref[t]) and np.array_equal(got[t], ref[t]), f"{t}: {first_diff(got[t], ref[t])}"
+    assert got["longest"] == ref["prj"]["longest"] and got["maxbranchdepth"] == ref["prj"]["maxbranchdepth"]
 
 
 def test_full_size_repeat_rich_30mbp(esa):
@@ -289,3 +368,48 @@ def test_full_size_repeat_rich_30mbp(esa):
 def test_full_size_protein_50m(esa):
     tis = synth.random_protein(50_000_000, seed=11, records=10000, xfrac=0.0005)
     _properties(esa, tis, 20, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# esa_check must FAIL on a damaged table (the reference's DEBUG checks abort the same way, bese.c:355-528)
+@pytest.fixture(scope="module")
+def resident(esa):
+    """A resident build with deep lcp values (llv pairs), bck and sti1."""
+    tis = synth.repeat_rich_dna(400_000, seed=3, copies=8, divergence=0.002, tandem_frac=0.05, tandem_len=3000)
+    return tis
+
+
+def _construct(esa, tis, mode=None):
+    esa.upload(tis, 4)
+    esa.construct(7, tables=("suf", "lcp", "bwt", "bck", "sti1"))
+    esa.check()
+
+
+@pytest.mark.parametrize("table,index,xor,needle", [
+    ("suf", 1234, 1 << 3, "permutation"), ("lcp", 4321, 1, "lcp"), ("bwt", 99, 2, "bwt"),
+    ("bck", 2 * 100, 1, "bck"), ("bck", 2 * 100 + 1, 1, "bck"), ("sti1", 777, 1, "sti1"),
+    ("llv", 1, 1, "llv"), ("llv", 2 * 5 + 1, 1 << 9, "llv"), ("llv", 2 * 7, 1, "llv")])
+def test_check_fails_on_a_damaged_table(esa, resident, table, index, xor, needle):
+    _construct(esa, resident)
+    if table == "sti1":
+        # damage an entry the check looks at: a suffix inside [left, mid) of some bucket
+        tabs = esa.download()
+        index = int(tabs["suf"][int(tabs["bck"][2 * 50])])
+    esa.debug_corrupt(table, index, xor)
+    with pytest.raises(EsaError) as ei:
+        esa.check()
+    assert ei.value.code == -8 and needle in str(ei.value), str(ei.value)
+    esa.debug_corrupt(table, index, xor)  # undo: consistent again
+    esa.check()
+
+
+def test_check_compares_exact_large_values_on_both_lcp_paths(esa, resident):
+    """largelcpvalues and maxbranchdepth are part of the check: a wrong exact value >= 255 is found even though its
+    saturated .lcp byte is right."""
+    _construct(esa, resident)
+    tabs = esa.download()
+    assert tabs["largelcpvalues"] > 100 and tabs["maxbranchdepth"] > 255
+    j = int(np.argmax(tabs["llv"][1::2]))  # the pair that carries maxbranchdepth
+    esa.debug_corrupt("llv", 2 * j + 1, 1 << 20)
+    with pytest.raises(EsaError):
+        esa.check()

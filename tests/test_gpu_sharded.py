@@ -119,3 +119,43 @@ def test_sharded_context_refuses_what_needs_the_whole_inverse_array(group):
     # the group survives a refused build
     got, _ = group.build(tis, 4, 5, tables=("suf",))
     assert int(got["suf"].sum()) == 50001 * 50000 // 2
+
+
+def test_upload_failure_on_one_rank_wakes_the_others(monkeypatch):
+    """A rank that fails inside the collective upload must abort the group by itself (esa_upload / esa_build call
+    esa_group_abort): the C driver runs one thread per rank and joins them -- nobody may wait forever.  The threads here
+    call the C ABI directly, without the Python wrapper's own abort."""
+    import ctypes
+    import threading
+    from vstree_b200.capi import ERRBUF, Result, Stats, load_library
+    lib = load_library()
+    tis = synth.random_dna(200000, seed=2)
+    for call in ("upload", "build"):
+        with EsaGroup([0, 0, 0]) as grp:
+            monkeypatch.setenv("ESA_DEBUG_FAIL_UPLOAD_RANK", "1")
+            codes, msgs = [None] * 3, [None] * 3
+
+            def work(r):
+                err = ctypes.create_string_buffer(ERRBUF)
+                ptr = ctypes.c_void_p(tis.ctypes.data)
+                if call == "upload":
+                    codes[r] = lib.esa_upload(grp.ranks[r].ctx, ptr, len(tis), 4, err, ERRBUF)
+                else:
+                    res, st = Result(), Stats()
+                    codes[r] = lib.esa_build(grp.ranks[r].ctx, ptr, len(tis), 4, 5, 1 << 5, ctypes.byref(res),
+                                             ctypes.byref(st), err, ERRBUF)
+                msgs[r] = err.value.decode()
+
+            threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(3)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join(timeout=60)
+            assert not any(t.is_alive() for t in threads), f"{call}: ranks hang after a failed upload on rank 1"
+            assert codes[1] == -4 and "injected" in msgs[1]
+            assert codes[0] == -9 and codes[2] == -9, (codes, msgs)
+            # the group is usable again after a reset
+            monkeypatch.delenv("ESA_DEBUG_FAIL_UPLOAD_RANK")
+            lib.esa_group_reset(grp.group)
+            got, _ = grp.build(tis, 4, 5, tables=("suf",))
+            assert int(got["suf"].sum()) == 200001 * 200000 // 2

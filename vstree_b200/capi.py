@@ -35,7 +35,8 @@ class Stats(ctypes.Structure):
                 ("ms_d2h", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("shard_first", ctypes.c_uint64), ("shard_count", ctypes.c_uint64),
                 ("comm_bytes_sent", ctypes.c_uint64), ("host_cpus", ctypes.c_uint32),
-                ("host_widen_threads", ctypes.c_uint32)]
+                ("host_widen_threads", ctypes.c_uint32), ("nllv", ctypes.c_uint64),
+                ("maxbranchdepth", ctypes.c_uint64), ("num_sorted", ctypes.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "kernel"}
@@ -98,6 +99,8 @@ def load_library():
     lib.esa_maximal_prefixlength.argtypes = [c.c_uint32, c.c_uint64]
     lib.esa_debug_radix_sort.restype = c.c_int
     lib.esa_debug_radix_sort.argtypes = [vp, c.c_int, vp, vp, c.c_uint64, c.c_uint32, c.c_uint32, cp, sz]
+    lib.esa_debug_corrupt.restype = c.c_int
+    lib.esa_debug_corrupt.argtypes = [vp, c.c_uint32, c.c_uint64, c.c_uint64, cp, sz]
     lib.esa_version.restype = cp
     lib.esa_version.argtypes = []
     lib.esa_comm_unique_id.restype = c.c_int
@@ -245,6 +248,12 @@ class Esa:
     def check(self):
         err = ctypes.create_string_buffer(ERRBUF)
         self._check(self.lib.esa_check(self.ctx, err, ERRBUF), err)
+
+    def debug_corrupt(self, table, index, xor_mask):
+        """Testing hook: damages one element of a resident device table ("llv" addresses the .llv words)."""
+        bit = (1 << 31) if table == "llv" else DEMAND_BITS[table]
+        err = ctypes.create_string_buffer(ERRBUF)
+        self._check(self.lib.esa_debug_corrupt(self.ctx, bit, index, xor_mask, err, ERRBUF), err)
 
     # ---- sharded builds: attach a communicator, then upload/construct/download/build are collective ----
     def attach_nccl(self, unique_id, nranks, rank):

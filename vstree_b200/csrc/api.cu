@@ -145,8 +145,22 @@ struct HostWiden
   pthread_cond_t cv_job = PTHREAD_COND_INITIALIZER, cv_done = PTHREAD_COND_INITIALIZER;
   u64 job_id = 0;  // under mu
   bool stop = false;
-  std::atomic<u32> next_chunk{0}, chunks_done{0};
+  // Tickets carry the job they belong to: next_ticket = job_id << 32 | next chunk, taken with compare-and-swap, so a
+  // worker that is still leaving the previous job can neither take a chunk of the next one with stale parameters nor
+  // add a stray completion (a plain fetch_add did both in a narrow window between two fused builds).
+  std::atomic<u64> next_ticket{0};
+  std::atomic<u32> chunks_done{0};
   std::atomic<bool> abort{false};
+};
+
+// what one job looks like to a worker: copied under mu together with the job id
+struct WidenJob
+{
+  u64 id;
+  u32 *staging;
+  u64 *dst;
+  u64 count, chunk;
+  u32 nchunks;
 };
 
 void widen_range(const u32 *src, u64 *dst, u64 cnt)
@@ -166,12 +180,21 @@ void widen_range(const u32 *src, u64 *dst, u64 cnt)
   _mm_sfence();
 }
 
-// takes chunks off the job until none is left; called by the workers and, at the end, by the building thread
-void widen_drain(HostWiden *w)
+// takes chunks off job j until none is left; called by the workers and, at the end, by the building thread
+void widen_drain(HostWiden *w, const WidenJob &j)
 {
-  u32 c;
-  while ((c = w->next_chunk.fetch_add(1)) < w->nchunks)
+  while (true)
   {
+    u64 t = w->next_ticket.load();
+    if ((t >> 32) != (j.id & 0xffffffffull) || (u32) t >= j.nchunks)
+    {
+      return;  // the job is used up, or a newer one has started (its parameters are not mine)
+    }
+    if (!w->next_ticket.compare_exchange_weak(t, t + 1))
+    {
+      continue;
+    }
+    const u32 c = (u32) t;
     u32 spins = 0;
     while (__atomic_load_n(w->progress, __ATOMIC_ACQUIRE) <= c && !w->abort.load())
     {
@@ -187,16 +210,22 @@ void widen_drain(HostWiden *w)
     }
     if (!w->abort.load())
     {
-      const u64 b = (u64) c * w->chunk, e = std::min(w->count, b + w->chunk);
-      widen_range(w->staging + b, w->dst + b, e - b);
+      const u64 b = (u64) c * j.chunk, e = std::min(j.count, b + j.chunk);
+      widen_range(j.staging + b, j.dst + b, e - b);
     }
-    if (w->chunks_done.fetch_add(1) + 1 == w->nchunks)
+    // a ticket of job j is completed before finish_host_widen(j) returns, so this never lands in a later job
+    if (w->chunks_done.fetch_add(1) + 1 == j.nchunks)
     {
       pthread_mutex_lock(&w->mu);
       pthread_cond_broadcast(&w->cv_done);
       pthread_mutex_unlock(&w->mu);
     }
   }
+}
+
+WidenJob widen_job_locked(const HostWiden *w)  // caller holds mu (or is the building thread that wrote the fields)
+{
+  return WidenJob{w->job_id, w->staging, w->dst, w->count, w->chunk, w->nchunks};
 }
 
 void *widen_worker(void *p)
@@ -211,13 +240,14 @@ void *widen_worker(void *p)
       pthread_cond_wait(&w->cv_job, &w->mu);
     }
     const bool stop = w->stop;
+    const WidenJob job = widen_job_locked(w);
     seen = w->job_id;
     pthread_mutex_unlock(&w->mu);
     if (stop)
     {
       return nullptr;
     }
-    widen_drain(w);
+    widen_drain(w, job);
   }
 }
 
@@ -313,6 +343,13 @@ void do_upload(FullCtx *ctx, const u8 *tis, u64 n, u32 numofchars)
     const u64 token = (u64) (uintptr_t) ctx->arena.base ^ ((u64) ctx->arena.capacity << 1);
     u64 moved = (need > ctx->arena.capacity || token != comm->mapped_token || !comm->direct) ? 1 : 0, all[ESA_MAX_RANKS];
     comm_exchange_host_u64(ctx, comm, &moved, 1, all);
+    if (const char *e = getenv("ESA_DEBUG_FAIL_UPLOAD_RANK"))  // test hook: one rank fails inside the collective upload
+    {
+      if (atoi(e) == comm->rank)
+      {
+        esa_throw(ESA_ERR_MEMORY, "injected upload failure on rank %d (ESA_DEBUG_FAIL_UPLOAD_RANK)", comm->rank);
+      }
+    }
     bool any = false;
     for (int r = 0; r < comm->nranks; r++)
     {
@@ -472,7 +509,6 @@ void start_host_widen(FullCtx *ctx)
   }
   w.nthreads_last = (int) w.threads.size();
   __atomic_store_n(w.progress, 0u, __ATOMIC_RELEASE);
-  w.next_chunk.store(0);
   w.chunks_done.store(0);
   w.abort.store(false);
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_sorted, ctx->stream));
@@ -487,6 +523,7 @@ void start_host_widen(FullCtx *ctx)
   }
   pthread_mutex_lock(&w.mu);
   w.job_id++;
+  w.next_ticket.store((w.job_id & 0xffffffffull) << 32);  // tickets of this job open only now, parameters in place
   pthread_cond_broadcast(&w.cv_job);
   pthread_mutex_unlock(&w.mu);
 }
@@ -504,7 +541,7 @@ u64 *finish_host_widen(FullCtx *ctx, bool keep)
     w.abort.store(true);  // the copy died: nobody waits for chunks that will never arrive
     keep = false;
   }
-  widen_drain(&w);  // the building thread takes what the workers have not started yet
+  widen_drain(&w, widen_job_locked(&w));  // the building thread takes what the workers have not started yet
   pthread_mutex_lock(&w.mu);
   while (w.chunks_done.load() < w.nchunks)
   {
@@ -762,6 +799,9 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     stats->device_bytes_peak = ar.peak;
     stats->shard_first = ctx->shard_first;
     stats->shard_count = ctx->shard_count;
+    stats->nllv = ctx->nllv;
+    stats->maxbranchdepth = ctx->maxbranchdepth;
+    stats->num_sorted = so.num_sorted;
     stats->comm_bytes_sent = ctx->comm != nullptr ? ctx->comm->bytes_sent : 0;
     stats->comm_direct = (is_sharded(ctx) && ctx->comm->direct) ? 1 : 0;
     collect_kernel_stats(ctx, stats);
@@ -956,10 +996,15 @@ int esa_upload(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, 
     return ESA_ERR_ARGUMENT;
   }
   FullCtx *ctx = static_cast<FullCtx *>(c);
-  return guarded(errbuf, errlen, [&]() {
+  const int rc = guarded(errbuf, errlen, [&]() {
     do_upload(ctx, tis, n, numofchars);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   });
+  if (rc != ESA_OK && is_sharded(ctx))
+  {
+    comm_abort(ctx->comm, rc);  // a sharded upload is collective: the other ranks must not wait forever
+  }
+  return rc;
 }
 
 int esa_construct(esa_ctx *c, uint32_t prefixlength, uint32_t demand, esa_stats *stats, char *errbuf, size_t errlen)
@@ -971,9 +1016,9 @@ int esa_construct(esa_ctx *c, uint32_t prefixlength, uint32_t demand, esa_stats 
   }
   FullCtx *ctx = static_cast<FullCtx *>(c);
   const int rc = guarded(errbuf, errlen, [&]() { do_construct(ctx, prefixlength, demand, stats); });
-  if (rc != ESA_OK && ctx->comm != nullptr && ctx->comm->group != nullptr)
+  if (rc != ESA_OK && is_sharded(ctx))
   {
-    esa_group_abort(ctx->comm->group);  // the other ranks must not wait for this one forever
+    comm_abort(ctx->comm, rc);  // the other ranks must not wait for this one forever
   }
   return rc;
 }
@@ -1008,19 +1053,30 @@ int esa_build(esa_ctx *c, const uint8_t *tis, uint64_t n, uint32_t numofchars, u
     cudaStream_t s = ctx->stream;
     CUDA_CHECK(cudaSetDevice(ctx->device));
     CUDA_CHECK(cudaEventRecord(ctx->x.ev_e, s));
-    do_upload(ctx, tis, n, numofchars);
-    ctx->x.fuse_download = getenv("ESA_NO_HOST_WIDEN") == nullptr;
     try
     {
+      // the upload of a sharded context is collective too (arena mapping, all-gather of the slices): a rank that
+      // fails in it must wake the others exactly like one that fails in the construction
+      do_upload(ctx, tis, n, numofchars);
+      ctx->x.fuse_download = getenv("ESA_NO_HOST_WIDEN") == nullptr;
       do_construct(ctx, prefixlength, demand, stats);  // records ev_a .. ev_d, synchronises
       ctx->x.fuse_download = false;
+    } catch (const EsaError &e)
+    {
+      ctx->x.fuse_download = false;
+      finish_host_widen(ctx, false);
+      if (is_sharded(ctx))
+      {
+        comm_abort(ctx->comm, e.code);
+      }
+      throw;
     } catch (...)
     {
       ctx->x.fuse_download = false;
       finish_host_widen(ctx, false);
-      if (ctx->comm != nullptr && ctx->comm->group != nullptr)
+      if (is_sharded(ctx))
       {
-        esa_group_abort(ctx->comm->group);
+        comm_abort(ctx->comm, ESA_ERR_MEMORY);
       }
       throw;
     }
@@ -1200,6 +1256,45 @@ int esa_debug_radix_sort(esa_ctx *c, int key_bytes, void *keys, uint32_t *vals, 
       CUDA_CHECK(cudaMemcpyAsync(vals, w ? vb : va, n * 4, cudaMemcpyDeviceToHost, s));
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int esa_debug_corrupt(esa_ctx *c, uint32_t table, uint64_t index, uint64_t xor_mask, char *errbuf, size_t errlen)
+{
+  if (c == nullptr)
+  {
+    set_err(errbuf, errlen, "ctx is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  return guarded(errbuf, errlen, [&]() {
+    if (!ctx->constructed)
+    {
+      esa_throw(ESA_ERR_STATE, "esa_debug_corrupt called before esa_construct");
+    }
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const u64 N = ctx->shard_count;
+    char *base = nullptr;
+    size_t width = 0;
+    u64 count = 0;
+    switch (table)
+    {
+      case ESA_SUFTAB: base = (char *) ctx->d_suf64, width = 8, count = N; break;
+      case ESA_LCPTAB: base = (char *) ctx->d_lcp, width = 1, count = N; break;
+      case ESA_BWTTAB: base = (char *) ctx->d_bwt, width = 1, count = N; break;
+      case ESA_BCKTAB: base = (char *) ctx->d_bck, width = 8, count = 2 * ctx->numofcodes; break;
+      case ESA_STI1TAB: base = (char *) ctx->d_sti1, width = 1, count = N; break;
+      case ESA_DEBUG_LLVTAB: base = (char *) ctx->d_llv, width = 8, count = 2 * ctx->nllv; break;
+      default: esa_throw(ESA_ERR_ARGUMENT, "esa_debug_corrupt: unknown table 0x%x", table);
+    }
+    if (base == nullptr || index >= count)
+    {
+      esa_throw(ESA_ERR_ARGUMENT, "esa_debug_corrupt: table 0x%x is not resident or index out of range", table);
+    }
+    u64 word = 0;
+    CUDA_CHECK(cudaMemcpy(&word, base + index * width, width, cudaMemcpyDeviceToHost));
+    word ^= xor_mask;
+    CUDA_CHECK(cudaMemcpy(base + index * width, &word, width, cudaMemcpyHostToDevice));
   });
 }
 

@@ -17,6 +17,7 @@ struct NcclApi
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;  // optional
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -78,6 +79,7 @@ NcclApi &nccl()
       nccl_sym(g_nccl.Recv, "ncclRecv");
       nccl_sym(g_nccl.GroupStart, "ncclGroupStart");
       nccl_sym(g_nccl.GroupEnd, "ncclGroupEnd");
+      g_nccl.CommAbort = (ncclResult_t (*)(ncclComm_t)) dlsym(g_nccl.handle, "ncclCommAbort");
     } catch (...)
     {
       g_nccl.handle = nullptr;
@@ -374,6 +376,35 @@ void comm_map_arenas(esa_ctx *ctx, esa_comm *comm)
   comm->mapped_token = (u64) (uintptr_t) ctx->arena.base ^ ((u64) ctx->arena.capacity << 1);
 }
 
+// A rank that failed inside a collective call leaves the others behind.  In-process group: wake them (they fail with
+// ESA_ERR_COMM at their next barrier).  NCCL: abort this rank's communicator so that its own queued operations and
+// its later esa_shutdown cannot block; the peers' pending NCCL operations end when their NCCL notices the loss of
+// this rank (connection reset when the process exits) -- the launcher tears the job down, as for any NCCL program.
+void comm_abort(esa_comm *comm, int code)
+{
+  if (comm == nullptr)
+  {
+    return;
+  }
+  if (comm->group != nullptr)
+  {
+    esa_group_abort(comm->group);
+  }
+  // argument / state errors are raised before the first collective of a call, identically on every rank: the
+  // communicator stays usable.  Run-time failures (CUDA, memory, transport) leave the ranks out of step.
+  const bool runtime_failure = code == ESA_ERR_CUDA || code == ESA_ERR_MEMORY || code == ESA_ERR_COMM;
+  if (comm->nccl != nullptr && comm->nranks > 1 && runtime_failure)
+  {
+    NcclApi &api = nccl();
+    if (api.CommAbort != nullptr)
+    {
+      api.CommAbort((ncclComm_t) comm->nccl);
+    }
+    comm->nccl = nullptr;
+    comm->aborted = true;
+  }
+}
+
 void comm_destroy(esa_comm *comm)
 {
   if (comm == nullptr)
@@ -460,6 +491,10 @@ void comm_exchange_host_u64(esa_ctx *ctx, esa_comm *comm, const u64 *mine, size_
   {
     memcpy(all, mine, count * sizeof(u64));
     return;
+  }
+  if (comm->aborted)
+  {
+    esa_throw(ESA_ERR_COMM, "the communicator was aborted after an earlier failure: attach a new one");
   }
   if (comm->group != nullptr)
   {

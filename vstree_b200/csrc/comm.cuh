@@ -54,6 +54,7 @@ struct esa_comm
   char *peer_base[ESA_MAX_RANKS] = {nullptr};
   void *ipc_opened[ESA_MAX_RANKS] = {nullptr};  // mappings to close (NCCL transport)
   u64 mapped_token = 0;                      // identifies the local arena allocation the peers have mapped
+  bool aborted = false;                      // NCCL transport: comm_abort ran, every later collective fails
 };
 
 // transport setup (comm.cu)
@@ -61,6 +62,7 @@ void comm_nccl_unique_id(u8 id[ESA_COMM_ID_BYTES]);
 esa_comm *comm_nccl_attach(esa_ctx *ctx, const u8 id[ESA_COMM_ID_BYTES], int nranks, int rank);
 esa_comm *comm_group_attach(esa_ctx *ctx, esa_group *g, int rank);
 void comm_destroy(esa_comm *comm);
+void comm_abort(esa_comm *comm, int code);  // a rank failed inside a collective call: do not leave the others (or itself) hanging
 
 // peer memory (collective): after the call comm->direct tells whether every rank could map every arena;
 // ESA_COMM_DIRECT=0 forces the message-passing paths.  Must be re-run (after comm_unmap_arenas) when any arena moved.

@@ -187,9 +187,11 @@ __device__ __forceinline__ u64 sym_at(const u8 *tis, u64 n, u64 p)
   return (p < n && tis[p] < ESA_WILDCARD) ? (u64) tis[p] : p + 256;
 }
 
+// scal (u64): [0] largest lcp value seen, [1] number of values >= 255
 __global__ void check_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict__ sa,
                              const u32 *__restrict__ isa, const u32 *__restrict__ v, const u8 *__restrict__ lcp8,
-                             const u8 *__restrict__ bwt, const u64 *__restrict__ suf64, u32 *__restrict__ errors)
+                             const u8 *__restrict__ bwt, const u64 *__restrict__ suf64, const u64 *__restrict__ llv,
+                             u64 nllv, u32 *__restrict__ errors, unsigned long long *__restrict__ scal)
 {
   const u64 N = n + 1;
   const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,6 +241,94 @@ __global__ void check_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__res
   if (v != nullptr && (u64) (v[s] - (u32) s) != l)
   {
     atomicAdd(&errors[3], 1u);
+  }
+  if (lcp8 != nullptr)
+  {
+    // 6: the EXACT value of a large entry is the one the .llv pair of index r holds (outlcpsubtab, bese.c:557-566;
+    // checklcpsubtab compares exact values, bese.c:454-528)
+    if (l >= 255)
+    {
+      atomicAdd(&scal[1], 1ull);
+      u64 lo = 0, hi = nllv;
+      while (lo < hi)
+      {
+        const u64 mid = (lo + hi) >> 1;
+        if (llv[2 * mid] < r)
+        {
+          lo = mid + 1;
+        } else
+        {
+          hi = mid;
+        }
+      }
+      if (lo >= nllv || llv[2 * lo] != r || llv[2 * lo + 1] != l)
+      {
+        atomicAdd(&errors[6], 1u);
+      }
+    }
+    if (l > *(volatile unsigned long long *) &scal[0])
+    {
+      atomicMax(&scal[0], (unsigned long long) l);
+    }
+  }
+}
+
+// 6 (continued): .llv indices strictly increase and every value is >= 255
+__global__ void check_llv_kernel(const u64 *__restrict__ llv, u64 nllv, u64 N, u32 *__restrict__ errors)
+{
+  const u64 j = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nllv)
+  {
+    return;
+  }
+  if (llv[2 * j] >= N || llv[2 * j + 1] < 255 || (j > 0 && llv[2 * (j - 1)] >= llv[2 * j]))
+  {
+    atomicAdd(&errors[6], 1u);
+  }
+}
+
+// 7: the bucket table against the suffix array (makebcktab, mkvprocess.c:251-327): left is monotone from 0,
+// left <= mid <= next left (N behind the last code), ...
+__global__ void check_bck_codes_kernel(u64 numofcodes, const u64 *__restrict__ bck, u64 N, u32 *__restrict__ errors)
+{
+  const u64 c = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= numofcodes)
+  {
+    return;
+  }
+  const u64 left = bck[2 * c], mid = bck[2 * c + 1], right = c + 1 < numofcodes ? bck[2 * (c + 1)] : N;
+  if ((c == 0 && left != 0) || left > mid || mid > right)
+  {
+    atomicAdd(&errors[7], 1u);
+  }
+}
+// ... and every suffix lies inside the bucket of its padded k-mer code (ppsort.c:134-153: the code is padded with the
+// largest letter behind a special), in front of mid exactly when no special lies inside its k-prefix
+__global__ void check_bck_suffix_kernel(const u8 *__restrict__ tis, u64 n, const u32 *__restrict__ sa, u32 sigma, u32 k,
+                                        u64 numofcodes, const u64 *__restrict__ bck, u32 *__restrict__ errors)
+{
+  const u64 N = n + 1;
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N)
+  {
+    return;
+  }
+  const u64 s = sa[r];
+  u64 code = 0;
+  bool full = true;
+  for (u32 i = 0; i < k; i++)
+  {
+    const u32 a = (full && s + i < n) ? tis[s + i] : 255u;
+    if (a >= ESA_WILDCARD)
+    {
+      full = false;
+    }
+    code = code * sigma + (full ? a : sigma - 1);
+  }
+  const u64 left = bck[2 * code], mid = bck[2 * code + 1], right = code + 1 < numofcodes ? bck[2 * (code + 1)] : N;
+  if (r < left || r >= right || (full != (r < mid)))
+  {
+    atomicAdd(&errors[7], 1u);
   }
 }
 
@@ -380,10 +470,27 @@ int run_checks(esa_ctx *ctx, std::string &msg)
   ensure_isa(ctx);
   const size_t mark = ctx->arena.mark();
   u32 *d_err = ctx->arena.alloc<u32>(8);
+  unsigned long long *d_scal = (unsigned long long *) ctx->arena.alloc<u64>(4);
   CUDA_CHECK(cudaMemsetAsync(d_err, 0, 8 * sizeof(u32), s));
-  check_kernel<<<div_up_u32(N, 256), 256, 0, s>>>(ctx->d_tis, ctx->n, ctx->d_sa, ctx->d_isa, ctx->d_plcpv, ctx->d_lcp,
-                                                   ctx->d_bwt, ctx->d_suf64, d_err);
+  CUDA_CHECK(cudaMemsetAsync(d_scal, 0, 4 * sizeof(u64), s));
+  const bool lcp_resident = ctx->d_lcp != nullptr && (ctx->demand & ESA_LCPTAB);
+  check_kernel<<<div_up_u32(N, 256), 256, 0, s>>>(ctx->d_tis, ctx->n, ctx->d_sa, ctx->d_isa, ctx->d_plcpv,
+                                                   lcp_resident ? ctx->d_lcp : nullptr, ctx->d_bwt, ctx->d_suf64,
+                                                   ctx->d_llv, ctx->d_llv != nullptr ? ctx->nllv : 0, d_err, d_scal);
   CUDA_CHECK(cudaGetLastError());
+  if (lcp_resident && ctx->d_llv != nullptr && ctx->nllv > 0)
+  {
+    check_llv_kernel<<<div_up_u32(ctx->nllv, 256), 256, 0, s>>>(ctx->d_llv, ctx->nllv, N, d_err);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (ctx->d_bck != nullptr && ctx->prefixlength > 0)
+  {
+    check_bck_codes_kernel<<<div_up_u32(ctx->numofcodes, 256), 256, 0, s>>>(ctx->numofcodes, ctx->d_bck, N, d_err);
+    CUDA_CHECK(cudaGetLastError());
+    check_bck_suffix_kernel<<<div_up_u32(N, 256), 256, 0, s>>>(ctx->d_tis, ctx->n, ctx->d_sa, ctx->sigma,
+                                                                ctx->prefixlength, ctx->numofcodes, ctx->d_bck, d_err);
+    CUDA_CHECK(cudaGetLastError());
+  }
   if (ctx->d_sti1 != nullptr && ctx->d_bck != nullptr)
   {
     check_sti1_kernel<<<div_up_u32(ctx->numofcodes, 256), 256, 0, s>>>(ctx->numofcodes, ctx->d_bck, ctx->d_sa,
@@ -391,13 +498,25 @@ int run_checks(esa_ctx *ctx, std::string &msg)
     CUDA_CHECK(cudaGetLastError());
   }
   u32 h_err[8];
+  u64 h_scal[4];
   CUDA_CHECK(cudaMemcpyAsync(h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof h_scal, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   ctx->arena.rewind(mark);
+  if (lcp_resident)
+  {
+    // the scalars the .prj file reports (maxbranchdepth, largelcpvalues) against the recomputed lcp values
+    if (h_scal[0] != ctx->maxbranchdepth || h_scal[1] != ctx->nllv)
+    {
+      h_err[6]++;
+    }
+  }
   static const char *names[8] = {"", "suftab is not a permutation / isa does not invert it",
                                  "adjacent suffixes out of order", "lcp value wrong", "bwt does not match the text",
-                                 "bck.left + sti1 != inverse suftab", "", ""};
-  for (int i = 1; i <= 5; i++)
+                                 "bck.left + sti1 != inverse suftab",
+                                 "exact lcp values: llv pairs / largelcpvalues / maxbranchdepth wrong",
+                                 "bck does not delimit the buckets of the suffix array"};
+  for (int i = 1; i <= 7; i++)
   {
     if (h_err[i] != 0)
     {
