@@ -89,13 +89,22 @@ def table_checksum(first, suf, lcp, bwt, llv):
         return int(x.sum(dtype=np.uint64))
 
     out = {"suf": 0, "lcp": 0, "bwt": 0, "llv": 0}
-    step = 1 << 24
-    with np.errstate(over="ignore"):
-        for o in range(0, len(suf), step):
+    step = 1 << 23
+
+    def chunk(o):
+        with np.errstate(over="ignore"):
             idx = np.arange(first + o, first + o + len(suf[o:o + step]), dtype=np.uint64)
-            out["suf"] = (out["suf"] + mix(idx, suf[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
-            out["lcp"] = (out["lcp"] + mix(idx, lcp[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
-            out["bwt"] = (out["bwt"] + mix(idx, bwt[o:o + step].astype(np.uint64))) & (2 ** 64 - 1)
+            return (mix(idx, suf[o:o + step].astype(np.uint64)), mix(idx, lcp[o:o + step].astype(np.uint64)),
+                    mix(idx, bwt[o:o + step].astype(np.uint64)))
+
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    with ThreadPoolExecutor(workers) as ex:  # numpy releases the GIL inside the array operations
+        for a, b, c in ex.map(chunk, range(0, len(suf), step)):
+            out["suf"] = (out["suf"] + a) & (2 ** 64 - 1)
+            out["lcp"] = (out["lcp"] + b) & (2 ** 64 - 1)
+            out["bwt"] = (out["bwt"] + c) & (2 ** 64 - 1)
+    with np.errstate(over="ignore"):
         pairs = np.asarray(llv, dtype=np.uint64).reshape(-1, 2)
         if len(pairs):
             out["llv"] = mix(pairs[:, 0].copy(), pairs[:, 1].copy()) & (2 ** 64 - 1)
@@ -273,7 +282,7 @@ def run_reference_arm(args, rank, world):
     unit = "Mbp/s" if flag == "-dna" else "Mres/s"
     # every step is the whole workload; when one step is so long that W + K of them would not end within the budget
     # (the reference is superlinear: N x 100 Mbp at N = 8), warm-ups go first, then timed steps (never below one)
-    budget_s = float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "1200"))
+    budget_s = float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "540"))  # the driver allows 870 s per N
     times, kind, cores = [], "reference", 1
     t_begin = time.perf_counter()
     if os.access(REF_MKVTREE, os.X_OK):
@@ -325,8 +334,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s host baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default: --steps)")
-    ap.add_argument("--no-verify", action="store_true",
-                    help="N > 1: skip the comparison of the sharded tables with a single-GPU build of the same text")
+    ap.add_argument("--verify", default=None, choices=["full", "sums", "off"],
+                    help="N > 1, outside the timed regions: 'full' compares order-sensitive checksums of the sharded tables "
+                         "with a single-GPU build of the same text on rank 0 (default for the weak-scaling workloads); "
+                         "'sums' only reports the checksums (default for c5: 3 Gbp on one GPU next to a live sharded "
+                         "context does not fit; tools/run_config.py prints the single-GPU ones); 'off' skips both")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -337,6 +349,8 @@ def main():
         return
     if args.e2e_steps <= 0:
         args.e2e_steps = args.steps
+    if args.verify is None:
+        args.verify = "sums" if args.workload in STRONG else "full"
     # libraries (NCCL's version banner) write to fd 1: keep stdout for the ONE JSON line
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -430,7 +444,7 @@ def main():
             dist.all_reduce(part)
             N = n + 1
             assert int(part[1]) == N and int(part[0]) % (1 << 56) == (N * (N - 1) // 2) % (1 << 56), "sharded suftab is not a permutation"
-            if not args.no_verify:
+            if args.verify != "off":
                 # outside every timed region: the tables of the sharded build against ONE GPU building the same text.
                 # Order-sensitive checksums over (global index, value) add up over the ranges.
                 cs = table_checksum(tabs["shard_first"], tabs["suf"], tabs["lcp"], tabs["bwt"], tabs["llv"])
@@ -466,7 +480,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max, e2e_median_max = float(t[0]), float(t[1]), float(t[2])
 
-    if verify is not None and rank == 0:
+    if verify is not None and rank == 0 and args.verify == "sums":
+        verify = {"against": None, "checksums_suf_lcp_bwt_llv_nllv": ["%016x" % x for x in verify["sharded"][:4]]
+                  + [verify["sharded"][4]], "maxbranchdepth": verify["maxbranchdepth"], "longest": verify["longest"],
+                  "identical": None}
+    elif verify is not None and rank == 0:
         # the same text on this GPU alone (a second context without communicator); the sharded context stays alive
         with Esa(local_rank) as one:
             t_one, _ = one.build(pinned, sigma, k, TABLES, want_stats=False, copy=False)

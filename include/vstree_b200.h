@@ -193,7 +193,9 @@ int esa_comm_attach_group(esa_ctx *ctx, esa_group *group, int rank, char *errbuf
 void esa_comm_detach(esa_ctx *ctx);
 /* Host logic of the exchange step, exposed for tests (no GPU needed): from every rank's per-bin suffix counts
  * hist[r*stride + b] (256 bins = top 8 bits of the initial sort key) derive the bin -> rank table, what rank `me`
- * sends to / receives from every rank, and where its run of every bin starts inside the owner's buffer. */
+ * sends to / receives from every rank, and where its run of every bin starts inside the owner's buffer.  With
+ * stride >= 258, hist[r*stride + 257] = special-initial suffixes rank r classified: they all end up in the tail of the
+ * table, i.e. in the last rank's range, and count towards its quota. */
 int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, int me, uint8_t owner[256], uint64_t *send_cnt,
                    uint64_t *recv_cnt, uint32_t start[256]);
 

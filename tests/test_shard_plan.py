@@ -149,3 +149,25 @@ def test_exchange_between_real_processes_over_gloo(world):
         p.join(timeout=180)
         assert p.exitcode == 0, f"rank process exited with {p.exitcode}"
     assert out.get(timeout=5) == "ok"
+
+
+def test_plan_counts_the_special_tail_in_the_last_ranks_quota(lib):
+    """Rows of 258 words: [257] = special-initial suffixes, which all land in the last range."""
+    nranks = 8
+    rng = np.random.default_rng(3)
+    hist = np.zeros((nranks, 258), np.uint64)
+    hist[:, :256] = rng.integers(900, 1100, size=(nranks, 256))
+    hist[:, 257] = 256 * 1000 // 20  # 5 % of the suffixes start with a special
+    h = np.ascontiguousarray(hist)
+    owner = np.zeros(256, np.uint8)
+    send, recv = np.zeros(nranks, np.uint64), np.zeros(nranks, np.uint64)
+    start = np.zeros(256, np.uint32)
+    loads = []
+    for me in range(nranks):
+        rc = lib.esa_shard_plan(h.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(258), nranks, me,
+                                owner.ctypes.data_as(ctypes.c_void_p), send.ctypes.data_as(ctypes.c_void_p),
+                                recv.ctypes.data_as(ctypes.c_void_p), start.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        loads.append(int(recv.sum()) + (int(hist[:, 257].sum()) if me == nranks - 1 else 0))
+    fair = sum(loads) / nranks
+    assert max(loads) < 1.05 * fair and min(loads) > 0.95 * fair, loads

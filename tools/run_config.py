@@ -33,8 +33,9 @@ if ngpus == 1:
         esa.upload(tis, sigma)
         for rep in range(2):
             st = esa.construct(k, bench.TABLES)
-        esa.check()
-        out["check"] = "esa_check passed (permutation, order, lcp, bwt on the device)"
+        if os.environ.get("RUN_CONFIG_NO_CHECK") is None:
+            esa.check()
+            out["check"] = "esa_check passed (permutation, order, exact lcp / llv, bwt on the device)"
         t1 = time.time()
         tabs = esa.download()
         out["download_s"] = round(time.time() - t1, 2)
@@ -56,6 +57,9 @@ assert np.array_equal(llv[:, 0], big.astype(np.uint64)) and (len(llv) == 0 or ll
 out["maxbranchdepth"], out["largelcpvalues"] = tabs["maxbranchdepth"], tabs["largelcpvalues"]
 import hashlib
 out["sha"] = {t: hashlib.sha256(np.ascontiguousarray(tabs[t]).tobytes()).hexdigest()[:16] for t in ("suf", "lcp", "llv", "bwt")}
+out["checksums_suf_lcp_bwt_llv_nllv"] = (lambda c: ["%016x" % c[t] for t in ("suf", "lcp", "bwt", "llv")] + [
+    tabs["largelcpvalues"]])(bench.table_checksum(0, suf, tabs["lcp"], tabs["bwt"], tabs["llv"]))
+out["longest"] = tabs["longest"]
 ms = max(s["ms_total"] for s in stats)
 out["ms_build_device"] = round(ms, 2)
 out["Msym_per_s"] = round(n / ms / 1e3, 1)

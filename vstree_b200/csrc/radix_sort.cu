@@ -13,6 +13,7 @@
 //                          (88 warp instructions per 32 pairs): see DESIGN.md section 5 for what was measured.
 // Algorithmic bytes: hist = n*sizeof(key); pass = 2*n*(sizeof(key)+sizeof(value)).
 #include "scan.cuh"
+#include <algorithm>
 
 namespace
 {
@@ -52,11 +53,22 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #ifndef ESA_SORT_XMASK
 #define ESA_SORT_XMASK 1  // ballot loop: peers &= ballot ^ (bit ? 0 : ~0), one LOP3 per bit
 #endif
+#ifndef ESA_SORT_PERSISTENT
+#define ESA_SORT_PERSISTENT 0  // 1: one CTA per slot of the device loops over tile tickets; measured 5 % SLOWER (the
+#endif                         //    hardware starts the next CTA while the last warps of the old one drain)
+#ifndef ESA_SORT_KV64
+#define ESA_SORT_KV64 1  // 32-bit key + value travel through shared memory as ONE 64-bit word: fewer shared-memory
+#endif                   // wavefronts (ncu: the LSU data pipe is the busiest unit, 72 %, 60 % of its wavefronts are
+                         // bank-conflict replays of the scattered tile reorder); measured neutral in time
+#ifndef ESA_SORT_LBK
+#define ESA_SORT_LBK 4  // status words of this many predecessor tiles are fetched per round trip of the look-back walk
+#endif
 #ifndef ESA_SORT_SPIN_NS
 #define ESA_SORT_SPIN_NS 0  // nanosleep while a predecessor tile has not published yet (0: busy spin)
 #endif
 constexpr int SORT_THREADS = ESA_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+template <int ITEMS> constexpr int pass_tile_items() { return SORT_THREADS * ITEMS; }
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_ITEMS = 8;
 // look-back status word: 2 flag bits + 62 value bits (counts reach 2^32 - 2, so 32-bit words with 30 value bits
@@ -199,6 +211,23 @@ radix_scan_kernel(const u32 *__restrict__ hist, u32 *__restrict__ base, u32 npas
 // REMOTE: the pass is the partition step of the sharded build fused with its all-to-all: digit d belongs to rank
 // remote->owner[d] and its run is stored straight into that rank's receive buffers (peer memory over NVLink);
 // base[d] then is the first index of THIS rank's run of digit d inside the owner's buffers.
+#ifdef ESA_SORT_TRACE
+// phase timeline of the pass kernel (tuning builds only): per tile, SM clock at the phase borders as seen by thread 0
+// (warp 0: walks the look-back) and by the last thread (warp 15: reorders at once)
+constexpr int TRACE_SLOTS = 12;
+__device__ u32 g_trace[2 * TRACE_SLOTS * 16384];
+#define TRACE(slot)                                                                                         \
+  do                                                                                                        \
+  {                                                                                                         \
+    if ((tid == 0 || tid == SORT_THREADS - 1) && tile < 16384)                                              \
+    {                                                                                                       \
+      g_trace[(tile * 2 + (tid != 0)) * TRACE_SLOTS + (slot)] = (u32) clock64();                            \
+    }                                                                                                       \
+  } while (0)
+#else
+#define TRACE(slot)
+#endif
+
 template <typename KeyT, bool HAS_VALS, int ITEMS, bool REMOTE = false>
 __global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
 radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u32 *__restrict__ vin,
@@ -206,6 +235,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
                   volatile u64 *status, u32 *ticket, const RadixRemoteDst *__restrict__ remote = nullptr)
 {
   constexpr int TILE = SORT_THREADS * ITEMS;
+  constexpr bool KV64 = ESA_SORT_KV64 && HAS_VALS && sizeof(KeyT) == 4;  // (key, value) as one 64-bit shared-memory word
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT *skeys = (KeyT *) smem_raw;
   u32 *svals = (u32 *) (skeys + TILE);
@@ -224,11 +254,16 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #define DIGIT(k) (REMOTE ? (u32) sowner[digit_of((k), shift, mask)] : digit_of((k), shift, mask))
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u32 *mywc = wc + warp * RADIX;
+#if ESA_SORT_PERSISTENT
+  const u32 ntiles = (u32) (((u64) count + TILE - 1) / TILE);
+  while (true)
+  {
+#endif
   if (tid == 0)
   {
     misc[0] = atomicAdd(ticket, 1u);
   }
-  u32 *mywc = wc + warp * RADIX;
 #pragma unroll
   for (int d = lane; d < RADIX; d += 32)
   {
@@ -243,8 +278,15 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   }
   __syncthreads();
   const u32 tile = misc[0];
-  const u32 tile_base = tile * (u32) TILE;                 // count < 2^30, so this cannot overflow
+#if ESA_SORT_PERSISTENT
+  if (tile >= ntiles)
+  {
+    break;  // the same for every thread of the CTA
+  }
+#endif
+  const u32 tile_base = tile * (u32) TILE;  // < count < 2^32
   const u32 tile_count = min((u32) TILE, count - tile_base);
+  TRACE(0);
 
   // ---- load, warp-striped: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile
   KeyT keys[ITEMS];
@@ -305,6 +347,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     status[(u64) tile * RADIX + tid] = (tile == 0 ? STATUS_PREFIX : STATUS_AGG) | (u64) valid_count;
   }
 #endif
+  TRACE(1);  // keys loaded, early histogram published
   // ---- rank inside the warp: stable in (item, lane) order = memory order
   const u32 lt_mask = (1u << lane) - 1;
   const u32 gt_mask = 0xfffffffeu << lane;  // lanes above mine
@@ -386,7 +429,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #endif
   }
 #endif
+  TRACE(2);  // ranked
   __syncthreads();
+  TRACE(3);  // all warps ranked
   // ---- per digit: tile count, then (after the scan over digits) the first slot of every warp's run
   u32 bcount = 0;
   if (tid < RADIX)
@@ -432,6 +477,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #if ESA_SORT_OVERLAP
   __syncthreads();  // warp offsets visible: warps 8.. reorder right away, warps 0-7 after their look-back
 #endif
+  TRACE(4);  // scanned
   // ---- decoupled look-back, one thread per digit
   if (tid < RADIX)
   {
@@ -452,6 +498,38 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #endif
     if (tile != 0)
     {
+#if ESA_SORT_LBK > 1
+      // The walk is a serial chain across tiles: with one status word per round trip it settles at
+      // (latency until a published prefix is visible) x (round trip) / (gap between the starts of consecutive tiles),
+      // measured 6300 clocks = a quarter of a tile's life (per-phase clock trace).  So every round trip
+      // fetches the words of the next ESA_SORT_LBK predecessors at once and consumes them in order.
+      u32 t = tile - 1;
+      bool found = false;
+      while (!found)
+      {
+        u64 sv[ESA_SORT_LBK];
+#pragma unroll
+        for (int j = 0; j < ESA_SORT_LBK; j++)
+        {
+          const u32 tj = t >= (u32) j ? t - (u32) j : 0u;  // clamped: tile 0 always holds a prefix, the walk ends there
+          sv[j] = status[(u64) tj * RADIX + tid];
+        }
+        u32 used = 0;
+#pragma unroll
+        for (int j = 0; j < ESA_SORT_LBK; j++)
+        {
+          const u32 flag = (u32) (sv[j] >> 62);
+          const bool take = !found && used == (u32) j && flag != 0;
+          if (take)
+          {
+            excl += (u32) (sv[j] & STATUS_VALUE_MASK);
+            used++;
+            found = flag == 2;
+          }
+        }
+        t -= found ? 0u : used;
+      }
+#else
       u32 t = tile - 1;
       while (true)
       {
@@ -470,6 +548,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
         }
         t--;
       }
+#endif
       status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (u64) (excl + cnt);
     }
     digit_start[tid] = dstart;
@@ -478,6 +557,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #if !ESA_SORT_OVERLAP
   __syncthreads();
 #endif
+  TRACE(5);  // walked (warps 0-7)
   // ---- reorder the tile in shared memory
   if (full_tile)
   {
@@ -487,10 +567,16 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     {
       const u32 d = DIGIT(keys[i]);
       const u32 pos = mywc[d] + ranks[i];
-      skeys[pos] = keys[i];
-      if (HAS_VALS)
+      if (KV64)
       {
-        svals[pos] = vp[i * 32];
+        reinterpret_cast<u64 *>(smem_raw)[pos] = (u64) keys[i] | ((u64) vp[i * 32] << 32);
+      } else
+      {
+        skeys[pos] = keys[i];
+        if (HAS_VALS)
+        {
+          svals[pos] = vp[i * 32];
+        }
       }
     }
   } else
@@ -500,15 +586,24 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     {
       const u32 d = DIGIT(keys[i]);
       const u32 pos = mywc[d] + ranks[i];
-      skeys[pos] = keys[i];
-      if (HAS_VALS)
+      const u32 idx = wbase + i * 32 + lane;
+      if (KV64)
       {
-        const u32 idx = wbase + i * 32 + lane;
-        svals[pos] = idx < tile_count ? vin[tile_base + idx] : 0u;
+        const u32 v = idx < tile_count ? vin[tile_base + idx] : 0u;
+        reinterpret_cast<u64 *>(smem_raw)[pos] = (u64) keys[i] | ((u64) v << 32);
+      } else
+      {
+        skeys[pos] = keys[i];
+        if (HAS_VALS)
+        {
+          svals[pos] = idx < tile_count ? vin[tile_base + idx] : 0u;
+        }
       }
     }
   }
+  TRACE(6);  // reordered
   __syncthreads();
+  TRACE(7);  // join
   // ---- write every digit run coalesced
 #pragma unroll
   for (int j = 0; j < ITEMS; j++)
@@ -516,7 +611,21 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
     const u32 p = j * SORT_THREADS + tid;
     if (full_tile || p < tile_count)
     {
-      const KeyT k = skeys[p];
+      KeyT k;
+      u32 v = 0;
+      if (KV64)
+      {
+        const u64 kv = reinterpret_cast<const u64 *>(smem_raw)[p];
+        k = (KeyT) (u32) kv;
+        v = (u32) (kv >> 32);
+      } else
+      {
+        k = skeys[p];
+        if (HAS_VALS)
+        {
+          v = svals[p];
+        }
+      }
       const u32 d = DIGIT(k);
       const u32 g = gbase[d] + p;
       if (REMOTE)
@@ -524,18 +633,23 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
         reinterpret_cast<KeyT *>(remote->keys[d])[g] = k;  // d is the owner rank
         if (HAS_VALS)
         {
-          remote->vals[d][g] = svals[p];
+          remote->vals[d][g] = v;
         }
       } else
       {
         kout[g] = k;
         if (HAS_VALS)
         {
-          vout[g] = svals[p];
+          vout[g] = v;
         }
       }
     }
   }
+  TRACE(8);  // written
+#if ESA_SORT_PERSISTENT
+  __syncthreads();  // the tile's shared memory is dead: the next ticket may overwrite it
+  }
+#endif
   if (REMOTE)
   {
     __threadfence_system();  // the stores crossed NVLink: visible to the owner before this kernel counts as done
@@ -543,9 +657,10 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 #undef DIGIT
 }
 
+
 template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
 {
-  constexpr int TILE = SORT_THREADS * SortTraits<KeyT>::ITEMS;
+  constexpr int TILE = pass_tile_items<SortTraits<KeyT>::ITEMS>();
   return (size_t) TILE * sizeof(KeyT) + (has_vals ? (size_t) TILE * 4 : 0) + (size_t) SORT_WARPS * RADIX * 4
          + 2 * RADIX * 4 + 16 * 4 + RADIX * 4 + (ESA_SORT_MATCH == 1 ? (size_t) SORT_WARPS * RADIX * 4 : 0);
 }
@@ -563,7 +678,7 @@ struct TempLayout
 
 template <typename KeyT> TempLayout temp_layout(u64 n)
 {
-  constexpr u64 TILE = (u64) SORT_THREADS * SortTraits<KeyT>::ITEMS;
+  constexpr u64 TILE = (u64) pass_tile_items<SortTraits<KeyT>::ITEMS>();
   TempLayout L;
   const u64 pim = part_items_max<KeyT>();
   L.parts = (u32) (n == 0 ? 1 : div_up_u64(n, pim));
@@ -588,7 +703,7 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
                     size_t temp_bytes)
 {
   constexpr int ITEMS = SortTraits<KeyT>::ITEMS;
-  constexpr u64 TILE = (u64) SORT_THREADS * ITEMS;
+  constexpr u64 TILE = (u64) pass_tile_items<ITEMS>();
   if (n <= 1 || end_bit <= begin_bit)
   {
     return 0;
@@ -633,6 +748,7 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
       const u64 off = (u64) part * pim;
       const u32 cnt = (u32) (n - off < pim ? n - off : pim);
       const u32 tiles = (u32) div_up_u64(cnt, TILE);
+      const u32 grid = ESA_SORT_PERSISTENT ? min(tiles, (u32) ctx->num_sms * ESA_SORT_MINBLOCKS) : tiles;
       ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 8, s)));
       const u32 *pbase = base + ((u64) part * npass + p) * RADIX;
       u32 *ticket = tickets + (u64) part * npass + p;
@@ -640,15 +756,39 @@ int radix_sort_impl(esa_ctx *ctx, KeyT *ka, KeyT *kb, u32 *va, u32 *vb, u64 n, u
       if (has_vals)
       {
         ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, bytes,
-                   (radix_pass_kernel<KeyT, true, ITEMS><<<tiles, SORT_THREADS, smem, s>>>(
+                   (radix_pass_kernel<KeyT, true, ITEMS><<<grid, SORT_THREADS, smem, s>>>(
                        ksrc + off, kdst, vsrc + off, vdst, cnt, shift, mask, pbase, status, ticket)));
       } else
       {
         ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, bytes,
-                   (radix_pass_kernel<KeyT, false, ITEMS><<<tiles, SORT_THREADS, smem, s>>>(
+                   (radix_pass_kernel<KeyT, false, ITEMS><<<grid, SORT_THREADS, smem, s>>>(
                        ksrc + off, kdst, nullptr, nullptr, cnt, shift, mask, pbase, status, ticket)));
       }
     }
+#ifdef ESA_SORT_TRACE
+    if (p == 0 && n > 50000000 && getenv("ESA_SORT_TRACE_DUMP") != nullptr)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      static std::vector<u32> h(2 * TRACE_SLOTS * 16384);
+      CUDA_CHECK(cudaMemcpyFromSymbol(h.data(), g_trace, h.size() * sizeof(u32)));
+      const u32 ntr = (u32) std::min<u64>(16384, div_up_u64(n, TILE)) - 1;
+      for (int who = 0; who < 2; who++)
+      {
+        double acc[TRACE_SLOTS] = {0};
+        for (u32 t = 300; t < ntr; t++)
+        {
+          const u32 *r = &h[(t * 2 + who) * TRACE_SLOTS];
+          for (int k = 1; k <= 8; k++)
+          {
+            acc[k] += (double) (u32) (r[k] - r[k - 1]);
+          }
+        }
+        fprintf(stderr, "TRACE %s: load+hist %.0f rank %.0f wait1 %.0f scan %.0f walk %.0f reorder %.0f wait2 %.0f write %.0f clocks (avg over %u tiles)\n",
+                who ? "warp15" : "warp0 ", acc[1] / (ntr - 300), acc[2] / (ntr - 300), acc[3] / (ntr - 300), acc[4] / (ntr - 300),
+                acc[5] / (ntr - 300), acc[6] / (ntr - 300), acc[7] / (ntr - 300), acc[8] / (ntr - 300), ntr - 300);
+      }
+    }
+#endif
     KeyT *kt = ksrc;
     ksrc = kdst;
     kdst = kt;
@@ -689,7 +829,7 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes)
 {
   constexpr int ITEMS = SortTraits<u32>::ITEMS;
-  constexpr u64 TILE = (u64) SORT_THREADS * ITEMS;
+  constexpr u64 TILE = (u64) pass_tile_items<ITEMS>();
   if (n == 0)
   {
     return;
@@ -721,10 +861,11 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
     const u64 off = (u64) part * pim;
     const u32 cnt = (u32) (n - off < pim ? n - off : pim);
     const u32 tiles = (u32) div_up_u64(cnt, TILE);
+    const u32 grid = ESA_SORT_PERSISTENT ? min(tiles, (u32) ctx->num_sms * ESA_SORT_MINBLOCKS) : tiles;
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 8, s)));
     // algorithmic bytes: one local read, one store into peer memory
     ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 2.0 * cnt * 8,
-               (radix_pass_kernel<u32, true, ITEMS, true><<<tiles, SORT_THREADS, smem, s>>>(
+               (radix_pass_kernel<u32, true, ITEMS, true><<<grid, SORT_THREADS, smem, s>>>(
                    keys + off, nullptr, vals + off, nullptr, cnt, begin_bit, mask, base + (u64) part * RADIX, status,
                    tickets + part, d_remote)));
   }
