@@ -123,7 +123,7 @@ typedef struct
   double ms_derive;          /* finalize (lcp8, llv, bwt, suf64), bck, sti1 */
   uint32_t h0;               /* symbols per initial key */
   uint32_t rounds;           /* prefix-doubling rounds after the initial sort */
-  uint32_t lcp_path;         /* 0 no lcp, 1 direct comparison in suffix-array order, 2 text-order plcp */
+  uint32_t lcp_path;         /* 0 no lcp, 1 direct comparison in suffix-array order, 2 text-order plcp, 3 direct + text-order for the deep slots */
   uint32_t comm_direct;      /* sharded builds: 1 when the ranks exchanged through mapped peer memory, 0 through messages */
   uint64_t active_sum;       /* sum over rounds of the active-set sizes */
   uint64_t active_first;     /* active-set size of round 1 */

@@ -53,6 +53,20 @@ def main():
             for sname in ("longest", "maxbranchdepth", "largelcpvalues"):
                 assert got[sname] == want[sname], f"{name}: {sname}"
             esa.check()
+    ranks = int(os.environ.get("VARIANT_RANKS", "0"))
+    if ranks > 1:
+        # the same variant on a sharded context (ranks share device 0 through the in-process transport)
+        from vstree_b200.capi import EsaGroup
+        with EsaGroup([0] * ranks) as grp:
+            for name, tis, sigma, k in inputs():
+                if k is None:
+                    k = max(1, int(lib.oracle_maximalprefixlength(sigma, len(tis))) - 1)
+                got, st = grp.build(tis, sigma, k, tables=("suf", "lcp", "bwt", "bck"))
+                want = ou.oracle_build(tis, sigma, k)
+                for t in ("suf", "lcp", "llv", "bwt", "bck"):
+                    assert np.array_equal(got[t], np.asarray(want[t])), f"{name} on {ranks} ranks: {t} differs from the oracle"
+                for sname in ("longest", "maxbranchdepth", "largelcpvalues"):
+                    assert got[sname] == want[sname], f"{name} on {ranks} ranks: {sname}"
     print("VARIANT-OK")
 
 

@@ -284,7 +284,8 @@ size_t arena_estimate(u64 n, int nranks)
     const size_t cap = (size_t) (0.92 * (double) total_b);
     return want <= cap ? want : (floor_b <= cap ? cap : floor_b);
   }
-  // sharded: replicated text 1 + packed text 0.4 + dense rank array 4 + bck (with all-reduce scratch) 2.5, plus the
+  // sharded: replicated text 1 + packed text 0.6 + dense rank array 4 + text-order lcp array of the deep slots 4 + bck
+  // (with all-reduce scratch) 2.5, plus the
   // per-range share of everything else with head room for uneven ranges (ESA_SHARD_SLACK percent, default 60)
   u64 slack = 60;
   if (const char *e = getenv("ESA_SHARD_SLACK"))
@@ -292,7 +293,7 @@ size_t arena_estimate(u64 n, int nranks)
     slack = (u64) atoi(e);
   }
   const u64 share = N / (u64) nranks + 1;
-  return (size_t) (8 * N) + (size_t) (56 * share * (100 + slack) / 100) + ((size_t) 256 << 20);
+  return (size_t) (12 * N) + (size_t) (56 * share * (100 + slack) / 100) + ((size_t) 256 << 20);
 }
 
 bool is_sharded(const esa_ctx *ctx) { return ctx->comm != nullptr && ctx->comm->nranks > 1; }
@@ -629,7 +630,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   ctx->d_suf64 = nullptr;
   ctx->d_lcp = ctx->d_bwt = ctx->d_sti1 = nullptr;
   ctx->d_bck = ctx->d_llv = ctx->d_sti64 = ctx->d_skp = nullptr;
-  ctx->d_plcpv = ctx->d_lcpfull = nullptr;
+  ctx->d_plcpv = ctx->d_lcpfull = ctx->d_deepv = nullptr;
   ctx->nllv = ctx->maxbranchdepth = ctx->longest = 0;
   ctx->prof.reset();
   ctx->prof.enabled = stats != nullptr;
@@ -716,20 +717,42 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     }
     ctx->lcp_work_estimate = work;
   }
+  // lcp: direct comparison in suffix-array order (lcp_direct.cu) for every slot except the DEEP ones -- slots that a
+  // refinement round with a start depth of at least ESA_LCP_DEEP symbols (default 1024) split from their predecessor.
+  // Those take their value from the text-order array V, computed for the deep stretches of the text only (lcp.cu,
+  // compute_plcp_deep): the cost of a slot no longer grows with its lcp value (long exact tandem arrays), and inputs
+  // without deep slots never see the text-order machinery.  ESA_LCP_MODE=plcp keeps the full text-order path of round 1
+  // (one GPU; tests compare the paths), ESA_LCP_MODE=direct compares everything directly.
+  u32 deep_round = 255;
+  if (want_lcp && ctx->lcp_mode != 1)
+  {
+    static const u32 deep_lb = [] {
+      const char *e = getenv("ESA_LCP_DEEP");
+      return (u32) (e != nullptr ? atoi(e) : 1024);
+    }();
+    const u32 want_depth = (ctx->lcp_mode == 2 && sharded) ? 1u : deep_lb;
+    for (u32 t = 1; t <= so.rounds && t < 255; t++)
+    {
+      if (round_start_depth(ctx->sched, t) >= want_depth)
+      {
+        deep_round = t;
+        break;
+      }
+    }
+  }
   if (want_lcp)
   {
-    use_plcp = ctx->lcp_mode == 2 || (ctx->lcp_mode == 0 && ctx->lcp_work_estimate > 48 * N);
+    use_plcp = ctx->lcp_mode == 2 && !sharded;
   }
+  ctx->d_deepv = nullptr;
   if (use_plcp)
   {
     ctx->d_plcpv = ar.alloc<u32>(N + 64);
-    if (sharded)
-    {
-      compute_plcp_sharded(ctx, ctx->comm, ctx->d_plcpv, halo);
-    } else
-    {
-      compute_plcp(ctx, ctx->d_plcpv);
-    }
+    compute_plcp(ctx, ctx->d_plcpv);
+  } else if (want_lcp && deep_round != 255)
+  {
+    ctx->d_deepv = ar.alloc<u32>(N + 64);
+    compute_plcp_deep(ctx, sharded ? ctx->comm : nullptr, ctx->d_deepv, halo, deep_round);
   }
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_c, s));
   if (!sharded)
@@ -739,7 +762,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       finalize_tables(ctx, table_demand, ctx->d_plcpv, N, 0);
     } else
     {
-      finalize_tables_direct(ctx, table_demand, N, 0, 0);
+      finalize_tables_direct(ctx, table_demand, N, 0, 0, ctx->d_deepv, deep_round);
     }
   } else
   {
@@ -748,12 +771,9 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       ctx->d_suf64 = (table_demand & ESA_SUFTAB) ? ar.alloc<u64>(4) : nullptr;
       ctx->d_bwt = (demand & ESA_BWTTAB) ? ar.alloc<u8>(4) : nullptr;
       ctx->d_lcp = want_lcp ? ar.alloc<u8>(4) : nullptr;
-    } else if (use_plcp)
-    {
-      finalize_tables(ctx, table_demand, ctx->d_plcpv, ctx->shard_count, ctx->shard_first);
     } else
     {
-      finalize_tables_direct(ctx, table_demand, ctx->shard_count, ctx->shard_first, halo);
+      finalize_tables_direct(ctx, table_demand, ctx->shard_count, ctx->shard_first, halo, ctx->d_deepv, deep_round);
     }
     // scalars of the whole table
     u64 sc[2] = {ctx->maxbranchdepth, ctx->longest}, all[2 * ESA_MAX_RANKS];
@@ -793,7 +813,7 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
     stats->ms_derive = ms;
     stats->h0 = so.h0;
     stats->rounds = so.rounds;
-    stats->lcp_path = want_lcp ? (use_plcp ? 2 : 1) : 0;
+    stats->lcp_path = want_lcp ? (use_plcp ? 2 : (ctx->d_deepv != nullptr ? 3 : 1)) : 0;
     stats->active_sum = so.active_sum;
     stats->active_first = so.active_first;
     stats->device_bytes_peak = ar.peak;

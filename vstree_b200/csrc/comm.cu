@@ -165,29 +165,6 @@ __global__ void group_reduce_kernel(PeerPtrs peers, int nranks, u64 *__restrict_
   }
 }
 
-struct PeerPtrs32
-{
-  u32 *p[ESA_MAX_RANKS];
-};
-
-// chunk [begin, end) of the local buffer := min over all ranks' buffers
-__global__ void group_min_chunk_kernel(PeerPtrs32 peers, int nranks, int me, u64 begin, u64 end)
-{
-  for (u64 i = begin + (u64) blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (u64) gridDim.x * blockDim.x)
-  {
-    u32 acc = peers.p[me][i];
-    for (int r = 0; r < nranks; r++)
-    {
-      if (r != me)
-      {
-        const u32 v = __ldcv(peers.p[r] + i);
-        acc = v < acc ? v : acc;
-      }
-    }
-    peers.p[me][i] = acc;
-  }
-}
-
 // publish -> barrier -> pull -> barrier.  The pulled buffers must be complete: every rank drains its stream first.
 template <typename Pull> void group_round(esa_ctx *ctx, esa_comm *comm, const void *ptr, const u64 *off, const u64 *cnt, Pull &&pull)
 {
@@ -575,51 +552,6 @@ void comm_allgather_bytes(esa_ctx *ctx, esa_comm *comm, u8 *d_buf, size_t slice)
   ESA_LAUNCH(ctx, ESA_K_COMM, (double) slice * (G - 1),
              NCCL_CHECK(nccl().AllGather(d_buf + (size_t) me * slice, d_buf, slice, ncclUint8, (ncclComm_t) comm->nccl,
                                          ctx->stream)));
-}
-
-void comm_allreduce_min_u32(esa_ctx *ctx, esa_comm *comm, u32 *d_buf, size_t count)
-{
-  if (comm->nranks == 1 || count == 0)
-  {
-    return;
-  }
-  comm->bytes_sent += (u64) count * 4 * 2 * (comm->nranks - 1) / comm->nranks;
-  if (comm->group != nullptr)
-  {
-    // reduce-scatter then all-gather, both in place: rank r owns chunk r.  Phase 1 only writes the own chunk of the
-    // own buffer (nobody else reads that chunk in phase 1), phase 2 only reads the owners' finished chunks.
-    const int G = comm->nranks, me = comm->rank;
-    const u64 chunk = div_up_u64(count, (u64) G);
-    group_round(ctx, comm, d_buf, nullptr, nullptr, [&](esa_group *g) {
-      PeerPtrs32 pp;
-      for (int r = 0; r < G; r++)
-      {
-        pp.p[r] = (u32 *) g->slot[r].ptr;
-      }
-      const u64 b = min((u64) count, (u64) me * chunk), e = min((u64) count, (u64) (me + 1) * chunk);
-      if (e > b)
-      {
-        const u32 grid = (u32) min((u64) ctx->num_sms * 16, div_up_u64(e - b, 256));
-        ESA_LAUNCH(ctx, ESA_K_COMM, 4.0 * (e - b) * G,
-                   (group_min_chunk_kernel<<<grid, 256, 0, ctx->stream>>>(pp, G, me, b, e)));
-      }
-    });
-    group_round(ctx, comm, d_buf, nullptr, nullptr, [&](esa_group *g) {
-      ESA_LAUNCH(ctx, ESA_K_COMM, 4.0 * count, {
-        for (int r = 0; r < G; r++)
-        {
-          const u64 b = min((u64) count, (u64) r * chunk), e = min((u64) count, (u64) (r + 1) * chunk);
-          if (r != me && e > b)
-          {
-            copy_words(ctx, d_buf + b, (const u32 *) g->slot[r].ptr + b, e - b);
-          }
-        }
-      });
-    });
-    return;
-  }
-  ESA_LAUNCH(ctx, ESA_K_COMM, 4.0 * count * 2,
-             NCCL_CHECK(nccl().AllReduce(d_buf, d_buf, count, ncclUint32, ncclMin, (ncclComm_t) comm->nccl, ctx->stream)));
 }
 
 void comm_alltoallv_u32(esa_ctx *ctx, esa_comm *comm, const u32 *d_send, const u64 *send_off, const u64 *send_cnt,

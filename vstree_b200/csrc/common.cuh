@@ -222,6 +222,7 @@ struct esa_ctx
   u64 *d_sti64 = nullptr;  // [N]
   u64 *d_skp = nullptr;    // [N]
   u32 *d_plcpv = nullptr;  // [N] V[i] = i + PLCP[i]
+  u32 *d_deepv = nullptr;  // [N] hybrid lcp: V[i] for the deep positions only (undefined elsewhere)
   u32 *d_lcpfull = nullptr;  // direct lcp path: exact values of the entries whose lcp8 is 255
   u64 nllv = 0, maxbranchdepth = 0, longest = 0;
   // sharded build: this rank holds suffix-array entries [shard_first, shard_first + shard_count) in d_sa, d_suf64,
@@ -346,12 +347,15 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
 
 // lcp.cu: V[i] = i + PLCP[i] for all text positions (ctx->d_plcpv)
 void compute_plcp(esa_ctx *ctx, u32 *d_v);
-void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev);
+// hybrid lcp: V[i] only for the positions whose slot was split off in a refinement round >= deep_round (comm may be null)
+void compute_plcp_deep(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev, u32 deep_round);
 
 // derive.cu
 void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base);
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev);  // lcp_direct.cu
+// lcp_direct.cu; deep_v / deep_round: slots split off in a round >= deep_round take their lcp from deep_v (hybrid)
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev, const u32 *deep_v = nullptr,
+                            u32 deep_round = 255);
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 void compute_skp(esa_ctx *ctx, const u32 *d_v, const u32 *d_lcpfull);  // skp.cu
 int run_checks(esa_ctx *ctx, std::string &msg);

@@ -142,11 +142,15 @@ __global__ void __launch_bounds__(SCAN1_THREADS) last_valid_scan_kernel(u32 *til
 }
 
 __global__ void __launch_bounds__(PL_THREADS)
-plcp_fill_kernel(u32 *__restrict__ v, u64 N, const u32 *__restrict__ tile_carry)
+plcp_fill_kernel(u32 *__restrict__ v, u64 N, const u32 *__restrict__ tile_carry, const u8 *__restrict__ tile_flag = nullptr)
 {
   __shared__ u32 sv[PL_TILE];
   __shared__ u32 scratch[PL_THREADS / 32];
   __shared__ u32 sincl[PL_THREADS];
+  if (tile_flag != nullptr && tile_flag[blockIdx.x] == 0)
+  {
+    return;  // no deep position in this tile (hybrid lcp): nothing to fill
+  }
   const u64 tile_base = (u64) blockIdx.x * PL_TILE;
 #pragma unroll
   for (int j = 0; j < PL_ITEMS; j++)
@@ -197,42 +201,20 @@ plcp_fill_kernel(u32 *__restrict__ v, u64 N, const u32 *__restrict__ tile_carry)
   }
 }
 
-// ---- sharded builds: the irreducible values of a rank's OWN suffixes, visited in suffix-array order ----
-// v is the dense text-order array, pre-set to MARK; after a minimum all-reduce over the ranks it holds every irreducible
-// value and the text-order fill below completes it on every rank.  hround gives the doubling depth at which a slot
-// split from its predecessor: the comparison starts there (lcp.cu header of lcp_direct.cu).
-template <typename Text>
-__global__ void __launch_bounds__(256)
-plcp_irreducible_shard_kernel(Text text, u64 count, const u32 *__restrict__ sa, const u8 *__restrict__ hround, DepthSched sched,
-                              u64 index_base, u32 halo_prev, u32 *__restrict__ v)
-{
-  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= count)
-  {
-    return;
-  }
-  const u32 i = sa[r];
-  if (index_base + r == 0)
-  {
-    v[i] = i;  // lcp of the first suffix is 0 (bese.c:639)
-    return;
-  }
-  const u32 j = r > 0 ? sa[r - 1] : halo_prev;
-  const u32 ci = text.before(i), cj = text.before(j);
-  if (ci == cj && ci < ESA_WILDCARD)
-  {
-    return;  // reducible: takes the value of its left neighbour in text order
-  }
-  const u32 hr = hround != nullptr ? hround[r] : 0u;
-  const u32 lb = hr ? round_start_depth(sched, hr) : 0u;
-  v[i] = i + text.lcp(i, j, lb);
-}
-
 // value of the last irreducible position of every tile (MARK if none), for the text-order fill
-__global__ void __launch_bounds__(PL_THREADS) plcp_tile_last_kernel(const u32 *__restrict__ v, u64 N, u32 *__restrict__ tile_last)
+__global__ void __launch_bounds__(PL_THREADS)
+plcp_tile_last_kernel(const u32 *__restrict__ v, u64 N, u32 *__restrict__ tile_last, const u8 *__restrict__ tile_flag = nullptr)
 {
   __shared__ u32 red_idx[PL_THREADS / 32];
   __shared__ u32 red_val[PL_THREADS / 32];
+  if (tile_flag != nullptr && tile_flag[blockIdx.x] == 0)
+  {
+    if (threadIdx.x == 0)
+    {
+      tile_last[blockIdx.x] = MARK;
+    }
+    return;
+  }
   const u64 tile_base = (u64) blockIdx.x * PL_TILE;
   u32 last_idx = 0, last_val = MARK;
 #pragma unroll
@@ -280,39 +262,137 @@ __global__ void __launch_bounds__(PL_THREADS) plcp_tile_last_kernel(const u32 *_
   }
 }
 
+
+// ---- hybrid lcp: the text-order machinery for the DEEP entries only ----
+// A slot that a refinement round t >= deep_round split from its predecessor has an lcp value of at least
+// round_start_depth(t) symbols; comparing such pairs directly costs up to that many symbols per entry (long exact tandem
+// arrays: hundreds of thousands), so they take their value from V[i] = i + PLCP[i] instead.  The set of deep positions is
+// closed under "left neighbour of a reducible member" (PLCP[i-1] = PLCP[i] + 1 is deeper still), so the last-valid fill
+// works on the deep stretches alone: no memset of V, no work in tiles without a deep position, and only the
+// IRREDUCIBLE deep positions are ever compared.  Everything else keeps the direct comparison of lcp_direct.cu, whose
+// cost per entry is now bounded by the depth of round deep_round.
+// list (sharded builds): (position, value) pairs of this rank's deep slots, for the other ranks.
+template <typename Text>
+__global__ void __launch_bounds__(256)
+plcp_deep_kernel(Text text, u64 count, const u32 *__restrict__ sa, const u8 *__restrict__ hround, DepthSched sched,
+                 u32 deep_round, u32 halo_prev, u32 *__restrict__ v, u8 *__restrict__ tile_flag, u32 *__restrict__ list,
+                 unsigned long long *__restrict__ list_count)
+{
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 hr = r < count ? hround[r] : 0u;
+  const bool deep = hr >= deep_round;
+  u32 i = 0, val = MARK;
+  if (deep)
+  {
+    i = sa[r];
+    const u32 j = r > 0 ? sa[r - 1] : halo_prev;  // hr > 0: the slot has a predecessor in its old group
+    const u32 ci = text.before(i), cj = text.before(j);
+    if (!(ci == cj && ci < ESA_WILDCARD))
+    {
+      val = i + text.lcp(i, j, round_start_depth(sched, hr));
+    }
+    v[i] = val;
+    tile_flag[i / PL_TILE] = 1;
+  }
+  if (list != nullptr)
+  {
+    const u32 bal = __ballot_sync(FULL_MASK, deep);
+    if (bal != 0)
+    {
+      const int lane = threadIdx.x & 31, leader = __ffs((int) bal) - 1;
+      unsigned long long base = 0;
+      if (lane == leader)
+      {
+        base = atomicAdd(list_count, (unsigned long long) __popc(bal));
+      }
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (deep)
+      {
+        const u64 o = base + __popc(bal & ((1u << lane) - 1));
+        list[2 * o] = i;
+        list[2 * o + 1] = val;
+      }
+    }
+  }
+}
+
+__global__ void plcp_deep_scatter_kernel(const u32 *__restrict__ list, u64 pairs, u32 *__restrict__ v, u8 *__restrict__ tile_flag)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < pairs)
+  {
+    const u32 i = list[2 * t];
+    v[i] = list[2 * t + 1];
+    tile_flag[i / PL_TILE] = 1;
+  }
+}
+
 }  // namespace
 
-// sharded text-order plcp: every rank ends up with the complete V array
-void compute_plcp_sharded(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev)
+// V[i] for every deep position i (see above); comm == nullptr on one GPU.  d_v needs no initialisation.
+void compute_plcp_deep(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev, u32 deep_round)
 {
-  const u64 n = ctx->n, N = n + 1;
+  const u64 N = ctx->n + 1;
   cudaStream_t s = ctx->stream;
+  Arena &ar = ctx->arena;
   const u32 tiles = (u32) div_up_u64(N, PL_TILE);
-  u32 *tile_last = ctx->arena.alloc<u32>(tiles);
-  ESA_LAUNCH(ctx, ESA_K_MEMOP, 4.0 * N, CUDA_CHECK(cudaMemsetAsync(d_v, 0xff, (N + 64) * sizeof(u32), s)));
+  u32 *tile_last = ar.alloc<u32>(tiles);
+  u8 *tile_flag = ar.alloc<u8>(tiles + 16);
+  unsigned long long *d_cnt = (unsigned long long *) ar.alloc<u64>(2);
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(tile_flag, 0, tiles + 16, s)));
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(u64), s)));
   const u64 count = ctx->shard_count;
+  const bool sharded = comm != nullptr && comm->nranks > 1;
+  // sharded: my pairs go to a list sized for the worst case of this range; it lives at the top of the scratch region
+  const size_t mark = ar.mark();
+  u32 *list = sharded ? ar.alloc<u32>(2 * count + 2) : nullptr;
   if (count > 0)
   {
     const u32 grid = (u32) div_up_u64(count, 256);
     if (ctx->d_pk != nullptr)
     {
       TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
-      ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
-                 (plcp_irreducible_shard_kernel<TextPacked2><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
-                                                                                   ctx->sched, ctx->shard_first, halo_prev, d_v)));
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 5.0 * count,
+                 (plcp_deep_kernel<TextPacked2><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround, ctx->sched,
+                                                                      deep_round, halo_prev, d_v, tile_flag, list, d_cnt)));
     } else
     {
       TextBytes text{ctx->d_tis};
-      ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * count,
-                 (plcp_irreducible_shard_kernel<TextBytes><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround,
-                                                                                 ctx->sched, ctx->shard_first, halo_prev, d_v)));
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 5.0 * count,
+                 (plcp_deep_kernel<TextBytes><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround, ctx->sched,
+                                                                    deep_round, halo_prev, d_v, tile_flag, list, d_cnt)));
     }
   }
-  comm_allreduce_min_u32(ctx, comm, d_v, N);
-  ESA_LAUNCH(ctx, ESA_K_PLCP, 4.0 * N, (plcp_tile_last_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last)));
+  if (sharded)
+  {
+    read_back_u64(ctx, d_cnt, 1, 8);
+    const u64 mine = ctx->h_scalars[8];
+    u64 all[ESA_MAX_RANKS], off[ESA_MAX_RANKS], cnt[ESA_MAX_RANKS], total = 0;
+    comm_exchange_host_u64(ctx, comm, &mine, 1, all);
+    for (int r = 0; r < comm->nranks; r++)
+    {
+      off[r] = 2 * total;
+      cnt[r] = 2 * all[r];
+      total += all[r];
+    }
+    if (total > 0)
+    {
+      u32 *gathered = ar.alloc<u32>(2 * total + 2);
+      comm_allgatherv_u32(ctx, comm, list, gathered, off, cnt);
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 12.0 * total,
+                 (plcp_deep_scatter_kernel<<<(u32) div_up_u64(total, 256), 256, 0, s>>>(gathered, total, d_v, tile_flag)));
+    }
+  }
+  ESA_LAUNCH(ctx, ESA_K_PLCP, (double) tiles, (plcp_tile_last_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last, tile_flag)));
   ESA_LAUNCH(ctx, ESA_K_MISC, 0, (last_valid_scan_kernel<<<1, SCAN1_THREADS, 0, s>>>(tile_last, tiles)));
-  ESA_LAUNCH(ctx, ESA_K_PLCP, 8.0 * N, (plcp_fill_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last)));
+  ESA_LAUNCH(ctx, ESA_K_PLCP, (double) tiles, (plcp_fill_kernel<<<tiles, PL_THREADS, 0, s>>>(d_v, N, tile_last, tile_flag)));
+  CUDA_CHECK(cudaStreamSynchronize(s));  // the list buffers are released below
+  ar.rewind(mark);
 }
+
+namespace
+{
+}  // namespace
 
 void compute_plcp(esa_ctx *ctx, u32 *d_v)
 {

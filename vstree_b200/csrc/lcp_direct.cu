@@ -103,7 +103,7 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
                        const u8 *__restrict__ hround, DepthSched sched, bool want_lcp, u8 *__restrict__ lcp8,
                        u32 *__restrict__ lcpfull, u8 *__restrict__ bwt, u64 *__restrict__ suf64,
                        u32 *__restrict__ tile_large, unsigned long long *__restrict__ scalars, u64 index_base,
-                       u32 halo_prev)
+                       u32 halo_prev, const u32 *__restrict__ deep_v, u32 deep_round)
 {
   // index_base: global suffix-array index of local entry 0 (0 on one GPU); halo_prev: the suffix in front of the
   // shard (last entry of the previous shard), used for the lcp of local entry 0
@@ -166,7 +166,10 @@ finalize_direct_kernel(Text text, const u8 *__restrict__ tis, u64 N, const u32 *
         {
           bb[q] = s[q + 1] > 0 ? (u8) pr[q + 1].before : (u8) ESA_UNDEFBWTCHAR;
         }
-        if (want_lcp && q < cnt && index_base + r0 + q > 0)
+        if (want_lcp && q < cnt && hr[q] >= deep_round)
+        {
+          l[q] = deep_v[s[q + 1]] - s[q + 1];  // deep slot: the text-order value (lcp.cu, compute_plcp_deep)
+        } else if (want_lcp && q < cnt && index_base + r0 + q > 0)
         {
           const u32 lb = hr[q] ? round_start_depth(sched, hr[q]) : 0u;
           // pairs split by a doubling round agree on lb symbols: start there (at most lb/WINDOW + 1 steps)
@@ -275,7 +278,8 @@ void pack_text(esa_ctx *ctx)
 }
 
 // lcp (when demanded) by direct comparison; fills d_lcp, d_llv, d_bwt, d_suf64, maxbranchdepth, longest, nllv
-void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev)
+void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev, const u32 *deep_v,
+                            u32 deep_round)
 {
   // count entries of ctx->d_sa (the whole table on one GPU, this rank's shard otherwise)
   const u64 N = count;
@@ -310,14 +314,14 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base,
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextPacked2><<<tiles, FN_THREADS, 0, s>>>(
                    text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
-                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
+                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev, deep_v, deep_v != nullptr ? deep_round : 255u)));
   } else
   {
     TextBytes text{ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextBytes><<<tiles, FN_THREADS, 0, s>>>(
                    text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
-                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev)));
+                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev, deep_v, deep_v != nullptr ? deep_round : 255u)));
   }
   if (want_lcp)
   {
