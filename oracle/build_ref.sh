@@ -44,12 +44,68 @@ build_vmatch() {
   gcc -o "$OUT/vmatch.x" "$O/main_vmatch.o" $L $L "$O/bzstub.o" -lz -lm -ldl -lpthread
   rm -rf "$O"
 }
+# The reference's OTHER callers of the sorter (mkrcidx, mkdna6idx, mkvram: src/Mkvtree/Makefile:144-153), unmodified, and
+# the "gpu family" next to them (oracle/_ref/gpu/): the very same reference objects, except that bese.o, besespecial.o
+# and ppsort.o -- the suffix sorter -- are replaced by integration/besegpu.c, which defines besesuffixsort[special] on
+# top of libvstree_b200 (esa_build).  mkvtree, mkvram, mkrcidx, mkdna6idx (callmkvtree[generic]) and vmatch's on-the-fly
+# query index (completevirtualtree) then build on the GPU: SURVEY.md 8f row 3, tests/test_gpu_refseam.py.
+build_families() {
+  local O="$OUT/objfam" ROOT
+  ROOT="$(cd "$HERE/.." && pwd)"
+  [ -f "$ROOT/vstree_b200/lib/libvstree_b200.so" ] || { echo "build_ref.sh: libvstree_b200.so not built yet: gpu family skipped" >&2; return 0; }
+  mkdir -p "$O" "$OUT/gpu"
+  local CV="$CF -I$S/Vmengine -I$S/Vmatch"
+  local LIST="vmatch parsevm optstring procargs runself runquery mlendistrib mapdemand procmatch queryindex verifysub lrseq echomatch substpos markmat nomatch showmasked vmcluster assigndig explain detmatch opensel vmdbfunc parsedbms chncallparse chainvm chainof initpost matchlenparm xmlfunc vplugin-open vmotif-start cpridx-start parsepp parsequery parsedbcl keepflags parsemcl cluedist matchclust clpos allmclust threadchain procfinal mokay vmatch.mn"
+  ( for f in "$S"/kurtz-basic/*.c; do echo "gcc $CF -c $f -o $O/kb_$(basename "$f" .c).o"; done
+    for f in "$S"/kurtz/*.c;       do echo "gcc $CF -c $f -o $O/k_$(basename "$f" .c).o"; done
+    for f in mkvtree mkvprocess mkvinput cprsuf remainsort; do
+      echo "gcc $CF -DWITHLCP -c $S/Mkvtree/$f.c -o $O/m_$f.o"; done
+    for f in bese ppsort; do echo "gcc $CF -DWITHLCP -c $S/Mkvtree/$f.c -o $O/s_$f.o"; done
+    echo "gcc $CF -DWITHLCP -DSPECIAL -c $S/Mkvtree/bese.c -o $O/s_besespecial.o"
+    for f in mkvfile mkvram mkrcidx mkdna6idx; do echo "gcc $CF -DWITHLCP -c $S/Mkvtree/$f.c -o $O/main_$f.o"; done
+    echo "gcc $CF -DWITHLCP -I$S/Mkvtree -I$ROOT/include -Wall -c $ROOT/integration/besegpu.c -o $O/g_besegpu.o"
+    for f in "$S"/Vmengine/*.c; do b=$(basename "$f" .c)
+      case $b in vmatfind|vmatcount|vmatgen) ;; *) echo "gcc $CV -c $f -o $O/e_$b.o";; esac; done
+    for a in 4 12 21 31 42 53 66; do
+      echo "gcc $CV -DALPHABETSIZE=$a -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind$a.o"
+      echo "gcc $CV -DALPHABETSIZE=$a -c $S/Vmengine/vmatcount.c -o $O/e_vmatcount$a.o"; done
+    echo "gcc $CV -DDYNAMICALPHABET -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind-dyn.o"
+    echo "gcc $CV -DDYNAMICALPHABET -DESASTREAMACCESS -c $S/Vmengine/vmatfind.c -o $O/e_vmatfind-strm.o"
+    for b in $LIST; do echo "gcc $CV -c $S/Vmatch/$b.c -o $O/v_$b.o"; done
+    echo "gcc $CF -c $HERE/stub/bzstub.c -o $O/bzstub.o"
+  ) | xargs -P "$J" -I{} sh -c "{}"
+  ar rcs "$O/libkb.a" "$O"/kb_*.o
+  ar rcs "$O/libk.a" "$O"/k_*.o
+  ar rcs "$O/libm.a" "$O"/m_*.o          # libmkvtree WITHOUT a sorter
+  ar rcs "$O/libsort_ref.a" "$O"/s_*.o   # the reference's sorter
+  ar rcs "$O/libe.a" "$O"/e_*.o
+  mv "$O/v_vmatch.mn.o" "$O/main_vmatch.o"
+  ar rcs "$O/libv.a" "$O"/v_*.o
+  local KL="$O/libk.a $O/libkb.a $O/libk.a $O/libkb.a $O/bzstub.o -lz -lm -ldl -lpthread"
+  local GPU="$O/g_besegpu.o -L$ROOT/vstree_b200/lib -lvstree_b200"
+  local RPATH='-Wl,-rpath,$ORIGIN/../../../vstree_b200/lib'   # oracle/_ref/gpu/ -> vstree_b200/lib, wherever the tree lies
+  for t in mkvram mkrcidx mkdna6idx; do
+    gcc -o "$OUT/$t.x" "$O/main_$t.o" "$O/libm.a" "$O/libsort_ref.a" "$O/libm.a" $KL
+    gcc -o "$OUT/gpu/$t.x" "$O/main_$t.o" "$O/libm.a" $GPU "$RPATH" "$O/libm.a" $KL
+  done
+  gcc -o "$OUT/gpu/mkvtree.x" "$O/main_mkvfile.o" "$O/libm.a" $GPU "$RPATH" "$O/libm.a" $KL
+  local L="$O/libv.a $O/libe.a $O/libm.a"
+  gcc -o "$OUT/gpu/vmatch.x" "$O/main_vmatch.o" $L $L $GPU "$RPATH" "$O/libm.a" $KL
+  rm -rf "$O"
+}
 CF="-D_LARGEFILE_SOURCE -D_FILE_OFFSET_BITS=64 -O3 -m64 -fno-stack-protector -U_FORTIFY_SOURCE -D_GNU_SOURCE -DWITHSYSCONF -I$HERE/stub -I$S/include -w"
 J=$(nproc)
+ROOT_="$(cd "$HERE/.." && pwd)"
+families_stale() {  # rebuild when a binary is missing or integration/besegpu.c is newer
+  [ ! -x "$OUT/gpu/vmatch.x" ] || [ ! -x "$OUT/gpu/mkvtree.x" ] || [ ! -x "$OUT/mkrcidx.x" ] || [ "$ROOT_/integration/besegpu.c" -nt "$OUT/gpu/mkvtree.x" ]
+}
 if [ -x "$OUT/mkvtree.x" ] && [ -x "$OUT/mkvtree.dbg.x" ] && [ "${1:-}" != "--force" ]; then
   if [ ! -x "$OUT/vmatch.x" ]; then
     mkdir -p "$OUT"
     build_vmatch || echo "build_ref.sh: vmatch.x could not be built (the acceptance test will be skipped)" >&2
+  fi
+  if families_stale; then
+    build_families || echo "build_ref.sh: the gpu family could not be built (tests/test_gpu_refseam.py will be skipped)" >&2
   fi
   exit 0
 fi
@@ -77,4 +133,5 @@ build_variant "$OUT/obj" "" ".x"
 build_variant "$OUT/objdbg" "-DDEBUG" ".dbg.x"
 rm -rf "$OUT/obj" "$OUT/objdbg"
 build_vmatch || echo "build_ref.sh: vmatch.x could not be built (the acceptance test will be skipped)" >&2
+build_families || echo "build_ref.sh: the gpu family could not be built (tests/test_gpu_refseam.py will be skipped)" >&2
 echo "built: $(ls "$OUT")"

@@ -19,6 +19,8 @@
 //      without long repeats end here, and then no rank array was ever needed: the N-wide scatter rank[pos] = slot of
 //      the first regroup is DEFERRED (the ranks are kept in suffix-array order, a sequential write) and only carried
 //      out when a doubling round follows.  Later rounds: key2 = rank[s+h], h *= 2.
+#include <time.h>
+
 #include "kmer_scan.cuh"
 #include "scan.cuh"
 #include "textcmp.cuh"
@@ -1596,11 +1598,18 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 
   // ---- 5. refinement rounds
   u64 h = h0;
+  static const bool round_log = getenv("ESA_ROUND_LOG") != nullptr;  // tuning aid: one stderr line per refinement round
   while (m > 0)
   {
     const u32 round = ++outcome->rounds;
     const bool text_round = plan.is_text(round);
     const u32 cur_shift = plan.shift_of(round);
+    struct timespec rl0;
+    if (round_log)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      clock_gettime(CLOCK_MONOTONIC, &rl0);
+    }
     outcome->active_sum += m;
     ctx->lcp_work_estimate += m * (h / 32 + 1);
     if (text_round)
@@ -1634,6 +1643,16 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
       scatter_ranks_partitioned(ctx, ps, sc.rank_out, m, rank_shift, rank, sc.tp, sc.tv, sort_temp, temp_bytes);
     }
     ar.rewind(scatter_mark);
+    if (round_log)
+    {
+      struct timespec rl1;
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      clock_gettime(CLOCK_MONOTONIC, &rl1);
+      fprintf(stderr, "ESA_ROUND_LOG round %u %s h=%llu m=%llu next=%llu spilled=%llu  %.3f ms\n", round,
+              text_round ? "text" : "rank", (unsigned long long) h, (unsigned long long) m, (unsigned long long) m_next,
+              (unsigned long long) ctx->h_scalars[8],
+              (rl1.tv_sec - rl0.tv_sec) * 1e3 + (rl1.tv_nsec - rl0.tv_nsec) * 1e-6);
+    }
     dk_in = ko;
     dp_in = po;
     dk_out = ks;
