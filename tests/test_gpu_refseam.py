@@ -142,7 +142,8 @@ def test_vmatch_online_query_indexes_through_completevirtualtree(tmp_path, vmarg
         assert pr.returncode == 0, pr.stderr.decode(errors="replace")
         outs.append(lines(pr.stdout.decode(errors="replace").replace(str(d), "CWD")))
     assert outs[0] == outs[1]
-    assert any(l and not l.startswith("#") for l in outs[0]), "the comparison is vacuous: vmatch reported no match"
+    if "-p" not in vmargs:  # (the planted repeats are direct ones)
+        assert any(l and not l.startswith("#") for l in outs[0]), "the comparison is vacuous: vmatch reported no match"
 
 
 @needs_families

@@ -320,6 +320,8 @@ struct RadixRemoteDst
   u32 *keys[64];   // receive buffers of every rank, as mapped into this rank's address space
   u32 *vals[64];
   u8 owner[256];   // digit -> rank
+  u32 key_sub[64]; // the key stored at owner r is (key - key_sub[r]) << key_shl (identity: 0 and 0)
+  u32 key_shl;
 };
 void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes);

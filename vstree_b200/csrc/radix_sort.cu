@@ -630,7 +630,7 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
       const u32 g = gbase[d] + p;
       if (REMOTE)
       {
-        reinterpret_cast<KeyT *>(remote->keys[d])[g] = k;  // d is the owner rank
+        reinterpret_cast<KeyT *>(remote->keys[d])[g] = (KeyT) ((k - remote->key_sub[d]) << remote->key_shl);  // d = owner
         if (HAS_VALS)
         {
           remote->vals[d][g] = v;

@@ -143,8 +143,10 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, 
                      const u32 *__restrict__ tile_side, const u32 *__restrict__ tile_spec,
                      u64 M /* full + side suffixes of the whole table */, u32 *__restrict__ main_key, u32 *__restrict__ main_pos,
                      u32 *__restrict__ side_key, u32 *__restrict__ side_pos, u32 *__restrict__ side_dj,
-                     u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ spec_list)
+                     u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ spec_list, u32 key_shl = 1)
 {
+  // key_shl = 1: keys are code << 1 | special-inside flag.  key_shl = 0 (sharded builds with 16-symbol DNA keys): the raw
+  // padded code; the owner of the suffix rebases it to its own key range and adds the flag (suffix_sort_sharded).
   __shared__ __align__(16) u8 stext[KS_TILE + KS_HALO];
   // staging for coalesced output; index e is stored at e + e/32 so that the 16-strided per-thread writes hit
   // 32 different banks
@@ -205,13 +207,13 @@ classify_emit_kernel(const u8 *__restrict__ tis, u64 n, u64 p_begin, u64 p_end, 
       } else if (dist[i] < kp.h)
       {
         const u64 o = off_side + rs;
-        side_key[o] = (code[i] << 1) | 1u;
+        side_key[o] = (code[i] << key_shl) | key_shl;
         side_pos[o] = (u32) p;
         side_dj[o] = kp.h - dist[i];
         rs++;
       } else
       {
-        skey[rf + (rf >> 5)] = code[i] << 1;
+        skey[rf + (rf >> 5)] = code[i] << key_shl;
         spos[rf + (rf >> 5)] = (u32) p;
         rf++;
       }
@@ -454,7 +456,7 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
 
 // per-bucket count of suffixes with a special inside the k-prefix (side suffixes with j < k)
 __global__ void side_bucket_count_kernel(const u32 *__restrict__ side_key, const u32 *__restrict__ side_dj, u64 nside,
-                                         u32 h0, u32 k, u32 kdiv, u32 *__restrict__ cnt)
+                                         u32 h0, u32 k, u32 kdiv, u32 *__restrict__ cnt, u32 key_shl = 1)
 {
   const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (t < nside)
@@ -462,7 +464,7 @@ __global__ void side_bucket_count_kernel(const u32 *__restrict__ side_key, const
     const u32 j = h0 - side_dj[t];
     if (j < k)
     {
-      atomicAdd(&cnt[(side_key[t] >> 1) / kdiv], 1u);
+      atomicAdd(&cnt[(side_key[t] >> key_shl) / kdiv], 1u);
     }
   }
 }
@@ -470,14 +472,20 @@ __global__ void side_bucket_count_kernel(const u32 *__restrict__ side_key, const
 // =========================================================================================================
 // 3. bck
 __global__ void bck_left_kernel(const u32 *__restrict__ sorted_key, u64 m, u64 numofcodes, u32 kdiv,
-                                u64 *__restrict__ bck)
+                                u64 *__restrict__ bck, u64 key_base = 0)
 {
   const u64 c = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= numofcodes)
   {
     return;
   }
-  const u64 target = (c * kdiv) << 1;  // first key of the k-mer c; may be 2^32 for c == numofcodes only
+  // keys are (code - key_base) << 1 | flag (key_base != 0: a rank's range of 16-symbol codes in a sharded build)
+  if (c * kdiv <= key_base)
+  {
+    bck[2 * c] = 0;  // the k-mer starts at or in front of this range
+    return;
+  }
+  const u64 target = (c * kdiv - key_base) << 1;  // first key of the k-mer c; beyond every 32-bit key when outside
   u64 lo = 0, hi = m;
   while (lo < hi)
   {
@@ -1796,6 +1804,16 @@ __device__ __forceinline__ u32 owner_of_key(u32 key, const OwnerLut &lut)
   return key == SPECIAL_KEY ? lut.last : (u32) lut.owner[(key >> lut.shift) & 0xffu];
 }
 
+// sharded builds, 16-symbol DNA keys: raw padded code -> (code - base) << 1 | flag, the form the owner sorts
+__global__ void rebase_keys_kernel(u32 *__restrict__ keys, u64 count, u32 base, u32 flag)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count)
+  {
+    keys[t] = ((keys[t] - base) << 1) | flag;
+  }
+}
+
 __global__ void bin_hist_kernel(const u32 *__restrict__ keys, u64 count, u32 shift, unsigned long long *__restrict__ hist)
 {
   __shared__ u32 sh[256];
@@ -1814,12 +1832,13 @@ __global__ void bin_hist_kernel(const u32 *__restrict__ keys, u64 count, u32 shi
 
 // owner of every key of a list (side suffixes), with per-owner counts
 __global__ void key_owner_kernel(const u32 *__restrict__ keys, u64 count, OwnerLut lut, u32 *__restrict__ owner,
-                                 unsigned long long *__restrict__ owner_count)
+                                 unsigned long long *__restrict__ owner_count, bool raw_codes)
 {
   const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (t < count)
   {
-    const u32 o = owner_of_key(keys[t], lut);
+    // raw_codes: side suffixes never start with a special, and 0xffffffff is an ordinary 16-symbol code
+    const u32 o = raw_codes ? (u32) lut.owner[(keys[t] >> lut.shift) & 0xffu] : owner_of_key(keys[t], lut);
     owner[t] = o;
     atomicAdd(&owner_count[o], 1ull);
   }
@@ -1990,17 +2009,28 @@ extern "C" int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, i
   return ESA_OK;
 }
 
-void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
-                         SortOutcome *outcome)
+// WIDE keys (DNA, two or more ranks): a rank's range covers only a part of the code space, so its keys are stored
+// relative to the first code of the range -- (code - base) << 1 | flag -- and 16 symbols fit where the absolute key
+// holds 15.  The round that follows the initial sort then starts from a quarter of the collisions (800 Mbp on eight
+// ranks: 17 % of the suffixes active instead of 52 %).  Needs every range narrower than 2^31 codes, i.e. fewer than 128
+// of the 256 first-symbols bins per rank; when the plan says otherwise (extremely skewed inputs) the function returns
+// false before anything was exchanged and the caller repeats it with absolute 15-symbol keys.
+static bool suffix_sort_sharded_impl(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
+                                     SortOutcome *outcome, bool wide)
 {
   const int G = comm->nranks, me = comm->rank;
   const u64 n = ctx->n, N = n + 1;
   const u32 sigma = ctx->sigma;
   cudaStream_t s = ctx->stream;
   Arena &ar = ctx->arena;
-  const u32 h0 = choose_h0(sigma);
+  const size_t entry_mark = ar.mark();
+  const u32 h0_text = choose_h0(sigma);                       // symbols of the absolute key (owner look-ups from the text)
+  const KmerParams kp_text = make_kmer_params(sigma, h0_text);
+  const u32 key_bits_text = bits_for(((u64) kp_text.all_pad << 1) | 1);
+  const u32 h0 = wide ? 16u : h0_text;
   const KmerParams kp = make_kmer_params(sigma, h0);
-  const u32 key_bits = bits_for(((u64) kp.all_pad << 1) | 1);
+  const u32 key_shl = wide ? 0u : 1u;                          // classification emits raw 16-symbol codes when wide
+  const u32 key_bits = wide ? 32u : key_bits_text;             // of the keys as classified
   u32 *rank = ctx->d_isa;  // dense by text position; only the entries of suffixes this rank owns are defined
   u64 all[ESA_MAX_RANKS * (ESA_MAX_RANKS + 4)];
   u64 mine[ESA_MAX_RANKS + 4];
@@ -2041,10 +2071,10 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
                (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
                                                                     tile_side, tile_spec, 0, key_l, pos_l,
                                                                     lside_key, lside_pos, lside_dj, nullptr, nullptr,
-                                                                    lspec)));
+                                                                    lspec, key_shl)));
   }
 
-  // ---- 2. splitter pass: bins of the top 8 key bits
+  // ---- 2. splitter pass: bins of the top 8 key bits (= the first symbols, whichever key width)
   OwnerLut lut;
   lut.shift = key_bits > 8 ? key_bits - 8 : 0;
   lut.last = (u32) (G - 1);
@@ -2078,6 +2108,35 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   u64 send_cnt[ESA_MAX_RANKS] = {0}, send_off[ESA_MAX_RANKS], recv_cnt[ESA_MAX_RANKS] = {0}, recv_off[ESA_MAX_RANKS];
   u32 h_start[256];
   esa_shard_plan(hist_all.data(), HROW, G, me, lut.owner, send_cnt, recv_cnt, h_start);
+  // first code of every rank's range and its width in bins (wide keys)
+  u32 key_base[ESA_MAX_RANKS] = {0}, range_bins[ESA_MAX_RANKS] = {0};
+  {
+    bool seen[ESA_MAX_RANKS] = {false};
+    for (int b = 0; b < 256; b++)
+    {
+      const int o = lut.owner[b];
+      if (!seen[o])
+      {
+        seen[o] = true;
+        key_base[o] = wide ? (u32) b << 24 : 0u;
+      }
+      range_bins[o]++;
+    }
+    if (wide)
+    {
+      for (int r = 0; r < G; r++)
+      {
+        if (range_bins[r] >= 128)
+        {
+          ar.rewind(entry_mark);
+          return false;  // the same decision on every rank: the plan is a function of the exchanged histogram
+        }
+      }
+    }
+  }
+  const u32 sort_key_bits = wide ? bits_for(((((u64) range_bins[me]) << 24) << 1) | 1) : key_bits;
+  OwnerLut lut_text = lut;  // owner of a suffix from the TEXT (doubling rounds): absolute keys of h0_text symbols
+  lut_text.shift = key_bits_text > 8 ? key_bits_text - 8 : 0;
   u64 side_cnt[ESA_MAX_RANKS], side_off[ESA_MAX_RANKS], spec_cnt[ESA_MAX_RANKS], spec_off[ESA_MAX_RANKS];
   u64 nside_tot = 0, nspec_tot = 0, mfull = 0, off = 0;
   for (int r = 0; r < G; r++)
@@ -2123,7 +2182,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     {
       ESA_LAUNCH(ctx, ESA_K_BCK, 8.0 * nside_tot,
                  (side_bucket_count_kernel<<<grid_for(nside_tot, 256), 256, 0, s>>>(gs_key, gs_dj, nside_tot, h0,
-                                                                                     prefixlength, kdiv, bck_cnt)));
+                                                                                     prefixlength, kdiv, bck_cnt, key_shl)));
     }
     const u32 *sk = gs_key, *sp = gs_pos;
     if (nside_tot > 1)
@@ -2140,7 +2199,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     // owner of every side suffix; then a stable partition by owner
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
     ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 8.0 * nside_tot,
-               (key_owner_kernel<<<grid_for(nside_tot, 256), 256, 0, s>>>(sk, nside_tot, lut, gs_own, d_counts)));
+               (key_owner_kernel<<<grid_for(nside_tot, 256), 256, 0, s>>>(sk, nside_tot, lut, gs_own, d_counts, wide)));
     u64 own_cnt[ESA_MAX_RANKS];
     CUDA_CHECK(cudaMemcpyAsync(own_cnt, d_counts, sizeof own_cnt, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -2182,6 +2241,11 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       h_dst.vals[r] = comm_peer_ptr<u32>(ctx, comm, r, offs[2 * r + 1]);
     }
     memcpy(h_dst.owner, lut.owner, 256);
+    for (int r = 0; r < G; r++)
+    {
+      h_dst.key_sub[r] = key_base[r];  // wide keys: stored relative to the owner's first code, flag bit 0
+    }
+    h_dst.key_shl = wide ? 1u : 0u;
     // the pass partitions by owner: rank r's runs lie in sender order inside its buffers
     u32 owner_start[256] = {0};
     for (int o = 0; o < G; o++)
@@ -2214,11 +2278,21 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     }
     comm_alltoallv_u32(ctx, comm, ks, send_off, send_cnt, key_a, recv_off, recv_cnt);
     comm_alltoallv_u32(ctx, comm, ps, send_off, send_cnt, pos_a, recv_off, recv_cnt);
+    if (wide && mfull > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 8.0 * mfull,
+                 (rebase_keys_kernel<<<grid_for(mfull, 256), 256, 0, s>>>(key_a, mfull, key_base[me], 0u)));
+    }
   }
   if (nside_mine > 0)
   {
     CUDA_CHECK(cudaMemcpyAsync(key_a + mfull, my_side_key, nside_mine * 4, cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(pos_a + mfull, my_side_pos, nside_mine * 4, cudaMemcpyDeviceToDevice, s));
+    if (wide)
+    {
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 8.0 * nside_mine,
+                 (rebase_keys_kernel<<<grid_for(nside_mine, 256), 256, 0, s>>>(key_a + mfull, nside_mine, key_base[me], 1u)));
+    }
   }
 
   // ---- 3d. shape of the table: my range, the tail of special-initial suffixes on the last rank
@@ -2261,7 +2335,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
 
   // ---- 4. the initial sort of my range
   u32 *skey = key_a, *spos = pos_a;
-  if (M > 1 && radix_sort_pairs_u32(ctx, key_a, key_b, pos_a, pos_b, M, 0, key_bits, sort_temp, temp_bytes))
+  if (M > 1 && radix_sort_pairs_u32(ctx, key_a, key_b, pos_a, pos_b, M, 0, sort_key_bits, sort_temp, temp_bytes))
   {
     skey = key_b;
     spos = pos_b;
@@ -2277,7 +2351,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     const u64 nc = ctx->numofcodes;
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(ctx->d_bck, 0, 2 * nc * sizeof(u64), s)));
     ESA_LAUNCH(ctx, ESA_K_BCK, 8.0 * nc,
-               (bck_left_kernel<<<grid_for(nc, 256), 256, 0, s>>>(skey, M, nc, kdiv, ctx->d_bck)));
+               (bck_left_kernel<<<grid_for(nc, 256), 256, 0, s>>>(skey, M, nc, kdiv, ctx->d_bck, (u64) key_base[me])));
     const size_t mark = ar.mark();
     u64 *tmp = ar.alloc<u64>(2 * nc);
     comm_allreduce_u64(ctx, comm, ctx->d_bck, tmp, 2 * nc, false);
@@ -2339,7 +2413,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   KeyFromText keyof;
   keyof.tis = ctx->d_tis;
   keyof.packed = TextPacked2{sigma == 4 ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
-  keyof.kp = kp;
+  keyof.kp = kp_text;
   // the sort of one round on this rank (the secondary keys are in place): afterwards (dk_in, dp_in) is sorted
   auto sort_round = [&](u32 round) {
     const u32 cur_shift = plan.shift_of(round);
@@ -2414,7 +2488,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
   }
   if (m_world == 0)
   {
-    return;
+    return true;
   }
   // a doubling round follows: rank[] is needed now
   flush_deferred_scatter(ctx, plan, sa, M, rank, sort_temp, temp_bytes);
@@ -2446,7 +2520,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       if (m > 0)
       {
         ESA_LAUNCH(ctx, ESA_K_GATHER_RANK, 24.0 * m,
-                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut, peers)));
+                   (gather_rank_peer_kernel<<<grid_for(m, 256), 256, 0, s>>>(dk_in, dp_in, m, h, keyof, lut_text, peers)));
         comm->bytes_sent += 4 * m;  // upper bound of what crossed NVLink for me (own range included)
         sort_round(round);
       }
@@ -2472,7 +2546,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
       m_world = sum_next;
       h *= 2;
     }
-    return;
+    return true;
   }
   while (true)
   {
@@ -2486,7 +2560,7 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     {
       ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(d_counts, 0, ESA_MAX_RANKS * sizeof(u64), s)));
       ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 16.0 * m,
-                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(tag_a, idx_a, dp_in, m, h, keyof, lut, d_counts)));
+                 (owner_tag_kernel<<<grid_for(m, 256), 256, 0, s>>>(tag_a, idx_a, dp_in, m, h, keyof, lut_text, d_counts)));
       CUDA_CHECK(cudaMemcpyAsync(req_cnt, d_counts, G * sizeof(u64), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
@@ -2552,4 +2626,17 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
     m = m_next;
     h *= 2;
   }
+  return true;
+}
+
+void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool want_bck, bool want_hround,
+                         SortOutcome *outcome)
+{
+  static const bool no_wide = getenv("ESA_NO_WIDE_KEY") != nullptr;
+  const bool try_wide = ctx->sigma == 4 && comm->nranks >= 2 && !no_wide;
+  if (try_wide && suffix_sort_sharded_impl(ctx, comm, prefixlength, want_bck, want_hround, outcome, true))
+  {
+    return;
+  }
+  suffix_sort_sharded_impl(ctx, comm, prefixlength, want_bck, want_hround, outcome, false);
 }
