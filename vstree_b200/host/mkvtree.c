@@ -1341,6 +1341,32 @@ typedef struct
   char err[512];
 } Rankjob;
 
+/* The CUDA context of a one-shot process costs more than parsing 100 Mbp: esa_init (context, streams, kernel images) runs
+ * on its own thread while the main thread reads and transforms the input; joined right before the build.  Nothing is
+ * allocated there (pinning gigabytes next to the page-cache traffic of the parser was tried in round 1 and proved
+ * erratic).  MKVTREE_TIMING=1 prints the phases of the process on stderr. */
+typedef struct
+{
+  pthread_t thread;
+  int started, device, rc;
+  esa_ctx *ctx;
+  char err[512];
+} Earlyinit;
+
+static void *earlyinitmain(void *arg)
+{
+  Earlyinit *e = (Earlyinit *) arg;
+  e->rc = esa_init(&e->ctx, e->device, e->err, sizeof e->err);
+  return NULL;
+}
+
+static double nowseconds(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
 static void *rankmain(void *arg)
 {
   Rankjob *job = (Rankjob *) arg;
@@ -1395,7 +1421,12 @@ int main(int argc, char **argv)
   uint32_t numofchars, k, builddemand;
   int rc, dosort, somethingout;
   FILE *lcpfp = NULL;
+  Earlyinit early;
+  const int timing = getenv("MKVTREE_TIMING") != NULL;
+  const double t_start = nowseconds();
+  double t_parsed = 0, t_hosttables = 0, t_built = 0;
 
+  memset(&early, 0, sizeof early);
   rc = parseoptions(&opt, argc, argv);
   if (rc == 1)
   {
@@ -1416,6 +1447,14 @@ int main(int argc, char **argv)
   }
   memset(&ms, 0, sizeof ms);
   memset(concatfilesep, 0, sizeof concatfilesep);
+  if ((opt.demand & (ESA_BWTTAB | ESA_SUFTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB))
+      && getenv("MKVTREE_GPUS") == NULL)
+  {
+    /* a table of the sorter is demanded: the device is needed, start it now (one GPU; several: see below) */
+    const char *dev = getenv("MKVTREE_GPU");
+    early.device = dev != NULL ? atoi(dev) : 0;
+    early.started = pthread_create(&early.thread, NULL, earlyinitmain, &early) == 0;
+  }
   if (alpha.fromtext && opt.numoffiles > 1)
   {
     fail("multiple input files require one of the options -smap, -dna, or -protein");
@@ -1547,6 +1586,7 @@ int main(int argc, char **argv)
   {
     verbosealphabet(&alpha);
   }
+  t_parsed = nowseconds();
   somethingout = (opt.demand & OUTPUTTABS) != 0;
   if (somethingout && removeexistingindex(opt.indexname) != 0)
   {
@@ -1578,6 +1618,7 @@ int main(int argc, char **argv)
              && !(opt.demand & (ESA_BWTTAB | ESA_SUFTAB | ESA_LCPTAB | ESA_BCKTAB | ESA_STI1TAB | ESA_SKPTAB)));
   memset(&res, 0, sizeof res);
   memset(&stats, 0, sizeof stats);
+  t_hosttables = nowseconds();
   if (dosort)
   {
     if (opt.demand & ESA_LCPTAB)
@@ -1617,8 +1658,23 @@ int main(int argc, char **argv)
       for (r = 0; r < njobs; r++)
       {
         const int device = (one != NULL && atoi(one) != 0) ? first : first + r;
-        if (esa_init(&jobs[r].ctx, device, err, sizeof err) != 0
-            || (njobs > 1 && esa_comm_attach_group(jobs[r].ctx, group, r, err, sizeof err) != 0))
+        if (r == 0 && early.started)
+        {
+          pthread_join(early.thread, NULL);  /* the context started behind the parser */
+          early.started = 0;
+          if (early.rc != 0)
+          {
+            fail("%s", early.err);
+            goto failure;
+          }
+          jobs[0].ctx = early.ctx;
+          early.ctx = NULL;
+        } else if (esa_init(&jobs[r].ctx, device, err, sizeof err) != 0)
+        {
+          fail("%s", err);
+          goto failure;
+        }
+        if (njobs > 1 && esa_comm_attach_group(jobs[r].ctx, group, r, err, sizeof err) != 0)
         {
           fail("%s", err);
           goto failure;
@@ -1694,6 +1750,7 @@ int main(int argc, char **argv)
         }
       }
     }
+    t_built = nowseconds();
     if (lcpfp != NULL)
     {
       FILE *fp = lcpfp;
@@ -1844,15 +1901,25 @@ alphabetwritten:;
     printf("overall space peak: main=%.2f MB (%.2f bytes/symbol), secondary=%.2f MB\n", hostbytes / (1 << 20),
            hostbytes / (double) ms.totallength, (double) stats.device_bytes_peak / (1 << 20));
   }
-  if (ctx != NULL)
   {
-    int r;
-    for (r = 0; r < njobs; r++)
+    const double t_written = nowseconds();
+    if (ctx != NULL)
     {
-      esa_free(jobs[r].ctx, &jobs[r].res);
-      esa_shutdown(jobs[r].ctx);
+      int r;
+      for (r = 0; r < njobs; r++)
+      {
+        esa_free(jobs[r].ctx, &jobs[r].res);
+        esa_shutdown(jobs[r].ctx);
+      }
+      esa_group_destroy(group);
     }
-    esa_group_destroy(group);
+    if (timing)
+    {
+      fprintf(stderr, "MKVTREE_TIMING parse %.3f s, host tables %.3f s, device (wait for context + upload + build + "
+                      "download) %.3f s [build on device %.3f s], table output %.3f s, teardown %.3f s, total %.3f s\n",
+              t_parsed - t_start, t_hosttables - t_parsed, dosort ? t_built - t_hosttables : 0.0, stats.ms_total * 1e-3,
+              dosort ? t_written - t_built : t_written - t_hosttables, nowseconds() - t_written, nowseconds() - t_start);
+    }
   }
   return EXIT_SUCCESS;
 
