@@ -86,6 +86,10 @@ typedef struct
      [shard_first, shard_first + shard_count) of this rank, llv indices are global; one GPU: 0 and N */
   uint64_t shard_first;
   uint64_t shard_count;
+  /* stitab1 / stitab are indexed by TEXT position: sharded builds return the positions [text_first, text_first +
+     text_count) of this rank (slices in rank order tile the text); one GPU: 0 and N */
+  uint64_t text_first;
+  uint64_t text_count;
 } esa_result;
 
 /* Kernel families, for esa_stats.kernel[]. */
@@ -160,6 +164,16 @@ int esa_build(esa_ctx *ctx, const uint8_t *tis, uint64_t n, uint32_t numofchars,
               uint32_t demand, esa_result *out, esa_stats *stats, char *errbuf, size_t errlen);
 void esa_free(esa_ctx *ctx, esa_result *out);
 
+/* Optional: where the result tables go.  By default esa_build / esa_download return tables in pinned memory owned by the
+ * library.  With an allocator set, the library asks it for the memory of a table (table = one ESA_*TAB bit; bytes = size
+ * of the table) and copies the table there instead; NULL from the allocator means "use your own buffer".  The memory
+ * stays the caller's (esa_free leaves it alone).  Meant for one-shot processes that want a table straight in its final
+ * place -- the mkvtree driver hands out the mapped pages of the .suf file, so 8 of the 10 output bytes per suffix are
+ * never copied on the host.  Ordinary (pageable) memory is fine; the chunked, overlapped download of esa_build needs
+ * pinned memory and is not used for such a table. */
+typedef void *(*esa_result_alloc_fn)(void *user, uint32_t table, uint64_t bytes);
+int esa_set_result_allocator(esa_ctx *ctx, esa_result_alloc_fn fn, void *user);
+
 /* ---- the same work in three stages, so that the device-resident part can be timed alone ---- */
 int esa_upload(esa_ctx *ctx, const uint8_t *tis, uint64_t n, uint32_t numofchars, char *errbuf, size_t errlen);
 int esa_construct(esa_ctx *ctx, uint32_t prefixlength, uint32_t demand, esa_stats *stats, char *errbuf,
@@ -174,8 +188,9 @@ int esa_download(esa_ctx *ctx, esa_result *out, char *errbuf, size_t errlen);
  * then call esa_upload / esa_construct / esa_download (or esa_build) on EVERY rank: they are collective.  The tables of
  * esa_result then cover suffix-array entries [shard_first, shard_first + shard_count) only (llv indices are global;
  * bcktab, maxbranchdepth and longest are complete on every rank); concatenating the ranks' tables in rank order gives
- * the files the reference writes.  ESA_STI1TAB / ESA_STITAB and esa_check need the whole inverse suffix array on
- * one device and are refused on a sharded context.
+ * the files the reference writes.  stitab1 / stitab (ESA_STI1TAB / ESA_STITAB) are indexed by text position: every rank
+ * returns the slice [text_first, text_first + text_count) of them, again tiling the table in rank order.  ESA_SKPTAB and
+ * esa_check need whole tables on one device and are refused on a sharded context.
  *
  * Transport A, one process per GPU (NCCL over NVLink): rank 0 calls esa_comm_unique_id and distributes the id by any
  * means (MPI, torch.distributed, a file); every rank calls esa_comm_attach_nccl.  libnccl.so.2 is loaded with dlopen.

@@ -399,12 +399,23 @@ def test_full_cli_several_gpus_one_index(tmp_path, monkeypatch, name, ranks):
             ["-db", "g.fa", flag, "-pl", "-suf", "-lcp", "-bwt", "-bck", "-tis", "-ois", "-v"])
 
 
+@needs_ref
 @pytest.mark.gpu
-def test_cli_several_gpus_refuses_sti1(tmp_path, monkeypatch):
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_cli_several_gpus_sti1(tmp_path, monkeypatch, ranks):
+    """-sti1 on several ranks: the table is indexed by text position, every rank contributes its slice of the text."""
+    monkeypatch.setenv("MKVTREE_GPUS", str(ranks))
+    monkeypatch.setenv("MKVTREE_GPUS_ONE_DEVICE", "1")
+    tis, sigma = make_input("dna_specials_50k")
+    compare(tmp_path, {"g.fa": synth.to_fasta(tis, "dna")}, ["-db", "g.fa", "-dna", "-pl", "-sti1", "-bwt", "-v"])
+
+
+@pytest.mark.gpu
+def test_cli_several_gpus_refuses_skp(tmp_path, monkeypatch):
     monkeypatch.setenv("MKVTREE_GPUS", "2")
     monkeypatch.setenv("MKVTREE_GPUS_ONE_DEVICE", "1")
     (tmp_path / "in.fna").write_bytes(DNA)
-    rc, out, err, files = run(OURS, ["-db", "in.fna", "-dna", "-pl", "-sti1"], str(tmp_path))
+    rc, out, err, files = run(OURS, ["-db", "in.fna", "-dna", "-pl", "-suf", "-lcp", "-skp"], str(tmp_path))
     assert rc == 1 and "sharded build" in err
 
 

@@ -111,10 +111,24 @@ def test_sharded_protein_and_staged_calls(group):
     assert stats[0]["kernel"]["comm"]["launches"] > 0
 
 
-def test_sharded_context_refuses_what_needs_the_whole_inverse_array(group):
+def test_sharded_tables_by_text_position(group):
+    """.sti1 and the full inverse suffix array of a sharded build: slices of the text in rank order."""
+    for tis, sigma, k in ((synth.dna_with_specials(70000, seed=23, nfrac=0.004, mean_run=6, records=11), 4, 6),
+                          (synth.random_protein(40000, seed=24, records=30, xfrac=0.002), 20, 2),
+                          (np.array([0, 1, 2, 3, 254, 0, 1, 2, 255, 0, 1, 2, 3, 255, 254, 254, 0, 1], np.uint8), 4, 1)):
+        want = ou.oracle_build(tis, sigma, k)
+        got, _ = group.build(tis, sigma, k, tables=("suf", "lcp", "bwt", "bck", "sti1", "sti"))
+        assert_same(got, want, f"sigma {sigma} on {group.nranks} ranks")
+        assert np.array_equal(got["sti1"], want["sti1"]), first_diff(got["sti1"], want["sti1"])
+        inv = np.zeros(len(tis) + 1, np.uint64)
+        inv[want["suf"]] = np.arange(len(tis) + 1, dtype=np.uint64)
+        assert np.array_equal(got["sti"], inv)
+
+
+def test_sharded_context_refuses_the_skip_table(group):
     tis = synth.random_dna(50000, seed=1)
     with pytest.raises(EsaError) as ei:
-        group.build(tis, 4, 5, tables=("suf", "sti1"))
+        group.build(tis, 4, 5, tables=("suf", "lcp", "skp"))
     assert "sharded" in str(ei.value)
     # the group survives a refused build
     got, _ = group.build(tis, 4, 5, tables=("suf",))

@@ -52,7 +52,7 @@ class Result(ctypes.Structure):
                 ("bwttab", ctypes.POINTER(ctypes.c_uint8)), ("bcktab", ctypes.POINTER(ctypes.c_uint64)),
                 ("stitab1", ctypes.POINTER(ctypes.c_uint8)), ("stitab", ctypes.POINTER(ctypes.c_uint64)),
                 ("skiptab", ctypes.POINTER(ctypes.c_uint64)), ("shard_first", ctypes.c_uint64),
-                ("shard_count", ctypes.c_uint64)]
+                ("shard_count", ctypes.c_uint64), ("text_first", ctypes.c_uint64), ("text_count", ctypes.c_uint64)]
 
 
 def library_path():
@@ -185,11 +185,12 @@ class Esa:
         return {"suf": arr(res.suftab, N, np.uint64), "lcp": arr(res.lcptab, N, np.uint8),
                 "llv": arr(res.llv, 2 * res.nllv, np.uint64) if res.lcptab else None,
                 "bwt": arr(res.bwttab, N, np.uint8), "bck": arr(res.bcktab, 2 * res.numofcodes, np.uint64),
-                "sti1": arr(res.stitab1, N, np.uint8), "sti": arr(res.stitab, N, np.uint64),
+                "sti1": arr(res.stitab1, res.text_count, np.uint8), "sti": arr(res.stitab, res.text_count, np.uint64),
                 "skp": arr(res.skiptab, N, np.uint64),
                 "maxbranchdepth": int(res.maxbranchdepth), "longest": int(res.longest),
                 "largelcpvalues": int(res.nllv), "numofcodes": int(res.numofcodes),
-                "shard_first": int(res.shard_first), "shard_count": int(res.shard_count)}
+                "shard_first": int(res.shard_first), "shard_count": int(res.shard_count),
+                "text_first": int(res.text_first), "text_count": int(res.text_count)}
 
     def build(self, tis, numofchars, prefixlength, tables=("suf", "lcp", "bwt"), want_stats=True, copy=True):
         """esa_build: host buffer in, tables out.  Returns (tables dict, stats dict or None).
@@ -291,8 +292,17 @@ def merge_shards(parts):
     for name in ("suf", "lcp", "bwt", "llv"):
         if parts[0].get(name) is not None:
             out[name] = np.concatenate([t[name] for t in parts])
+    tpos = 0
+    if any(parts[0].get(name) is not None for name in ("sti1", "sti")):
+        for t in parts:  # the tables indexed by text position are cut into slices of the text, in rank order as well
+            assert t["text_first"] == tpos or t["text_count"] == 0, "text slices of the ranks do not tile the text"
+            tpos += t["text_count"]
+        for name in ("sti1", "sti"):
+            if parts[0].get(name) is not None:
+                out[name] = np.concatenate([t[name] for t in parts])
     out["largelcpvalues"] = sum(t["largelcpvalues"] for t in parts)
     out["shard_first"], out["shard_count"] = 0, pos
+    out["text_first"], out["text_count"] = 0, tpos
     return out
 
 

@@ -58,6 +58,36 @@ struct PinnedPool
     bool used;
   };
   std::vector<Block> blocks;
+  // ESA_PAGEABLE_RESULTS=1 (set by one-shot processes such as the mkvtree driver): ordinary page-aligned memory instead
+  // of pinned memory.  Pinning the 1.3 GB of tables of a 100 Mbp index costs 0.3 to 3 s of a fresh process (measured
+  // on the B200 box, erratic), the staged copy into pageable memory about 0.1 s.  A resident context that builds many
+  // indexes keeps the default: pinned once, reused, and required by the chunked download that overlaps the build.
+  bool pageable = false;
+  void *allocate(size_t bytes)
+  {
+    void *p = nullptr;
+    if (pageable)
+    {
+      if (posix_memalign(&p, 4096, (bytes + 4095) & ~(size_t) 4095) != 0)
+      {
+        esa_throw(ESA_ERR_MEMORY, "cannot allocate %zu bytes of host memory", bytes);
+      }
+    } else
+    {
+      CUDA_CHECK(cudaMallocHost(&p, bytes));
+    }
+    return p;
+  }
+  void release(void *p)
+  {
+    if (pageable)
+    {
+      free(p);
+    } else
+    {
+      cudaFreeHost(p);
+    }
+  }
   void *get(size_t bytes)
   {
     if (bytes == 0)
@@ -77,8 +107,7 @@ struct PinnedPool
       best->used = true;
       return best->p;
     }
-    void *p = nullptr;
-    CUDA_CHECK(cudaMallocHost(&p, bytes));
+    void *p = allocate(bytes);
     blocks.push_back({p, bytes, true});
     return p;
   }
@@ -103,7 +132,7 @@ struct PinnedPool
         keep.push_back(b);
       } else
       {
-        cudaFreeHost(b.p);
+        release(b.p);
       }
     }
     blocks.swap(keep);
@@ -112,7 +141,7 @@ struct PinnedPool
   {
     for (Block &b : blocks)
     {
-      cudaFreeHost(b.p);
+      release(b.p);
     }
     blocks.clear();
   }
@@ -256,6 +285,8 @@ struct CtxExtra
   PinnedPool pool;
   HostWiden widen;
   bool fuse_download = false;  // set by esa_build around do_construct
+  esa_result_alloc_fn user_alloc = nullptr;  // esa_set_result_allocator
+  void *user_alloc_arg = nullptr;
   u64 h2d_bytes = 0;           // what the last upload moved over PCIe on this rank
   cudaEvent_t ev_sorted = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
@@ -640,13 +671,14 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   }
 
   const bool sharded = is_sharded(ctx);
-  if (sharded && (demand & (ESA_STI1TAB | ESA_STITAB | ESA_SKPTAB)))
+  if (sharded && (demand & ESA_SKPTAB))
   {
-    esa_throw(ESA_ERR_ARGUMENT, "sti1/sti/skp need the whole inverse suffix array on one device: not available in a "
-                                "sharded build");
+    esa_throw(ESA_ERR_ARGUMENT, "the skip table needs the whole lcp table on one device: not available in a sharded build");
   }
   ctx->shard_first = 0;
   ctx->shard_count = N;
+  ctx->text_first = 0;
+  ctx->text_count = N;
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_a, s));
   ctx->d_sa = sharded ? nullptr : ar.alloc<u32>(N + 64);
   ctx->d_isa = ar.alloc<u32>(N + 64);
@@ -685,7 +717,9 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_b, s));
   ar.rewind(scratch_mark);  // everything the sorter carved is dead now
   u32 table_demand = demand;  // what the sweeps over the suffix array still have to produce on the device
-  if (ctx->x.fuse_download && (demand & ESA_SUFTAB) && ctx->shard_count >= ((u64) 1 << 22) && widen_threads(ctx) > 0)
+  if (ctx->x.fuse_download && !ctx->x.pool.pageable && ctx->x.user_alloc == nullptr && (demand & ESA_SUFTAB)
+      && ctx->shard_count >= ((u64) 1 << 22)
+      && widen_threads(ctx) > 0)
   {
     start_host_widen(ctx);
     table_demand &= ~(u32) ESA_SUFTAB;
@@ -784,17 +818,23 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
       ctx->longest = std::max(ctx->longest, all[2 * r + 1]);
     }
   }
-  if (demand & ESA_STI1TAB)
+  if (sharded && (demand & (ESA_STI1TAB | ESA_STITAB)))
   {
-    compute_sti1(ctx, prefixlength);
+    compute_sti_sharded(ctx, ctx->comm, prefixlength, demand);
+  } else
+  {
+    if (demand & ESA_STI1TAB)
+    {
+      compute_sti1(ctx, prefixlength);
+    }
+    if (demand & ESA_STITAB)
+    {
+      widen_isa(ctx);
+    }
   }
   if (demand & ESA_SKPTAB)
   {
     compute_skp(ctx, use_plcp ? ctx->d_plcpv : nullptr, ctx->d_lcpfull);
-  }
-  if (demand & ESA_STITAB)
-  {
-    widen_isa(ctx);
   }
   CUDA_CHECK(cudaEventRecord(ctx->x.ev_d, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -829,9 +869,17 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   }
 }
 
-template <typename T> T *download_table(FullCtx *ctx, const T *d, u64 count)
+template <typename T> T *download_table(FullCtx *ctx, const T *d, u64 count, u32 table = 0)
 {
-  T *h = (T *) ctx->x.pool.get(count * sizeof(T));
+  T *h = nullptr;
+  if (ctx->x.user_alloc != nullptr && table != 0)
+  {
+    h = (T *) ctx->x.user_alloc(ctx->x.user_alloc_arg, table, count * sizeof(T));  // the caller's memory (may decline)
+  }
+  if (h == nullptr)
+  {
+    h = (T *) ctx->x.pool.get(count * sizeof(T));
+  }
   if (count > 0)
   {
     CUDA_CHECK(cudaMemcpyAsync(h, d, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
@@ -861,7 +909,7 @@ u64 do_download(FullCtx *ctx, esa_result *out)
     bytes += 4 * N;  // what crossed PCIe for this table
   } else if (ctx->d_suf64 != nullptr)
   {
-    out->suftab = download_table(ctx, ctx->d_suf64, N);
+    out->suftab = download_table(ctx, ctx->d_suf64, N, ESA_SUFTAB);
     bytes += 8 * N;
   }
   if (ctx->d_lcp != nullptr && (ctx->demand & ESA_LCPTAB))
@@ -880,15 +928,17 @@ u64 do_download(FullCtx *ctx, esa_result *out)
     out->bcktab = download_table(ctx, ctx->d_bck, 2 * ctx->numofcodes);
     bytes += 16 * ctx->numofcodes;
   }
+  out->text_first = ctx->text_first;
+  out->text_count = ctx->text_count;
   if (ctx->d_sti1 != nullptr)
   {
-    out->stitab1 = download_table(ctx, ctx->d_sti1, N);
-    bytes += N;
+    out->stitab1 = download_table(ctx, ctx->d_sti1, ctx->text_count);
+    bytes += ctx->text_count;
   }
   if (ctx->d_sti64 != nullptr)
   {
-    out->stitab = download_table(ctx, ctx->d_sti64, N);
-    bytes += 8 * N;
+    out->stitab = download_table(ctx, ctx->d_sti64, ctx->text_count);
+    bytes += 8 * ctx->text_count;
   }
   if (ctx->d_skp != nullptr)
   {
@@ -952,6 +1002,10 @@ int esa_init(esa_ctx **out, int device, char *errbuf, size_t errlen)
       CUDA_CHECK(cudaEventCreate(ev));
     }
     radix_sort_init();
+    if (const char *pg = getenv("ESA_PAGEABLE_RESULTS"))
+    {
+      ctx->x.pool.pageable = atoi(pg) != 0;
+    }
     if (const char *m = getenv("ESA_LCP_MODE"))
     {
       ctx->lcp_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "plcp") == 0 ? 2 : 0;
@@ -1277,6 +1331,18 @@ int esa_debug_radix_sort(esa_ctx *c, int key_bytes, void *keys, uint32_t *vals, 
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
   });
+}
+
+int esa_set_result_allocator(esa_ctx *c, esa_result_alloc_fn fn, void *user)
+{
+  if (c == nullptr)
+  {
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  ctx->x.user_alloc = fn;
+  ctx->x.user_alloc_arg = user;
+  return ESA_OK;
 }
 
 int esa_debug_corrupt(esa_ctx *c, uint32_t table, uint64_t index, uint64_t xor_mask, char *errbuf, size_t errlen)

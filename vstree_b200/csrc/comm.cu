@@ -21,6 +21,7 @@ struct NcclApi
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -75,6 +76,7 @@ NcclApi &nccl()
       nccl_sym(g_nccl.GetErrorString, "ncclGetErrorString");
       nccl_sym(g_nccl.AllReduce, "ncclAllReduce");
       nccl_sym(g_nccl.AllGather, "ncclAllGather");
+      nccl_sym(g_nccl.ReduceScatter, "ncclReduceScatter");
       nccl_sym(g_nccl.Send, "ncclSend");
       nccl_sym(g_nccl.Recv, "ncclRecv");
       nccl_sym(g_nccl.GroupStart, "ncclGroupStart");
@@ -523,6 +525,55 @@ void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, si
   ESA_LAUNCH(ctx, ESA_K_COMM, 8.0 * count,
              NCCL_CHECK(nccl().AllReduce(d_buf, d_buf, count, ncclUint64, max_instead_of_sum ? ncclMax : ncclSum,
                                          (ncclComm_t) comm->nccl, ctx->stream)));
+}
+
+namespace
+{
+// out[i] = sum over ranks of their word (first + i)
+__global__ void group_reduce_slice_kernel(PeerPtrs peers, int nranks, u64 first, u64 *__restrict__ out, u64 count)
+{
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64) gridDim.x * blockDim.x)
+  {
+    u64 acc = 0;
+    for (int r = 0; r < nranks; r++)
+    {
+      acc += __ldcv(peers.p[r] + first + i);
+    }
+    out[i] = acc;
+  }
+}
+}  // namespace
+
+void comm_reduce_scatter_sum_u64(esa_ctx *ctx, esa_comm *comm, const u64 *d_full, u64 *d_out, size_t slice_words)
+{
+  if (slice_words == 0)
+  {
+    return;
+  }
+  const int G = comm->nranks, me = comm->rank;
+  if (G == 1)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(d_out, d_full, slice_words * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    return;
+  }
+  comm->bytes_sent += (u64) slice_words * 8 * (G - 1);
+  if (comm->group != nullptr)
+  {
+    group_round(ctx, comm, d_full, nullptr, nullptr, [&](esa_group *g) {
+      PeerPtrs pp;
+      for (int r = 0; r < G; r++)
+      {
+        pp.p[r] = (const u64 *) g->slot[r].ptr;
+      }
+      const u32 grid = (u32) min((u64) ctx->num_sms * 8, div_up_u64(slice_words, 256));
+      ESA_LAUNCH(ctx, ESA_K_COMM, 8.0 * slice_words * G,
+                 (group_reduce_slice_kernel<<<grid, 256, 0, ctx->stream>>>(pp, G, (u64) me * slice_words, d_out, slice_words)));
+    });
+    return;
+  }
+  ESA_LAUNCH(ctx, ESA_K_COMM, 8.0 * slice_words * G,
+             NCCL_CHECK(nccl().ReduceScatter(d_full, d_out, slice_words, ncclUint64, ncclSum, (ncclComm_t) comm->nccl,
+                                             ctx->stream)));
 }
 
 void comm_allgather_bytes(esa_ctx *ctx, esa_comm *comm, u8 *d_buf, size_t slice)

@@ -80,6 +80,9 @@ template <typename T> static inline T *comm_peer_ptr(esa_ctx *ctx, esa_comm *com
 void comm_exchange_host_u64(esa_ctx *ctx, esa_comm *comm, const u64 *mine, size_t count, u64 *all);
 // in-place sum / max over ranks of `count` 64-bit words in device memory (`d_tmp`: count words of scratch)
 void comm_allreduce_u64(esa_ctx *ctx, esa_comm *comm, u64 *d_buf, u64 *d_tmp, size_t count, bool max_instead_of_sum);
+// reduce-scatter: d_full holds nranks * slice_words 64-bit words on every rank; rank r receives in d_out the sums over
+// the ranks of the words [r * slice_words, (r + 1) * slice_words)
+void comm_reduce_scatter_sum_u64(esa_ctx *ctx, esa_comm *comm, const u64 *d_full, u64 *d_out, size_t slice_words);
 // in-place all-gather of equal byte slices: rank r's slice lives at d_buf + r*slice on every rank
 void comm_allgather_bytes(esa_ctx *ctx, esa_comm *comm, u8 *d_buf, size_t slice);
 // variable all-to-all of 32-bit words: counts/offsets are host arrays of nranks entries (in words);

@@ -228,6 +228,8 @@ struct esa_ctx
   // sharded build: this rank holds suffix-array entries [shard_first, shard_first + shard_count) in d_sa, d_suf64,
   // d_lcp, d_bwt, d_hround (all indexed from 0); one GPU: [0, n+1)
   u64 shard_first = 0, shard_count = 0;
+  // tables indexed by TEXT position (sti1, sti): the whole text on one GPU, this rank's slice in a sharded build
+  u64 text_first = 0, text_count = 0;
   size_t arena_after_upload = 0;
   struct esa_comm *comm = nullptr;  // attached communicator (sharded builds), see comm.cuh
 
@@ -359,5 +361,6 @@ void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 in
 void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev, const u32 *deep_v = nullptr,
                             u32 deep_round = 255);
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
+void compute_sti_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, u32 demand);  // .sti1 / .sti of a sharded build
 void compute_skp(esa_ctx *ctx, const u32 *d_v, const u32 *d_lcpfull);  // skp.cu
 int run_checks(esa_ctx *ctx, std::string &msg);

@@ -5,6 +5,7 @@
 //   sti1:      makestitab1 (src/Mkvtree/mkvprocess.c:583-643) restated per text position:
 //              sti1[s] = 0 if a special lies inside the k-prefix of s, else min(255, isa[s] - bck.left[kmer(s)])
 //   checks:    the reference's DEBUG invariants as device-side property checks.
+#include "comm.cuh"
 #include "kmer_scan.cuh"
 #include "llv.cuh"
 #include "scan.cuh"
@@ -452,6 +453,90 @@ void compute_sti1(esa_ctx *ctx, u32 prefixlength)
   ESA_LAUNCH(ctx, ESA_K_STI1, 14.0 * N,
              (sti1_kernel<<<tiles, KS_THREADS, 0, ctx->stream>>>(ctx->d_tis, ctx->n, kp, ctx->d_isa, ctx->d_bck,
                                                                   ctx->d_sti1)));
+}
+
+// ---- sharded builds: the tables that are indexed by TEXT position (.sti1, .sti) ----
+// A rank knows the values of the suffixes of its suffix-array range, which lie anywhere in the text: every rank writes
+// them into a zeroed table of the whole text, and a reduce-scatter (sum: every position is written by exactly one rank)
+// leaves rank g with the text slice [g * slice, (g + 1) * slice) -- concatenated in rank order, the reference's files.
+// makestitab1 (src/Mkvtree/mkvprocess.c:583-643) per suffix-array entry: 0 when a special lies inside the k-prefix,
+// else min(255, index - left border of the k-mer's bucket); full inverse: mksti.c:15-34.
+namespace
+{
+template <typename T>
+__global__ void sti_sharded_kernel(const u8 *__restrict__ tis, const u32 *__restrict__ sa, u64 count, u64 index_base,
+                                   u32 sigma, u32 k, const u64 *__restrict__ bck, T *__restrict__ full)
+{
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= count)
+  {
+    return;
+  }
+  const u64 s = sa[r], R = index_base + r;
+  if (sizeof(T) == 4)
+  {
+    full[s] = (T) R;  // inverse suffix array
+    return;
+  }
+  u64 code = 0;
+  for (u32 i = 0; i < k; i++)
+  {
+    const u32 a = tis[s + i];  // padded with 255 behind position n
+    if (a >= ESA_WILDCARD)
+    {
+      return;  // special inside the prefix: 0
+    }
+    code = code * sigma + a;
+  }
+  const u64 off = R - bck[2 * code];
+  full[s] = (T) (off < 255 ? off : 255);
+}
+}  // namespace
+
+void compute_sti_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, u32 demand)
+{
+  const u64 N = ctx->n + 1;
+  const int G = comm->nranks, me = comm->rank;
+  cudaStream_t s = ctx->stream;
+  Arena &ar = ctx->arena;
+  const u64 slice = div_up_u64(div_up_u64(N, (u64) G), 64) * 64;  // text positions per rank
+  ctx->text_first = (u64) me * slice < N ? (u64) me * slice : N;
+  ctx->text_count = ((u64) (me + 1) * slice < N ? (u64) (me + 1) * slice : N) - ctx->text_first;
+  const u32 grid = (u32) div_up_u64(ctx->shard_count > 0 ? ctx->shard_count : 1, 256);
+  if (demand & ESA_STI1TAB)
+  {
+    ctx->d_sti1 = ar.alloc<u8>(slice + 64);
+    const size_t mark = ar.mark();
+    u8 *full = ar.alloc<u8>(slice * G + 64);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, (double) slice * G, CUDA_CHECK(cudaMemsetAsync(full, 0, slice * G, s)));
+    if (ctx->shard_count > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_STI1, 14.0 * ctx->shard_count,
+                 (sti_sharded_kernel<u8><<<grid, 256, 0, s>>>(ctx->d_tis, ctx->d_sa, ctx->shard_count, ctx->shard_first,
+                                                               ctx->sigma, prefixlength, ctx->d_bck, full)));
+    }
+    comm_reduce_scatter_sum_u64(ctx, comm, (const u64 *) full, (u64 *) ctx->d_sti1, slice / 8);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ar.rewind(mark);
+  }
+  if (demand & ESA_STITAB)
+  {
+    ctx->d_sti64 = ar.alloc<u64>(slice + 8);
+    const size_t mark = ar.mark();
+    u32 *full = ar.alloc<u32>(slice * G + 16), *mine = ar.alloc<u32>(slice + 16);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 4.0 * slice * G, CUDA_CHECK(cudaMemsetAsync(full, 0, 4 * slice * G, s)));
+    if (ctx->shard_count > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_FINALIZE, 8.0 * ctx->shard_count,
+                 (sti_sharded_kernel<u32><<<grid, 256, 0, s>>>(ctx->d_tis, ctx->d_sa, ctx->shard_count, ctx->shard_first,
+                                                                ctx->sigma, prefixlength, ctx->d_bck, full)));
+    }
+    comm_reduce_scatter_sum_u64(ctx, comm, (const u64 *) full, (u64 *) mine, slice / 2);
+    ESA_LAUNCH(ctx, ESA_K_FINALIZE, 12.0 * slice,
+               (widen_kernel<<<div_up_u32(slice, 256), 256, 0, s>>>(mine, ctx->d_sti64, slice)));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ar.rewind(mark);
+  }
 }
 
 void widen_isa(esa_ctx *ctx)

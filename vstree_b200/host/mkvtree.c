@@ -24,6 +24,8 @@
 #include <errno.h>
 #include <limits.h>
 #include <pthread.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -1341,6 +1343,108 @@ typedef struct
   char err[512];
 } Rankjob;
 
+/* The suffix table is 8 of the 10 output bytes per suffix.  On one GPU it is never copied on the host: the .suf file is
+ * created and mapped as soon as the sequence length is known, its pages are touched by a few threads while the main
+ * thread writes the host-side tables and waits for the device, and the library downloads the table straight into the
+ * mapping (esa_set_result_allocator).  What is left at the place where the reference writes .suf is the -v line. */
+typedef struct
+{
+  char name[PATH_MAX + 16];
+  int fd;
+  uint8_t *map;
+  uint64_t bytes;
+  int used;       /* the library took the mapping */
+  pthread_t touch[4];
+  int ntouch;
+} Mappedtable;
+
+typedef struct
+{
+  uint8_t *begin, *end;
+} Touchjob;
+static Touchjob touchjobs[4];
+
+static void *touchmain(void *arg)
+{
+  Touchjob *j = (Touchjob *) arg;
+  for (uint8_t *p = j->begin; p < j->end; p += 4096)
+  {
+    *(volatile uint8_t *) p = 0;
+  }
+  return NULL;
+}
+
+static void mapoutput(Mappedtable *m, const char *indexname, const char *suffix, uint64_t bytes)
+{
+  memset(m, 0, sizeof *m);
+  m->fd = -1;
+  snprintf(m->name, sizeof m->name, "%s.%s", indexname, suffix);
+  m->fd = open(m->name, O_RDWR | O_CREAT | O_EXCL, 0666);
+  if (m->fd < 0)
+  {
+    return;  /* the ordinary write path will report what is wrong */
+  }
+  if (ftruncate(m->fd, (off_t) bytes) != 0
+      || (m->map = (uint8_t *) mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, m->fd, 0)) == (uint8_t *) MAP_FAILED)
+  {
+    close(m->fd);
+    unlink(m->name);
+    m->fd = -1;
+    m->map = NULL;
+    return;
+  }
+  m->bytes = bytes;
+  for (int t = 0; t < 4; t++)
+  {
+    const uint64_t part = ((bytes / 4) + 4095) & ~(uint64_t) 4095;
+    touchjobs[t].begin = m->map + (uint64_t) t * part < m->map + bytes ? m->map + (uint64_t) t * part : m->map + bytes;
+    touchjobs[t].end = m->map + (uint64_t) (t + 1) * part < m->map + bytes ? m->map + (uint64_t) (t + 1) * part : m->map + bytes;
+    if (pthread_create(&m->touch[m->ntouch], NULL, touchmain, &touchjobs[t]) == 0)
+    {
+      m->ntouch++;
+    }
+  }
+}
+
+static void jointouchers(Mappedtable *m)
+{
+  for (int t = 0; t < m->ntouch; t++)
+  {
+    pthread_join(m->touch[t], NULL);
+  }
+  m->ntouch = 0;
+}
+
+static void dropmapping(Mappedtable *m, int keepfile)
+{
+  jointouchers(m);
+  if (m->map != NULL)
+  {
+    munmap(m->map, m->bytes);
+    m->map = NULL;
+  }
+  if (m->fd >= 0)
+  {
+    close(m->fd);
+    m->fd = -1;
+    if (!keepfile)
+    {
+      unlink(m->name);
+    }
+  }
+}
+
+static void *mappedalloc(void *user, uint32_t table, uint64_t bytes)
+{
+  Mappedtable *m = (Mappedtable *) user;
+  if (table == ESA_SUFTAB && m->map != NULL && bytes == m->bytes)
+  {
+    m->used = 1;
+    return m->map;
+  }
+  return NULL;
+}
+
 /* The CUDA context of a one-shot process costs more than parsing 100 Mbp: esa_init (context, streams, kernel images) runs
  * on its own thread while the main thread reads and transforms the input; joined right before the build.  Nothing is
  * allocated there (pinning gigabytes next to the page-cache traffic of the parser was tried in round 1 and proved
@@ -1388,8 +1492,10 @@ static int writeranges(const char *indexname, const char *suffix, FILE *fp, Rank
   {
     const esa_result *res = &jobs[r].res;
     const void *data = which == 0 ? (const void *) res->lcptab : which == 1 ? (const void *) res->llv
-                     : which == 2 ? (const void *) res->suftab : (const void *) res->bwttab;
-    const uint64_t count = which == 1 ? res->nllv : res->shard_count;
+                     : which == 2 ? (const void *) res->suftab : which == 3 ? (const void *) res->bwttab
+                     : (const void *) res->stitab1;
+    /* suffix-array tables come in ranges of the suffix array, .sti1 in slices of the text; both in rank order */
+    const uint64_t count = which == 1 ? res->nllv : which == 4 ? res->text_count : res->shard_count;
     if (count > 0 && fwrite(data, size, count, fp) != count)
     {
       fclose(fp);
@@ -1422,11 +1528,19 @@ int main(int argc, char **argv)
   int rc, dosort, somethingout;
   FILE *lcpfp = NULL;
   Earlyinit early;
+  Mappedtable sufmap;
   const int timing = getenv("MKVTREE_TIMING") != NULL;
   const double t_start = nowseconds();
-  double t_parsed = 0, t_hosttables = 0, t_built = 0;
+  double t_parsed = 0, t_hosttables = 0, t_built = 0, t_context = 0;
 
   memset(&early, 0, sizeof early);
+  memset(&sufmap, 0, sizeof sufmap);
+  sufmap.fd = -1;
+  /* a one-shot process: kernel images are loaded with the context (on the thread that starts it behind the parser, not
+     one by one at the first launches of the build: 0.45 s of a cold 100 Mbp build), and the tables come back into
+     ordinary memory (pinning 1.3 GB costs more than the staged copy); an existing setting of the user wins */
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+  setenv("ESA_PAGEABLE_RESULTS", "1", 0);
   rc = parseoptions(&opt, argc, argv);
   if (rc == 1)
   {
@@ -1592,6 +1706,10 @@ int main(int argc, char **argv)
   {
     goto failure;
   }
+  if ((opt.demand & ESA_SUFTAB) && getenv("MKVTREE_GPUS") == NULL && getenv("MKVTREE_NO_MAPPED_SUF") == NULL)
+  {
+    mapoutput(&sufmap, opt.indexname, "suf", 8 * ((uint64_t) ms.totallength + 1));
+  }
   if (somethingout && ms.numofsequences > 1
       && writetable(opt.indexname, "ssp", ms.markpos, sizeof(uint64_t), ms.numofsequences - 1, 0) != 0)
   {
@@ -1669,6 +1787,7 @@ int main(int argc, char **argv)
           }
           jobs[0].ctx = early.ctx;
           early.ctx = NULL;
+          t_context = nowseconds();
         } else if (esa_init(&jobs[r].ctx, device, err, sizeof err) != 0)
         {
           fail("%s", err);
@@ -1687,6 +1806,11 @@ int main(int argc, char **argv)
       }
       if (njobs == 1)
       {
+        if (sufmap.map != NULL)
+        {
+          jointouchers(&sufmap);
+          esa_set_result_allocator(jobs[0].ctx, mappedalloc, &sufmap);
+        }
         rankmain(&jobs[0]);
       } else
       {
@@ -1766,11 +1890,20 @@ int main(int argc, char **argv)
     {
       goto failure;
     }
-    if ((opt.demand & ESA_SUFTAB) && writeranges(opt.indexname, "suf", NULL, jobs, njobs, sizeof(uint64_t), 2) != 0)
+    if ((opt.demand & ESA_SUFTAB) && sufmap.used)
     {
-      goto failure;
+      say("create file \"%s\"", sufmap.name);  /* the table is in the mapped file already */
+      dropmapping(&sufmap, 1);
+      jobs[0].res.suftab = NULL;
+    } else
+    {
+      dropmapping(&sufmap, 0);
+      if ((opt.demand & ESA_SUFTAB) && writeranges(opt.indexname, "suf", NULL, jobs, njobs, sizeof(uint64_t), 2) != 0)
+      {
+        goto failure;
+      }
     }
-    if ((opt.demand & ESA_STI1TAB) && writetable(opt.indexname, "sti1", res.stitab1, 1, ms.totallength + 1, 1) != 0)
+    if ((opt.demand & ESA_STI1TAB) && writeranges(opt.indexname, "sti1", NULL, jobs, njobs, 1, 4) != 0)
     {
       goto failure;
     }
@@ -1903,6 +2036,13 @@ alphabetwritten:;
   }
   {
     const double t_written = nowseconds();
+    if (ctx != NULL && getenv("MKVTREE_TEARDOWN") == NULL && !timing)
+    {
+      /* every file is closed: leave the release of the device context and of a gigabyte of tables to the operating
+         system (0.14 s of a 100 Mbp run when done call by call) */
+      fflush(NULL);
+      _exit(EXIT_SUCCESS);
+    }
     if (ctx != NULL)
     {
       int r;
@@ -1915,15 +2055,18 @@ alphabetwritten:;
     }
     if (timing)
     {
-      fprintf(stderr, "MKVTREE_TIMING parse %.3f s, host tables %.3f s, device (wait for context + upload + build + "
-                      "download) %.3f s [build on device %.3f s], table output %.3f s, teardown %.3f s, total %.3f s\n",
-              t_parsed - t_start, t_hosttables - t_parsed, dosort ? t_built - t_hosttables : 0.0, stats.ms_total * 1e-3,
-              dosort ? t_written - t_built : t_written - t_hosttables, nowseconds() - t_written, nowseconds() - t_start);
+      fprintf(stderr, "MKVTREE_TIMING parse %.3f s, host tables %.3f s, wait for context %.3f s, esa_build %.3f s [upload "
+                      "%.3f, build on device %.3f, download tail %.3f], table output %.3f s, teardown %.3f s, total %.3f s\n",
+              t_parsed - t_start, t_hosttables - t_parsed, t_context > 0 ? t_context - t_hosttables : 0.0,
+              dosort ? t_built - (t_context > 0 ? t_context : t_hosttables) : 0.0, stats.ms_h2d * 1e-3,
+              stats.ms_total * 1e-3, stats.ms_d2h * 1e-3, dosort ? t_written - t_built : t_written - t_hosttables,
+              nowseconds() - t_written, nowseconds() - t_start);
     }
   }
   return EXIT_SUCCESS;
 
 failure:
+  dropmapping(&sufmap, 0);
   fprintf(stderr, "%s: %s\n", argv[0], message);
   return EXIT_FAILURE;
 }
