@@ -42,7 +42,7 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #define ESA_SORT_CHAIN 1     // serial chain through the warp counters without shuffles
 #endif
 #ifndef ESA_SORT_MATCH
-#define ESA_SORT_MATCH 0  // 0: eight ballots per key, 1: shared-memory atomicOr lane masks
+#define ESA_SORT_MATCH 0  // 0: eight ballots per key, 1: shared-memory atomicOr lane masks, 2: MATCH.ANY
 #endif
 #ifndef ESA_SORT_OVERLAP
 #define ESA_SORT_OVERLAP 1  // look-back (warps 0-7) runs while the other warps already reorder their keys
@@ -384,7 +384,9 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
   {
     const u32 d = DIGIT(keys[i]);
     u32 peers = FULL_MASK;
-#if ESA_SORT_XMASK
+#if ESA_SORT_MATCH == 2
+    peers = __match_any_sync(FULL_MASK, d);  // one MATCH.ANY instead of eight ballots (tuning variant)
+#elif ESA_SORT_XMASK
     peers = match_digit_bits<0>(~d, peers);
 #else
 #pragma unroll
