@@ -692,12 +692,16 @@ void do_construct(FullCtx *ctx, u32 prefixlength, u32 demand, esa_stats *stats)
   }
   const bool want_lcp = (demand & ESA_LCPTAB) != 0;
   ctx->d_pk = nullptr;
+  ctx->d_pk5 = nullptr;
   ctx->d_spm = nullptr;
   ctx->d_hround = nullptr;
   ctx->lcp_work_estimate = 0;
   if (ctx->sigma <= 4)
   {
     pack_text(ctx);  // 2-bit text + special mask: text keys of the sorter, suffix-start accesses of lcp and bwt
+  } else if (ctx->sigma <= 30 && getenv("ESA_NO_PACK5") == nullptr)
+  {
+    pack_text5(ctx);  // 5-bit records (protein): one load per suffix start instead of three
   }
   if (want_lcp && ctx->lcp_mode != 2 && !sharded)
   {

@@ -196,6 +196,7 @@ struct esa_ctx
   // resident input
   u8 *d_tis = nullptr;   // arena; n symbols followed by >= 64 bytes of 255
   u64 *d_pk = nullptr;   // 2-bit packed text (sigma <= 4 only), see textcmp.cuh
+  u64 *d_pk5 = nullptr;  // 5-bit packed text (5 <= sigma <= 30: protein), see textcmp.cuh
   u32 *d_spm = nullptr;  // special mask of the packed text
   u8 *d_hround = nullptr;  // [N] doubling round in which slot r became a group head (lcp lower bound), 0 = initial sort
   DepthSched sched;        // depth schedule of the last sort (turns d_hround entries into lcp lower bounds)
@@ -356,6 +357,7 @@ void compute_plcp_deep(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev, u3
 
 // derive.cu
 void pack_text(esa_ctx *ctx);  // fills ctx->d_pk / d_spm from d_tis (sigma <= 4)
+void pack_text5(esa_ctx *ctx);  // fills ctx->d_pk5 from d_tis (5 <= sigma <= 30)
 void finalize_tables(esa_ctx *ctx, u32 demand, const u32 *d_v, u64 count, u64 index_base);
 // lcp_direct.cu; deep_v / deep_round: slots split off in a round >= deep_round take their lcp from deep_v (hybrid)
 void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev, const u32 *deep_v = nullptr,

@@ -355,6 +355,12 @@ void compute_plcp_deep(esa_ctx *ctx, esa_comm *comm, u32 *d_v, u32 halo_prev, u3
       ESA_LAUNCH(ctx, ESA_K_PLCP, 5.0 * count,
                  (plcp_deep_kernel<TextPacked2><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround, ctx->sched,
                                                                       deep_round, halo_prev, d_v, tile_flag, list, d_cnt)));
+    } else if (ctx->d_pk5 != nullptr)
+    {
+      TextPacked5 text{ctx->d_pk5};
+      ESA_LAUNCH(ctx, ESA_K_PLCP, 5.0 * count,
+                 (plcp_deep_kernel<TextPacked5><<<grid, 256, 0, s>>>(text, count, ctx->d_sa, ctx->d_hround, ctx->sched,
+                                                                      deep_round, halo_prev, d_v, tile_flag, list, d_cnt)));
     } else
     {
       TextBytes text{ctx->d_tis};
@@ -407,6 +413,12 @@ void compute_plcp(esa_ctx *ctx, u32 *d_v)
     TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * N,
                (plcp_irreducible_kernel<TextPacked2><<<tiles, PL_THREADS, 0, s>>>(text, n, ctx->d_sa, ctx->d_isa, d_v,
+                                                                                   tile_last)));
+  } else if (ctx->d_pk5 != nullptr)
+  {
+    TextPacked5 text{ctx->d_pk5};
+    ESA_LAUNCH(ctx, ESA_K_PLCP, 14.0 * N,
+               (plcp_irreducible_kernel<TextPacked5><<<tiles, PL_THREADS, 0, s>>>(text, n, ctx->d_sa, ctx->d_isa, d_v,
                                                                                    tile_last)));
   } else
   {

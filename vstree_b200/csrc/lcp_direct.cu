@@ -96,6 +96,44 @@ pack2_kernel(const u8 *__restrict__ tis, u64 n, u64 padded_len, u64 words, u64 *
   spm[w] = mask;
 }
 
+// one thread per 5-bit record (layout: textcmp.cuh, TextPacked5): the 24 symbols starting one in front of position 16w
+__global__ void __launch_bounds__(256)
+pack5_kernel(const u8 *__restrict__ tis, u64 n, u64 words, u64 *__restrict__ pk)
+{
+  const u64 w = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words)
+  {
+    return;
+  }
+  const u64 p0 = w * 16;
+  u64 lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < 24; j++)
+  {
+    const u64 pos = p0 + j;  // text position + 1
+    u32 c = TextPacked5::CODE_SEPARATOR;
+    if (pos >= 1 && pos - 1 < n)
+    {
+      const u32 a = tis[pos - 1];
+      c = a < ESA_WILDCARD ? a : (a == ESA_WILDCARD ? TextPacked5::CODE_WILDCARD : TextPacked5::CODE_SEPARATOR);
+    }
+    const int sh = 5 * j;
+    if (sh < 64)
+    {
+      lo |= (u64) c << sh;
+      if (sh > 59)
+      {
+        hi |= (u64) c >> (64 - sh);
+      }
+    } else
+    {
+      hi |= (u64) c << (sh - 64);
+    }
+  }
+  pk[2 * w] = lo;
+  pk[2 * w + 1] = hi;
+}
+
 // scalars: [0] maxbranchdepth [1] longest [2] nllv
 template <typename Text>
 __global__ void __launch_bounds__(FN_THREADS)
@@ -277,6 +315,15 @@ void pack_text(esa_ctx *ctx)
   CUDA_CHECK(cudaGetLastError());
 }
 
+void pack_text5(esa_ctx *ctx)
+{
+  const u64 n = ctx->n, N = n + 1;
+  const u64 words = (N + 15) / 16 + 4;
+  ctx->d_pk5 = ctx->arena.alloc<u64>(2 * words);  // 16-byte records
+  pack5_kernel<<<div_up_u32(words, 256), 256, 0, ctx->stream>>>(ctx->d_tis, n, words, ctx->d_pk5);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 // lcp (when demanded) by direct comparison; fills d_lcp, d_llv, d_bwt, d_suf64, maxbranchdepth, longest, nllv
 void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base, u32 halo_prev, const u32 *deep_v,
                             u32 deep_round)
@@ -313,6 +360,13 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base,
     TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
     ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
                (finalize_direct_kernel<TextPacked2><<<tiles, FN_THREADS, 0, s>>>(
+                   text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
+                   ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev, deep_v, deep_v != nullptr ? deep_round : 255u)));
+  } else if (ctx->d_pk5 != nullptr)
+  {
+    TextPacked5 text{ctx->d_pk5};
+    ESA_LAUNCH(ctx, ESA_K_FINALIZE, bytes,
+               (finalize_direct_kernel<TextPacked5><<<tiles, FN_THREADS, 0, s>>>(
                    text, ctx->d_tis, N, ctx->d_sa, ctx->d_hround, ctx->sched, want_lcp, ctx->d_lcp, lcpfull, ctx->d_bwt,
                    ctx->d_suf64, tile_large, d_scalars, index_base, halo_prev, deep_v, deep_v != nullptr ? deep_round : 255u)));
   } else

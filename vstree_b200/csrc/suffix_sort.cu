@@ -1030,6 +1030,7 @@ struct TextKeyParams
 {
   const u8 *tis;
   TextPacked2 packed;  // packed.pk == nullptr: byte path
+  TextPacked5 packed5; // packed5.pk != nullptr: 5-bit records (L <= 8)
   u32 len;             // L
   u32 flag_bits;       // F = bits_for(L)
   u32 sigma;
@@ -1059,6 +1060,23 @@ text_key_kernel(u64 *__restrict__ key, const u32 *__restrict__ pos, u64 m, u64 h
     {
       code |= ((u64) 1 << (2 * (L - d))) - 1;
       flag = L - d;
+    }
+  } else if (tk.packed5.pk != nullptr)
+  {
+    const u64 w = tk.packed5.window(q);  // 8 symbols >= L
+    for (u32 i = 0; i < L; i++)
+    {
+      const u32 a = TextPacked5::window_symbol(w, i);
+      if (a >= ESA_WILDCARD)
+      {
+        for (u32 j = i; j < L; j++)
+        {
+          code = code * tk.sigma + (tk.sigma - 1);
+        }
+        flag = L - i;
+        break;
+      }
+      code = code * tk.sigma + a;
     }
   } else
   {
@@ -1243,6 +1261,7 @@ RefinePlan make_refine_plan(esa_ctx *ctx, u32 rank_shift, u32 h0)
   plan.text_rounds = plan.tks.len > 0 ? text_rounds_setting() : 0;
   plan.tk.tis = ctx->d_tis;
   plan.tk.packed = TextPacked2{packed ? ctx->d_pk : nullptr, ctx->d_spm, ctx->d_tis};
+  plan.tk.packed5 = TextPacked5{(!packed && plan.tks.len <= TextPacked5::WINDOW) ? ctx->d_pk5 : nullptr};
   plan.tk.len = plan.tks.len;
   plan.tk.flag_bits = plan.tks.flag_bits;
   plan.tk.sigma = ctx->sigma;

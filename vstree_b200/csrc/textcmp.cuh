@@ -229,3 +229,119 @@ struct TextPacked2
   }
   __device__ __forceinline__ u32 before(u64 p) const { return before_of(load(p), p); }
 };
+
+// 5-bit records for alphabets of 5 to 30 letters (protein: 20).  One 16-byte record per 16 positions that carries 24
+// symbols: record i holds the text symbols [16i - 1, 16i + 23), symbol j in bits [5j, 5j + 5) of the 128-bit word; codes
+// 0 .. sigma-1 are the letters, 30 the wildcard (254), 31 the separator (255) and everything outside [0, n).  ONE 16-byte
+// load yields, for any position, the symbol in front of it and a window of 8 symbols behind it with the specials inline --
+// the byte view needs two unaligned 8-byte loads for the window and a third load for the symbol in front, and these random
+// accesses are bound by L1 wavefronts per load instruction, not by bytes (same reasoning as TextPacked2).  1 B/symbol.
+struct TextPacked5
+{
+  const u64 *pk;  // records, two words each (lo, hi)
+
+  static constexpr u32 WINDOW = 8;  // symbols per comparison step
+  static constexpr u64 WINDOW_BITS_MASK = ((u64) 1 << (5 * WINDOW)) - 1;
+  static constexpr u64 GROUP_BIT1 = 0x0842108421ull << 1;  // bit 1 of each of the 8 five-bit groups
+  static constexpr u32 CODE_WILDCARD = 30, CODE_SEPARATOR = 31;
+
+  struct Rec
+  {
+    u64 lo, hi;
+    u32 o;  // index of position p inside the record: 1..16
+  };
+  __device__ __forceinline__ Rec load(u64 p) const
+  {
+    const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(pk) + (p >> 4));
+    Rec x;
+    x.lo = r.x;
+    x.hi = r.y;
+    x.o = (u32) (p & 15) + 1;
+    return x;
+  }
+  static __device__ __forceinline__ u64 rec_window(const Rec &x)
+  {
+    const u32 sh = 5 * x.o;  // 5..80
+    const u64 w = sh < 64 ? ((x.lo >> sh) | (x.hi << (64 - sh))) : (x.hi >> (sh - 64));
+    return w & WINDOW_BITS_MASK;
+  }
+  static __device__ __forceinline__ u32 rec_symbol(const Rec &x, u32 j)  // record symbol j (0..23)
+  {
+    const u32 sh = 5 * j;
+    u64 w;
+    if (sh < 64)
+    {
+      w = x.lo >> sh;
+      if (sh > 59)
+      {
+        w |= x.hi << (64 - sh);  // symbol 12 straddles the two words
+      }
+    } else
+    {
+      w = x.hi >> (sh - 64);
+    }
+    return (u32) (w & 31u);
+  }
+  __device__ __forceinline__ u64 window(u64 p) const { return rec_window(load(p)); }
+  // symbol k of a window as a tis byte value (letters as they are, 254, 255)
+  static __device__ __forceinline__ u32 window_symbol(u64 w, u32 k)
+  {
+    const u32 c = (u32) (w >> (5 * k)) & 31u;
+    return c < CODE_WILDCARD ? c : (c == CODE_WILDCARD ? (u32) ESA_WILDCARD : (u32) ESA_SEPARATOR);
+  }
+  struct Probe
+  {
+    u64 w;
+    u32 before;
+  };
+  static __device__ __forceinline__ Probe probe_from_lane_below(u32 mask, const Probe &x)
+  {
+    Probe r;
+    r.w = __shfl_up_sync(mask, x.w, 1);
+    r.before = __shfl_up_sync(mask, x.before, 1);
+    return r;
+  }
+  static __device__ __forceinline__ u32 before_of(const Rec &x, u64 p)
+  {
+    if (p == 0)
+    {
+      return 255u;
+    }
+    const u32 c = rec_symbol(x, x.o - 1);
+    return c < CODE_WILDCARD ? c : (c == CODE_WILDCARD ? (u32) ESA_WILDCARD : (u32) ESA_SEPARATOR);
+  }
+  __device__ __forceinline__ Probe probe(u64 p) const
+  {
+    const Rec x = load(p);
+    Probe r;
+    r.w = rec_window(x);
+    r.before = before_of(x, p);
+    return r;
+  }
+  // equal leading letters of two windows: 0..WINDOW; a special (codes 30, 31: the four high bits of the group are set)
+  // on the first side ends the match even when the other side holds the same code
+  static __device__ __forceinline__ u32 stop_of(u64 wa, u64 wb)
+  {
+    const u64 diff = wa ^ wb;
+    const u64 sp = wa & (wa >> 1) & (wa >> 2) & (wa >> 3) & GROUP_BIT1;
+    const u32 stop_mis = diff ? (u32) (__ffsll((long long) diff) - 1) / 5u : WINDOW;
+    const u32 stop_sp = sp ? (u32) (__ffsll((long long) sp) - 1) / 5u : WINDOW;
+    return min(stop_mis, stop_sp);
+  }
+  static __device__ __forceinline__ u32 probe_stop(const Probe &a, const Probe &b) { return stop_of(a.w, b.w); }
+  __device__ __forceinline__ u32 step(u64 pa, u64 pb) const { return stop_of(window(pa), window(pb)); }
+  __device__ __forceinline__ u32 lcp(u64 a, u64 b, u32 start) const
+  {
+    u32 l = start;
+    while (true)
+    {
+      const u32 stop = step(a + l, b + l);
+      l += stop;
+      if (stop < WINDOW)
+      {
+        return l;
+      }
+    }
+  }
+  __device__ __forceinline__ u32 before(u64 p) const { return before_of(load(p), p); }
+};
