@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from vstree_b200 import Esa, synth  # noqa: E402
 from vstree_b200.capi import comm_unique_id, merge_shards  # noqa: E402
 
-TABLES = ("suf", "lcp", "bwt", "bck")
+TABLES = ("suf", "lcp", "bwt", "bck", "sti1", "sti")  # sti1 / sti: slices of the text (reduce-scatter between the ranks)
 
 
 def main():
@@ -22,6 +22,8 @@ def main():
     box = [comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     cases = [("human_like", synth.human_like_dna(6_000_000, seed=3, records=5), 4, 9),
+             ("repeat_deep", synth.repeat_rich_dna(3_000_000, seed=8, copies=12, divergence=0.002, tandem_frac=0.05,
+                                                   tandem_len=6000), 4, 8),  # lcp values beyond the deep threshold
              ("protein", synth.random_protein(2_000_000, seed=4, records=500, xfrac=0.001), 20, 4),
              ("tiny", np.array([0, 1, 2, 3, 254, 0, 1, 2, 255, 0, 1, 2, 3, 255, 254, 254, 0, 1], np.uint8), 4, 1)]
     esa = Esa(local)
@@ -38,7 +40,7 @@ def main():
             for name, tis, sigma, k, gathered, st in parts_all:
                 want, _ = one.build(tis, sigma, k, TABLES)
                 got = merge_shards(gathered)
-                for t in ("suf", "lcp", "llv", "bwt", "bck"):
+                for t in ("suf", "lcp", "llv", "bwt", "bck", "sti1", "sti"):
                     assert np.array_equal(got[t], want[t]), f"{name}: {t} differs between {world} ranks and one GPU"
                 for sc in ("longest", "maxbranchdepth", "largelcpvalues"):
                     assert got[sc] == want[sc], f"{name}: {sc}"
