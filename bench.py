@@ -498,9 +498,9 @@ def main():
         assert same, f"sharded tables differ from the single-GPU build: {verify}"
 
     cpu, e2e_cli = None, None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # (at N > 1 the reference arm of the driver is the CPU figure)
         try:
-            sec, kind, cores, ours_sec = time_reference_cli(tis, sigma, flag, k, also_ours=(world == 1))
+            sec, kind, cores, ours_sec = time_reference_cli(tis, sigma, flag, k, also_ours=True)
             cpu = {"value": n / sec / 1e6, "unit": "Mbp/s" if flag == "-dna" else "Mres/s", "cores": cores,
                    "kind": kind, "sample": f"the whole workload once ({n} symbols), CLI wall time incl. FASTA parse and "
                                            f"file output to tmpfs: {sec:.2f} s"}

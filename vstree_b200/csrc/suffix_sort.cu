@@ -2028,7 +2028,7 @@ extern "C" int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, i
   return ESA_OK;
 }
 
-// WIDE keys (DNA, two or more ranks): a rank's range covers only a part of the code space, so its keys are stored
+// WIDE keys (DNA, three or more ranks): a rank's range covers only a part of the code space, so its keys are stored
 // relative to the first code of the range -- (code - base) << 1 | flag -- and 16 symbols fit where the absolute key
 // holds 15.  The round that follows the initial sort then starts from a quarter of the collisions (800 Mbp on eight
 // ranks: 17 % of the suffixes active instead of 52 %).  Needs every range narrower than 2^31 codes, i.e. fewer than 128
@@ -2652,7 +2652,8 @@ void suffix_sort_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, bool wa
                          SortOutcome *outcome)
 {
   static const bool no_wide = getenv("ESA_NO_WIDE_KEY") != nullptr;
-  const bool try_wide = ctx->sigma == 4 && comm->nranks >= 2 && !no_wide;
+  // (two ranks: each range is half of the code space, 2^31 codes, one bit too many)
+  const bool try_wide = ctx->sigma == 4 && comm->nranks >= 3 && !no_wide;
   if (try_wide && suffix_sort_sharded_impl(ctx, comm, prefixlength, want_bck, want_hround, outcome, true))
   {
     return;
