@@ -22,6 +22,7 @@ VARIANTS = {
     "plcp_no_text_round": {"ESA_LCP_MODE": "plcp", "ESA_TEXT_ROUNDS": "0"},
     # hybrid lcp: slots split at a depth of at least ESA_LCP_DEEP symbols take the text-order value (default 1024, which
     # the small inputs rarely reach: force it down); also on a sharded context, where the deep values travel between ranks
+    "dna_emitted_first_pass": {"ESA_NO_TEXT_PASS": "1"},  # initial DNA sort from an emitted (key, position) list
     "protein_byte_text": {"ESA_NO_PACK5": "1"},  # alphabets of 5..30 letters without the 5-bit records
     "lcp_direct_only": {"ESA_LCP_MODE": "direct"},
     "lcp_hybrid_deep16": {"ESA_LCP_DEEP": "16"},
@@ -35,7 +36,7 @@ VARIANTS = {
 def test_sorter_variant_matches_oracle(name):
     env = dict(os.environ)
     for k in ("ESA_TEXT_ROUNDS", "ESA_NO_DNA_CLASSIFY", "ESA_REGROUP_STAGED", "ESA_REGROUP_BLOCKED", "ESA_NO_LOCAL_SORT",
-              "ESA_LCP_MODE", "ESA_LCP_DEEP", "VARIANT_RANKS", "ESA_NO_PACK5"):
+              "ESA_LCP_MODE", "ESA_LCP_DEEP", "VARIANT_RANKS", "ESA_NO_PACK5", "ESA_NO_TEXT_PASS"):
         env.pop(k, None)
     env.update(VARIANTS[name])
     pr = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variant_worker.py")], capture_output=True,

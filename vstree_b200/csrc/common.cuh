@@ -317,6 +317,11 @@ int radix_sort_pairs_u32(esa_ctx *ctx, u32 *keys_a, u32 *keys_b, u32 *vals_a, u3
 int radix_sort_pairs_u64(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *vals_a, u32 *vals_b, u64 n, u32 begin_bit,
                          u32 end_bit, void *temp, size_t temp_bytes);
 
+// initial sort of a DNA text with the keys of pass 1 taken from the packed text (radix_sort.cu); same return convention
+int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 N, u32 h, u64 nfull,
+                           const u32 *side_key, const u32 *side_pos, u64 nside, u32 *keys_a, u32 *keys_b, u32 *vals_a,
+                           u32 *vals_b, u32 key_bits, void *temp, size_t temp_bytes);
+
 // the partition step of the sharded build fused with its all-to-all (stores into peer memory); see radix_sort.cu
 struct RadixRemoteDst
 {

@@ -13,6 +13,7 @@
 //                          (88 warp instructions per 32 pairs): see DESIGN.md section 5 for what was measured.
 // Algorithmic bytes: hist = n*sizeof(key); pass = 2*n*(sizeof(key)+sizeof(value)).
 #include "scan.cuh"
+#include "textcmp.cuh"
 #include <algorithm>
 
 namespace
@@ -660,6 +661,322 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------
+// First pass of the initial DNA sort with the keys taken FROM THE PACKED TEXT.
+// classify_dna_emit used to write a (key, position) pair per suffix (8 B), the histogram kernel re-read the keys (4 B)
+// and pass 1 re-read the pairs (8 B).  Key and position of a "full" suffix (no special among its first h symbols) are a
+// function of the text position alone, so the histogram kernel and pass 1 compute them from the 2-bit records
+// (0.5 B per position, staged in shared memory: the 32 positions of a warp row share one record) and the pairs exist
+// for the first time in the OUTPUT of pass 1.  Positions that are not full (special-initial, special inside the
+// prefix, behind the text) are simply not ranked; the few suffixes with a special inside their prefix ("side",
+// already ordered by the caller) follow as extra tiles read from arrays, so that they stay behind the full suffixes
+// with the same padded code, as the stable sort needs (suffix_sort.cu, step 1).
+struct DnaKeySource
+{
+  TextPacked2 text;
+  u64 N;              // positions 0 .. N-1 (N - 1 is the sentinel)
+  u32 h;              // symbols per key
+  u32 text_tiles;     // tiles of tile_items positions
+  const u32 *side_key, *side_pos;
+  u32 nside;
+};
+
+// key (padded code << 1, flag never set for a full suffix) of the position that is symbol o_rec of record words x0..x3;
+// full: no special among the h symbols
+__device__ __forceinline__ u32 dna_full_key(const TextPacked2 &text, u32 x0, u32 x1, u32 x2, u32 x3, u32 o_rec, u32 h, u64 p,
+                                            bool &full)
+{
+  const u32 bitoff = 2 * o_rec, wi = bitoff >> 5, bo = bitoff & 31;
+  const u32 lo32 = wi == 0 ? x0 : (wi == 1 ? x1 : x2), hi32 = wi == 0 ? x1 : (wi == 1 ? x2 : x3);
+  const u32 w32 = __funnelshift_r(lo32, hi32, bo);
+  const u32 gmask = ((2u << (((o_rec + h - 1) >> 3) - (o_rec >> 3))) - 1) << (o_rec >> 3);
+  full = true;
+  if (((x3 >> 24) & gmask) != 0)  // a special among the record symbols around [o, o + h): ask the mask
+  {
+    const u32 msk = text.mask_slow(p);
+    const u32 d = msk ? (u32) (__ffs((int) msk) - 1) : 32u;
+    full = d >= h;
+  }
+  u32 r = __brev(w32);
+  r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);
+  return (r >> (32 - 2 * h)) << 1;
+}
+
+__global__ void __launch_bounds__(HIST_THREADS)
+radix_hist_dna_kernel(DnaKeySource src, u32 end_bit, u32 npass, u32 *__restrict__ hist /* [npass][256] */)
+{
+  __shared__ u32 sh[4 * RADIX];
+  for (u32 i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS)
+  {
+    sh[i] = 0;
+  }
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31;
+  const u64 rows = (src.N + 31) / 32;  // one warp row = the 32 positions of one record
+  constexpr int ROWS = 8;              // records in flight per warp (one record per load: latency, not bytes, is the limit)
+  const u64 warp_global = ((u64) blockIdx.x * HIST_THREADS + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * HIST_THREADS) >> 5;
+  for (u64 row0 = warp_global * ROWS; row0 < rows; row0 += nwarps * ROWS)
+  {
+    ulonglong2 rr[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; j++)
+    {
+      rr[j] = row0 + j < rows ? __ldg(reinterpret_cast<const ulonglong2 *>(src.text.pk) + row0 + j) : make_ulonglong2(0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; j++)
+    {
+      const u64 p = (row0 + j) * 32 + lane;
+      if (p < src.N)
+      {
+        bool full;
+        const u32 key = dna_full_key(src.text, (u32) rr[j].x, (u32) (rr[j].x >> 32), (u32) rr[j].y, (u32) (rr[j].y >> 32), lane + 1,
+                                     src.h, p, full);
+        if (full)
+        {
+          for (u32 q = 0; q < npass; q++)
+          {
+            const u32 shift = q * RADIX_BITS;
+            const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
+            atomicAdd(&sh[q * RADIX + ((key >> shift) & ((1u << bits) - 1))], 1u);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS)
+  {
+    const u32 v = sh[i];
+    if (v != 0)
+    {
+      atomicAdd(&hist[i], v);
+    }
+  }
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
+radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict__ vout, u32 mask /* shift is 0 */,
+                      const u32 *__restrict__ base, volatile u64 *status, u32 *ticket)
+{
+  constexpr int TILE = SORT_THREADS * ITEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64 *skv = (u64 *) smem_raw;                  // [TILE] reordered (key, position) pairs
+  u32 *wc = (u32 *) (skv + TILE);               // [SORT_WARPS][RADIX]
+  u32 *digit_start = wc + SORT_WARPS * RADIX;   // [RADIX]
+  u32 *gbase = digit_start + RADIX;             // [RADIX]
+  u32 *misc = gbase + RADIX;                    // [0] ticket, [1..8] scan scratch, [9] valid pairs of the tile
+  u32 *thist = misc + 16;                       // [RADIX]
+  ulonglong2 *srec = (ulonglong2 *) (thist + RADIX);  // [TILE / 32] records of a text tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+  {
+    misc[0] = atomicAdd(ticket, 1u);
+  }
+  u32 *mywc = wc + warp * RADIX;
+#pragma unroll
+  for (int d = lane; d < RADIX; d += 32)
+  {
+    mywc[d] = 0;
+  }
+  if (tid < RADIX)
+  {
+    thist[tid] = 0;
+  }
+  __syncthreads();
+  const u32 tile = misc[0];
+  const bool text_tile = tile < src.text_tiles;
+  const u64 tile_base = (u64) tile * TILE;  // text position of item 0 (text tiles)
+  if (text_tile && tid < TILE / 32 && ((tile_base >> 5) + tid) * 32 < src.N + 64)  // (records end 4 behind the text)
+  {
+    srec[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(src.text.pk) + (tile_base >> 5) + tid);
+  }
+  __syncthreads();
+  u32 keys[ITEMS], ranks[ITEMS];
+  u32 valid = 0;  // bit i: item i takes part
+  const u32 wbase = warp * (32 * ITEMS);
+  const u32 side_base = text_tile ? 0u : (tile - src.text_tiles) * (u32) TILE;
+  if (text_tile)
+  {
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      const u64 p = tile_base + wbase + i * 32 + lane;
+      keys[i] = 0;
+      if (p < src.N)
+      {
+        const ulonglong2 rr = srec[warp * ITEMS + i];  // one record per warp row: a broadcast read
+        bool full;
+        keys[i] = dna_full_key(src.text, (u32) rr.x, (u32) (rr.x >> 32), (u32) rr.y, (u32) (rr.y >> 32), (u32) lane + 1, src.h, p,
+                               full);
+        valid |= full ? (1u << i) : 0u;
+      }
+    }
+  } else
+  {
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      const u32 idx = side_base + wbase + i * 32 + lane;
+      keys[i] = idx < src.nside ? src.side_key[idx] : 0u;
+      valid |= idx < src.nside ? (1u << i) : 0u;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    if ((valid >> i) & 1u)
+    {
+      atomicAdd(&thist[keys[i] & mask], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < RADIX)
+  {
+    status[(u64) tile * RADIX + tid] = (tile == 0 ? STATUS_PREFIX : STATUS_AGG) | (u64) thist[tid];
+  }
+  const u32 lt_mask = (1u << lane) - 1;
+  const u32 gt_mask = 0xfffffffeu << lane;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const bool v = (valid >> i) & 1u;
+    const u32 vb = __ballot_sync(FULL_MASK, v);
+    ranks[i] = match_digit_bits<0>(~(keys[i] & mask), vb);  // valid lanes with my digit
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    const bool v = (valid >> i) & 1u;
+    const u32 peers = ranks[i];
+    u32 *cp = mywc + (keys[i] & mask);
+    const u32 r = *cp + __popc(peers & lt_mask);
+    __syncwarp();
+    if (v && (peers & gt_mask) == 0)
+    {
+      *cp = r + 1;
+    }
+    __syncwarp();
+    ranks[i] = r;
+  }
+  __syncthreads();
+  u32 bcount = 0;
+  if (tid < RADIX)
+  {
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+    {
+      bcount += wc[w * RADIX + tid];
+    }
+  }
+  u32 dstart = 0;
+  {
+    const u32 incl = warp_inclusive_sum(bcount);
+    if (tid < RADIX && lane == 31)
+    {
+      misc[1 + warp] = incl;
+    }
+    __syncthreads();
+    if (tid < RADIX)
+    {
+      u32 before = 0;
+#pragma unroll
+      for (int w = 0; w < RADIX / 32; w++)
+      {
+        const u32 t = misc[1 + w];
+        before += w < warp ? t : 0u;
+      }
+      dstart = before + incl - bcount;
+    }
+  }
+  if (tid < RADIX)
+  {
+    u32 run = dstart;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+    {
+      const u32 c = wc[w * RADIX + tid];
+      wc[w * RADIX + tid] = run;
+      run += c;
+    }
+    if (tid == RADIX - 1)
+    {
+      misc[9] = dstart + bcount;  // pairs of the tile
+    }
+  }
+  __syncthreads();
+  if (tid < RADIX)
+  {
+    u32 excl = 0;
+    if (tile != 0)
+    {
+      u32 t = tile - 1;
+      bool found = false;
+      while (!found)
+      {
+        u64 sv[ESA_SORT_LBK];
+#pragma unroll
+        for (int j = 0; j < ESA_SORT_LBK; j++)
+        {
+          const u32 tj = t >= (u32) j ? t - (u32) j : 0u;
+          sv[j] = status[(u64) tj * RADIX + tid];
+        }
+        u32 used = 0;
+#pragma unroll
+        for (int j = 0; j < ESA_SORT_LBK; j++)
+        {
+          const u32 flag = (u32) (sv[j] >> 62);
+          const bool take = !found && used == (u32) j && flag != 0;
+          if (take)
+          {
+            excl += (u32) (sv[j] & STATUS_VALUE_MASK);
+            used++;
+            found = flag == 2;
+          }
+        }
+        t -= found ? 0u : used;
+      }
+      status[(u64) tile * RADIX + tid] = STATUS_PREFIX | (u64) (excl + bcount);
+    }
+    digit_start[tid] = dstart;
+    gbase[tid] = base[tid] + excl - dstart;
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+  {
+    if ((valid >> i) & 1u)
+    {
+      const u32 idx = wbase + i * 32 + lane;
+      const u32 pos = mywc[keys[i] & mask] + ranks[i];
+      const u32 val = text_tile ? (u32) (tile_base + idx) : src.side_pos[side_base + idx];
+      skv[pos] = (u64) keys[i] | ((u64) val << 32);
+    }
+  }
+  __syncthreads();
+  const u32 tile_pairs = misc[9];
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++)
+  {
+    const u32 p = j * SORT_THREADS + tid;
+    if (p < tile_pairs)
+    {
+      const u64 kv = skv[p];
+      const u32 k = (u32) kv;
+      const u32 g = gbase[k & mask] + p;
+      kout[g] = k;
+      vout[g] = (u32) (kv >> 32);
+    }
+  }
+}
+
+constexpr size_t pass_dna_smem_bytes()
+{
+  constexpr int TILE = pass_tile_items<SortTraits<u32>::ITEMS>();
+  return (size_t) TILE * 8 + (size_t) SORT_WARPS * RADIX * 4 + 2 * RADIX * 4 + 16 * 4 + RADIX * 4 + (size_t) (TILE / 32) * 16;
+}
+
 template <typename KeyT> constexpr size_t pass_smem_bytes(bool has_vals)
 {
   constexpr int TILE = pass_tile_items<SortTraits<KeyT>::ITEMS>();
@@ -818,6 +1135,8 @@ template <typename KeyT> void set_smem_attr()
 
 void radix_sort_init()
 {
+  CUDA_CHECK(cudaFuncSetAttribute(radix_pass_dna_kernel<SortTraits<u32>::ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int) pass_dna_smem_bytes()));
 
   set_smem_attr<u32>();
   set_smem_attr<u64>();
@@ -871,6 +1190,78 @@ void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, 
                    keys + off, nullptr, vals + off, nullptr, cnt, begin_bit, mask, base + (u64) part * RADIX, status,
                    tickets + part, d_remote)));
   }
+}
+
+
+// The initial sort of a DNA text: M = nfull + nside pairs that exist only implicitly (see radix_pass_dna_kernel).
+// Pass 1 reads the text and writes (keys_b, vals_b); the remaining passes ping-pong as in radix_sort_impl.  Returns 0
+// when the result is in (keys_a, vals_a), 1 when it is in (keys_b, vals_b).
+int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 N, u32 h, u64 nfull,
+                           const u32 *side_key, const u32 *side_pos, u64 nside, u32 *keys_a, u32 *keys_b, u32 *vals_a,
+                           u32 *vals_b, u32 key_bits, void *temp, size_t temp_bytes)
+{
+  constexpr int ITEMS = SortTraits<u32>::ITEMS;
+  constexpr u64 TILE = (u64) pass_tile_items<ITEMS>();
+  const u64 M = nfull + nside;
+  const u32 npass = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+  DnaKeySource src;
+  src.text = TextPacked2{d_pk, d_spm, d_tis};
+  src.N = N;
+  src.h = h;
+  src.text_tiles = (u32) div_up_u64(N, TILE);
+  src.side_key = side_key;
+  src.side_pos = side_pos;
+  src.nside = (u32) nside;
+  const u32 tiles1 = src.text_tiles + (u32) div_up_u64(nside, TILE);
+  const TempLayout L = temp_layout<u32>(N + nside + TILE);  // the status rows of pass 1 cover text tiles + side tiles
+  if (temp_bytes < L.total || npass > 4)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "radix sort scratch too small: %zu < %zu", temp_bytes, L.total);
+  }
+  char *t = (char *) temp;
+  u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off);
+  u64 *status = (u64 *) (t + L.status_off);
+  cudaStream_t s = ctx->stream;
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
+  {
+    const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(N, (u64) HIST_THREADS * HIST_ITEMS));
+    ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, 0.5 * (double) N,
+               (radix_hist_dna_kernel<<<grid, HIST_THREADS, 0, s>>>(src, key_bits, npass, hist)));
+    if (nside > 0)
+    {
+      const u32 g2 = (u32) min((u64) ctx->num_sms * 4, div_up_u64(nside, (u64) HIST_THREADS * HIST_ITEMS));
+      ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, 4.0 * nside,
+                 (radix_hist_kernel<u32><<<g2, HIST_THREADS, 0, s>>>(side_key, (u32) nside, 0, key_bits, npass, hist)));
+    }
+  }
+  ESA_LAUNCH(ctx, ESA_K_MISC, 0, (radix_scan_kernel<<<npass, RADIX, 0, s>>>(hist, base, npass, 1, nullptr)));
+  // pass 1: text -> b
+  {
+    const u32 bits = min((u32) RADIX_BITS, key_bits);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles1 * RADIX * 8, s)));
+    ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 0.5 * (double) N + 8.0 * (double) M + 8.0 * (double) nside,
+               (radix_pass_dna_kernel<ITEMS><<<tiles1, SORT_THREADS, pass_dna_smem_bytes(), s>>>(
+                   src, keys_b, vals_b, (1u << bits) - 1, base, status, tickets)));
+  }
+  u32 *ksrc = keys_b, *kdst = keys_a, *vsrc = vals_b, *vdst = vals_a;
+  const size_t smem = pass_smem_bytes<u32>(true);
+  const u32 tiles = (u32) div_up_u64(M, TILE);
+  for (u32 p = 1; p < npass; p++)
+  {
+    const u32 shift = p * RADIX_BITS;
+    const u32 bits = min((u32) RADIX_BITS, key_bits - shift);
+    ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles * RADIX * 8, s)));
+    ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 16.0 * (double) M,
+               (radix_pass_kernel<u32, true, ITEMS><<<tiles, SORT_THREADS, smem, s>>>(
+                   ksrc, kdst, vsrc, vdst, (u32) M, shift, (1u << bits) - 1, base + (u64) p * RADIX, status, tickets + p)));
+    u32 *kt = ksrc;
+    ksrc = kdst;
+    kdst = kt;
+    u32 *vt = vsrc;
+    vsrc = vdst;
+    vdst = vt;
+  }
+  return ksrc == keys_a ? 0 : 1;
 }
 
 size_t radix_sort_temp_bytes(u64 n, u32 key_bytes)

@@ -305,6 +305,10 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
   const u32 tile = blockIdx.x;
   const u64 tile_base = p_begin + (u64) tile * CD_TILE;
   const u32 lt_mask = (1u << lane) - 1;
+  if (main_key == nullptr && tile_cnt[tile] == 0)
+  {
+    return;  // only the rare classes are wanted (the sort takes the full suffixes from the text) and the tile has none
+  }
   // the tile's 128 records, one coalesced 16-byte load per thread (the 32 positions of a warp share ONE record: loaded
   // per position, a warp-wide load fetched 16 bytes and the sweep ran at 1 ms per 100 Mbp on memory latency alone)
   if (tid < CD_TILE / 32 && ((tile_base >> 5) + tid) * 32 < p_end + 64)  // (records end 4 behind the last position)
@@ -429,9 +433,12 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
     const int e = i * CD_WARPS + warp;
     if (is_full)
     {
-      const u64 o = bfull + cnt[0][e] + __popc(bf & lt_mask);
-      main_key[o] = key[i];
-      main_pos[o] = (u32) p;
+      if (main_key != nullptr)
+      {
+        const u64 o = bfull + cnt[0][e] + __popc(bf & lt_mask);
+        main_key[o] = key[i];
+        main_pos[o] = (u32) p;
+      }
     } else if (is_side)
     {
       const u64 o = bside + cnt[1][e] + __popc(bs & lt_mask);
@@ -1499,15 +1506,21 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
   u32 *key_a = ar.alloc<u32>(Mal), *key_b = ar.alloc<u32>(Mal), *pos_a = sa, *pos_b = ar.alloc<u32>(Mal);
   u32 *side_key = ar.alloc<u32>(nside + 1), *side_pos = ar.alloc<u32>(nside + 1), *side_dj = ar.alloc<u32>(nside + 1),
       *side_tmp = ar.alloc<u32>(nside + 1);
-  const size_t temp_bytes = max(radix_sort_temp_bytes(M, 4), radix_sort_temp_bytes(M, 8));
+  // (the text-keyed first pass of the DNA sort walks tiles of text positions: N of them, plus the side tiles)
+  const size_t temp_bytes = max(radix_sort_temp_bytes(N + nside + 16384, 4), radix_sort_temp_bytes(M, 8));
   void *sort_temp = ar.alloc<char>(temp_bytes);
 
+  // DNA: the full suffixes never exist as an emitted list -- the histogram and the first pass of the sort compute key
+  // and position from the packed text (radix_sort.cu, radix_pass_dna_kernel); only the rare classes are emitted
+  static const bool no_text_pass = getenv("ESA_NO_TEXT_PASS") != nullptr;
+  const bool text_pass = dna_classify && !no_text_pass && M > 1;
+  u32 *side_key_s = nullptr, *side_pos_s = nullptr;  // text pass: the side suffixes in their final relative order
   if (dna_classify)
   {
     const TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
-    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, 0.5 * N + 8.0 * M + 8.0 * nspec,
-               (classify_dna_emit_kernel<<<dtiles, CD_THREADS, 0, s>>>(text, 0, N, h0, M, key_a, pos_a, side_key,
-                                                                        side_pos, side_dj, sa, rank, nullptr,
+    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, text_pass ? 0.125 * N + 12.0 * nside + 8.0 * nspec : 0.5 * N + 8.0 * M + 8.0 * nspec,
+               (classify_dna_emit_kernel<<<dtiles, CD_THREADS, 0, s>>>(text, 0, N, h0, M, text_pass ? nullptr : key_a, pos_a,
+                                                                        side_key, side_pos, side_dj, sa, rank, nullptr,
                                                                         dna_group_shift, dna_tile_cnt, dna_group_cnt)));
   } else
   {
@@ -1516,15 +1529,23 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
                                                                     tile_spec, M, key_a, pos_a, side_key, side_pos,
                                                                     side_dj, sa, rank, nullptr)));
   }
-  // side suffixes: stable sort by h0-j, written straight behind the full ones
+  // side suffixes: stable sort by h0-j, written straight behind the full ones (text pass: into their own arrays)
+  u32 *side_key_dst = key_a + nfull, *side_pos_dst = pos_a + nfull;
+  if (text_pass)
+  {
+    side_key_s = ar.alloc<u32>(nside + 1);
+    side_pos_s = ar.alloc<u32>(nside + 1);
+    side_key_dst = side_key_s;
+    side_pos_dst = side_pos_s;
+  }
   if (nside == 1)
   {
-    CUDA_CHECK(cudaMemcpyAsync(key_a + nfull, side_key, 4, cudaMemcpyDeviceToDevice, s));
-    CUDA_CHECK(cudaMemcpyAsync(pos_a + nfull, side_pos, 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(side_key_dst, side_key, 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(side_pos_dst, side_pos, 4, cudaMemcpyDeviceToDevice, s));
   } else if (nside > 1)
   {
-    int w = radix_sort_pairs_u32(ctx, side_dj, side_tmp, side_pos, pos_a + nfull, nside, 0, 8, sort_temp, temp_bytes);
-    int w2 = radix_sort_pairs_u32(ctx, side_dj, side_tmp, side_key, key_a + nfull, nside, 0, 8, sort_temp, temp_bytes);
+    int w = radix_sort_pairs_u32(ctx, side_dj, side_tmp, side_pos, side_pos_dst, nside, 0, 8, sort_temp, temp_bytes);
+    int w2 = radix_sort_pairs_u32(ctx, side_dj, side_tmp, side_key, side_key_dst, nside, 0, 8, sort_temp, temp_bytes);
     if (w != 1 || w2 != 1)
     {
       esa_throw(ESA_ERR_CUDA, "internal: side sort expected exactly one pass");
@@ -1552,7 +1573,15 @@ void suffix_sort(esa_ctx *ctx, u32 prefixlength, bool want_bck, SortOutcome *out
 
   // ---- 2. the initial sort
   u32 *skey = key_a, *spos = pos_a;
-  if (M > 1)
+  if (text_pass)
+  {
+    if (radix_sort_dna_initial(ctx, ctx->d_pk, ctx->d_spm, ctx->d_tis, N, h0, nfull, side_key_s, side_pos_s, nside, key_a,
+                               key_b, pos_a, pos_b, key_bits, sort_temp, temp_bytes))
+    {
+      skey = key_b;
+      spos = pos_b;
+    }
+  } else if (M > 1)
   {
     if (radix_sort_pairs_u32(ctx, key_a, key_b, pos_a, pos_b, M, 0, key_bits, sort_temp, temp_bytes))
     {
