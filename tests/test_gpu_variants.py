@@ -23,6 +23,7 @@ VARIANTS = {
     # hybrid lcp: slots split at a depth of at least ESA_LCP_DEEP symbols take the text-order value (default 1024, which
     # the small inputs rarely reach: force it down); also on a sharded context, where the deep values travel between ranks
     "dna_emitted_first_pass": {"ESA_NO_TEXT_PASS": "1"},  # initial DNA sort from an emitted (key, position) list
+    "dna_emitted_first_pass_sharded": {"ESA_NO_TEXT_PASS": "1", "VARIANT_RANKS": "3"},
     "protein_byte_text": {"ESA_NO_PACK5": "1"},  # alphabets of 5..30 letters without the 5-bit records
     "lcp_direct_only": {"ESA_LCP_MODE": "direct"},
     "lcp_hybrid_deep16": {"ESA_LCP_DEEP": "16"},

@@ -334,6 +334,13 @@ struct RadixRemoteDst
 void radix_partition_remote_u32(esa_ctx *ctx, const u32 *keys, const u32 *vals, u64 n, u32 begin_bit, u32 end_bit,
                                 const RadixRemoteDst *d_remote, const u32 *d_start, void *temp, size_t temp_bytes);
 
+// the same two steps for a DNA slice with the keys taken from the packed text (radix_sort.cu)
+void radix_bin_hist_dna(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 p_begin, u64 p_end, u32 h,
+                        u32 key_shl, u32 bin_shift, u32 *d_hist256);
+void radix_partition_remote_dna(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 p_begin, u64 p_end,
+                                u32 h, u32 key_shl, u64 nfull, u32 bin_shift, const RadixRemoteDst *d_remote,
+                                const u32 *d_start, void *temp, size_t temp_bytes);
+
 // doubling_sort.cu: the sort of one refinement round (list grouped by key >> shift; sorts by key bits [0, end_bit),
 // end_bit > shift); same return convention as radix_sort_pairs_u64
 int doubling_sort(esa_ctx *ctx, u64 *keys_a, u64 *keys_b, u32 *pos_a, u32 *pos_b, u64 m, u32 shift, u32 end_bit,

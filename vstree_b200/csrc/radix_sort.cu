@@ -675,17 +675,19 @@ radix_pass_kernel(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const u
 struct DnaKeySource
 {
   TextPacked2 text;
-  u64 N;              // positions 0 .. N-1 (N - 1 is the sentinel)
+  u64 p_begin;        // first text position (a multiple of 32): 0 on one GPU, the rank's slice in a sharded build
+  u64 N;              // positions p_begin .. N-1 are classified (N - 1 may be the sentinel)
   u32 h;              // symbols per key
+  u32 key_shl;        // 1: key = code << 1 (flag bit 0); 0: raw 16-symbol code (sharded builds with wide keys)
   u32 text_tiles;     // tiles of tile_items positions
   const u32 *side_key, *side_pos;
   u32 nside;
 };
 
-// key (padded code << 1, flag never set for a full suffix) of the position that is symbol o_rec of record words x0..x3;
-// full: no special among the h symbols
+// key (padded code << key_shl, flag never set for a full suffix) of the position that is symbol o_rec of record words
+// x0..x3; full: no special among the h symbols
 __device__ __forceinline__ u32 dna_full_key(const TextPacked2 &text, u32 x0, u32 x1, u32 x2, u32 x3, u32 o_rec, u32 h, u64 p,
-                                            bool &full)
+                                            bool &full, u32 key_shl = 1)
 {
   const u32 bitoff = 2 * o_rec, wi = bitoff >> 5, bo = bitoff & 31;
   const u32 lo32 = wi == 0 ? x0 : (wi == 1 ? x1 : x2), hi32 = wi == 0 ? x1 : (wi == 1 ? x2 : x3);
@@ -700,11 +702,11 @@ __device__ __forceinline__ u32 dna_full_key(const TextPacked2 &text, u32 x0, u32
   }
   u32 r = __brev(w32);
   r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);
-  return (r >> (32 - 2 * h)) << 1;
+  return (r >> (32 - 2 * h)) << key_shl;
 }
 
 __global__ void __launch_bounds__(HIST_THREADS)
-radix_hist_dna_kernel(DnaKeySource src, u32 end_bit, u32 npass, u32 *__restrict__ hist /* [npass][256] */)
+radix_hist_dna_kernel(DnaKeySource src, u32 begin_bit, u32 end_bit, u32 npass, u32 *__restrict__ hist /* [npass][256] */)
 {
   __shared__ u32 sh[4 * RADIX];
   for (u32 i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS)
@@ -713,10 +715,10 @@ radix_hist_dna_kernel(DnaKeySource src, u32 end_bit, u32 npass, u32 *__restrict_
   }
   __syncthreads();
   const u32 lane = threadIdx.x & 31;
-  const u64 rows = (src.N + 31) / 32;  // one warp row = the 32 positions of one record
+  const u64 rows = (src.N + 31) / 32, first_row = src.p_begin >> 5;  // one warp row = the 32 positions of one record
   constexpr int ROWS = 8;              // records in flight per warp (one record per load: latency, not bytes, is the limit)
   const u64 warp_global = ((u64) blockIdx.x * HIST_THREADS + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * HIST_THREADS) >> 5;
-  for (u64 row0 = warp_global * ROWS; row0 < rows; row0 += nwarps * ROWS)
+  for (u64 row0 = first_row + warp_global * ROWS; row0 < rows; row0 += nwarps * ROWS)
   {
     ulonglong2 rr[ROWS];
 #pragma unroll
@@ -732,12 +734,12 @@ radix_hist_dna_kernel(DnaKeySource src, u32 end_bit, u32 npass, u32 *__restrict_
       {
         bool full;
         const u32 key = dna_full_key(src.text, (u32) rr[j].x, (u32) (rr[j].x >> 32), (u32) rr[j].y, (u32) (rr[j].y >> 32), lane + 1,
-                                     src.h, p, full);
+                                     src.h, p, full, src.key_shl);
         if (full)
         {
           for (u32 q = 0; q < npass; q++)
           {
-            const u32 shift = q * RADIX_BITS;
+            const u32 shift = begin_bit + q * RADIX_BITS;
             const u32 bits = min((u32) RADIX_BITS, end_bit - shift);
             atomicAdd(&sh[q * RADIX + ((key >> shift) & ((1u << bits) - 1))], 1u);
           }
@@ -756,12 +758,21 @@ radix_hist_dna_kernel(DnaKeySource src, u32 end_bit, u32 npass, u32 *__restrict_
   }
 }
 
-template <int ITEMS>
+// REMOTE: the pass is the partition step of a sharded build fused with its all-to-all (see radix_pass_kernel): the digit
+// of a key is the rank that owns its bin, the runs are stored into the owners' buffers.
+template <int ITEMS, bool REMOTE = false>
 __global__ void __launch_bounds__(SORT_THREADS, ESA_SORT_MINBLOCKS)
-radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict__ vout, u32 mask /* shift is 0 */,
-                      const u32 *__restrict__ base, volatile u64 *status, u32 *ticket)
+radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict__ vout, u32 shift, u32 mask,
+                      const u32 *__restrict__ base, volatile u64 *status, u32 *ticket,
+                      const RadixRemoteDst *__restrict__ remote = nullptr)
 {
   constexpr int TILE = SORT_THREADS * ITEMS;
+  __shared__ u8 sowner[RADIX];
+  if (REMOTE && threadIdx.x < RADIX)
+  {
+    sowner[threadIdx.x] = remote->owner[threadIdx.x];
+  }
+#define DIG(k) (REMOTE ? (u32) sowner[((k) >> shift) & mask] : (((k) >> shift) & mask))
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *skv = (u64 *) smem_raw;                  // [TILE] reordered (key, position) pairs
   u32 *wc = (u32 *) (skv + TILE);               // [SORT_WARPS][RADIX]
@@ -788,7 +799,7 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
   __syncthreads();
   const u32 tile = misc[0];
   const bool text_tile = tile < src.text_tiles;
-  const u64 tile_base = (u64) tile * TILE;  // text position of item 0 (text tiles)
+  const u64 tile_base = src.p_begin + (u64) tile * TILE;  // text position of item 0 (text tiles)
   if (text_tile && tid < TILE / 32 && ((tile_base >> 5) + tid) * 32 < src.N + 64)  // (records end 4 behind the text)
   {
     srec[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(src.text.pk) + (tile_base >> 5) + tid);
@@ -810,7 +821,7 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
         const ulonglong2 rr = srec[warp * ITEMS + i];  // one record per warp row: a broadcast read
         bool full;
         keys[i] = dna_full_key(src.text, (u32) rr.x, (u32) (rr.x >> 32), (u32) rr.y, (u32) (rr.y >> 32), (u32) lane + 1, src.h, p,
-                               full);
+                               full, src.key_shl);
         valid |= full ? (1u << i) : 0u;
       }
     }
@@ -829,7 +840,7 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
   {
     if ((valid >> i) & 1u)
     {
-      atomicAdd(&thist[keys[i] & mask], 1u);
+      atomicAdd(&thist[DIG(keys[i])], 1u);
     }
   }
   __syncthreads();
@@ -844,14 +855,14 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
   {
     const bool v = (valid >> i) & 1u;
     const u32 vb = __ballot_sync(FULL_MASK, v);
-    ranks[i] = match_digit_bits<0>(~(keys[i] & mask), vb);  // valid lanes with my digit
+    ranks[i] = match_digit_bits<0>(~DIG(keys[i]), vb);  // valid lanes with my digit
   }
 #pragma unroll
   for (int i = 0; i < ITEMS; i++)
   {
     const bool v = (valid >> i) & 1u;
     const u32 peers = ranks[i];
-    u32 *cp = mywc + (keys[i] & mask);
+    u32 *cp = mywc + DIG(keys[i]);
     const u32 r = *cp + __popc(peers & lt_mask);
     __syncwarp();
     if (v && (peers & gt_mask) == 0)
@@ -949,7 +960,7 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
     if ((valid >> i) & 1u)
     {
       const u32 idx = wbase + i * 32 + lane;
-      const u32 pos = mywc[keys[i] & mask] + ranks[i];
+      const u32 pos = mywc[DIG(keys[i])] + ranks[i];
       const u32 val = text_tile ? (u32) (tile_base + idx) : src.side_pos[side_base + idx];
       skv[pos] = (u64) keys[i] | ((u64) val << 32);
     }
@@ -964,11 +975,24 @@ radix_pass_dna_kernel(DnaKeySource src, u32 *__restrict__ kout, u32 *__restrict_
     {
       const u64 kv = skv[p];
       const u32 k = (u32) kv;
-      const u32 g = gbase[k & mask] + p;
-      kout[g] = k;
-      vout[g] = (u32) (kv >> 32);
+      const u32 d = DIG(k);
+      const u32 g = gbase[d] + p;
+      if (REMOTE)
+      {
+        remote->keys[d][g] = (k - remote->key_sub[d]) << remote->key_shl;  // d = owner; rebased to its key range
+        remote->vals[d][g] = (u32) (kv >> 32);
+      } else
+      {
+        kout[g] = k;
+        vout[g] = (u32) (kv >> 32);
+      }
     }
   }
+  if (REMOTE)
+  {
+    __threadfence_system();  // the stores crossed NVLink: visible to the owner before this kernel counts as done
+  }
+#undef DIG
 }
 
 constexpr size_t pass_dna_smem_bytes()
@@ -1137,6 +1161,8 @@ void radix_sort_init()
 {
   CUDA_CHECK(cudaFuncSetAttribute(radix_pass_dna_kernel<SortTraits<u32>::ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int) pass_dna_smem_bytes()));
+  CUDA_CHECK(cudaFuncSetAttribute(radix_pass_dna_kernel<SortTraits<u32>::ITEMS, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_dna_smem_bytes()));
 
   set_smem_attr<u32>();
   set_smem_attr<u64>();
@@ -1206,8 +1232,10 @@ int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, cons
   const u32 npass = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
   DnaKeySource src;
   src.text = TextPacked2{d_pk, d_spm, d_tis};
+  src.p_begin = 0;
   src.N = N;
   src.h = h;
+  src.key_shl = 1;
   src.text_tiles = (u32) div_up_u64(N, TILE);
   src.side_key = side_key;
   src.side_pos = side_pos;
@@ -1226,7 +1254,7 @@ int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, cons
   {
     const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(N, (u64) HIST_THREADS * HIST_ITEMS));
     ESA_LAUNCH(ctx, ESA_K_RADIX_HIST, 0.5 * (double) N,
-               (radix_hist_dna_kernel<<<grid, HIST_THREADS, 0, s>>>(src, key_bits, npass, hist)));
+               (radix_hist_dna_kernel<<<grid, HIST_THREADS, 0, s>>>(src, 0, key_bits, npass, hist)));
     if (nside > 0)
     {
       const u32 g2 = (u32) min((u64) ctx->num_sms * 4, div_up_u64(nside, (u64) HIST_THREADS * HIST_ITEMS));
@@ -1241,7 +1269,7 @@ int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, cons
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles1 * RADIX * 8, s)));
     ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 0.5 * (double) N + 8.0 * (double) M + 8.0 * (double) nside,
                (radix_pass_dna_kernel<ITEMS><<<tiles1, SORT_THREADS, pass_dna_smem_bytes(), s>>>(
-                   src, keys_b, vals_b, (1u << bits) - 1, base, status, tickets)));
+                   src, keys_b, vals_b, 0u, (1u << bits) - 1, base, status, tickets)));
   }
   u32 *ksrc = keys_b, *kdst = keys_a, *vsrc = vals_b, *vdst = vals_a;
   const size_t smem = pass_smem_bytes<u32>(true);
@@ -1262,6 +1290,69 @@ int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, cons
     vdst = vt;
   }
   return ksrc == keys_a ? 0 : 1;
+}
+
+
+// Sharded DNA builds: the splitter histogram (256 bins = key bits [bin_shift, bin_shift + 8)) of the full suffixes of the
+// text slice [p_begin, p_end), and the partition pass fused with the all-to-all (radix_partition_remote_u32), both with
+// the keys taken from the packed text instead of an emitted list.
+static DnaKeySource dna_slice_source(const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 p_begin, u64 p_end, u32 h,
+                                     u32 key_shl)
+{
+  constexpr u64 TILE = (u64) pass_tile_items<SortTraits<u32>::ITEMS>();
+  DnaKeySource src;
+  src.text = TextPacked2{d_pk, d_spm, d_tis};
+  src.p_begin = p_begin;
+  src.N = p_end;
+  src.h = h;
+  src.key_shl = key_shl;
+  src.text_tiles = (u32) div_up_u64(p_end - p_begin, TILE);
+  src.side_key = src.side_pos = nullptr;
+  src.nside = 0;
+  return src;
+}
+
+void radix_bin_hist_dna(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 p_begin, u64 p_end, u32 h,
+                        u32 key_shl, u32 bin_shift, u32 *d_hist256)
+{
+  if (p_end <= p_begin)
+  {
+    return;
+  }
+  const DnaKeySource src = dna_slice_source(d_pk, d_spm, d_tis, p_begin, p_end, h, key_shl);
+  const u32 grid = (u32) min((u64) ctx->num_sms * 4, div_up_u64(p_end - p_begin, (u64) HIST_THREADS * HIST_ITEMS));
+  ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 0.5 * (double) (p_end - p_begin),
+             (radix_hist_dna_kernel<<<grid, HIST_THREADS, 0, ctx->stream>>>(src, bin_shift, bin_shift + 8, 1, d_hist256)));
+}
+
+void radix_partition_remote_dna(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, const u8 *d_tis, u64 p_begin, u64 p_end,
+                                u32 h, u32 key_shl, u64 nfull, u32 bin_shift, const RadixRemoteDst *d_remote,
+                                const u32 *d_start, void *temp, size_t temp_bytes)
+{
+  constexpr int ITEMS = SortTraits<u32>::ITEMS;
+  constexpr u64 TILE = (u64) pass_tile_items<ITEMS>();
+  if (p_end <= p_begin)
+  {
+    return;
+  }
+  const DnaKeySource src = dna_slice_source(d_pk, d_spm, d_tis, p_begin, p_end, h, key_shl);
+  const TempLayout L = temp_layout<u32>(p_end - p_begin + TILE);
+  if (temp_bytes < L.total)
+  {
+    esa_throw(ESA_ERR_ARGUMENT, "radix sort scratch too small: %zu < %zu", temp_bytes, L.total);
+  }
+  char *t = (char *) temp;
+  u32 *hist = (u32 *) (t + L.hist_off), *tickets = (u32 *) (t + L.ticket_off), *base = (u32 *) (t + L.base_off);
+  u64 *status = (u64 *) (t + L.status_off);
+  cudaStream_t s = ctx->stream;
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(hist, 0, L.base_off - L.hist_off, s)));
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0,
+             CUDA_CHECK(cudaMemcpyAsync(base, d_start, RADIX * sizeof(u32), cudaMemcpyDeviceToDevice, s)));
+  ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) src.text_tiles * RADIX * 8, s)));
+  // algorithmic bytes: the text slice, one store of the pairs into peer memory
+  ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 0.5 * (double) (p_end - p_begin) + 8.0 * (double) nfull,
+             (radix_pass_dna_kernel<ITEMS, true><<<src.text_tiles, SORT_THREADS, pass_dna_smem_bytes(), s>>>(
+                 src, nullptr, nullptr, bin_shift, 0xffu, base, status, tickets, d_remote)));
 }
 
 size_t radix_sort_temp_bytes(u64 n, u32 key_bytes)

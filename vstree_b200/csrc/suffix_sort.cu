@@ -295,8 +295,10 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
                          u32 *__restrict__ main_pos, u32 *__restrict__ side_key, u32 *__restrict__ side_pos,
                          u32 *__restrict__ side_dj, u32 *__restrict__ sa, u32 *__restrict__ rank,
                          u32 *__restrict__ spec_list, u32 group_shift, const u32 *__restrict__ tile_cnt,
-                         const unsigned long long *__restrict__ group_cnt)
+                         const unsigned long long *__restrict__ group_cnt, u32 key_shl = 1)
 {
+  // key_shl = 1: keys are code << 1 | special-inside flag; 0: raw padded codes of h = 16 symbols (sharded builds with wide
+  // keys, see classify_emit_kernel)
   __shared__ u32 cnt[3][CD_ITEMS * CD_WARPS];  // per (item, warp): members of the class; then exclusive offsets
   __shared__ u64 base[3];
   __shared__ u64 part[CD_WARPS];
@@ -339,7 +341,7 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
   const u32 o_rec = (u32) lane + 1, bitoff = 2 * o_rec, wi = bitoff >> 5, bo = bitoff & 31;
   const u32 gmask = ((2u << (((o_rec + h - 1) >> 3) - (o_rec >> 3))) - 1) << (o_rec >> 3);
   u32 key[CD_ITEMS];
-  u64 dpk = 0;  // 4 bits per item: min(distance to the next special, h), h <= 15
+  u64 dpk[2] = {0, 0};  // 8 bits per item: min(distance to the next special, h), h <= 16
 #pragma unroll
   for (int i = 0; i < CD_ITEMS; i++)
   {
@@ -366,11 +368,11 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
       code = r >> (32 - 2 * h);
       if (d < h)
       {
-        code |= (1u << (2 * (h - d))) - 1;  // padded with the largest letter behind the special
+        code |= (u32) (((u64) 1 << (2 * (h - d))) - 1);  // padded with the largest letter behind the special
       }
     }
-    key[i] = (code << 1) | (d < h ? 1u : 0u);
-    dpk |= (u64) d << (4 * i);
+    key[i] = (code << key_shl) | (d < h ? key_shl : 0u);
+    dpk[i >> 3] |= (u64) d << (8 * (i & 7));
     const u32 bf = __ballot_sync(FULL_MASK, valid && d == h);
     const u32 bs = __ballot_sync(FULL_MASK, valid && d > 0 && d < h);
     const u32 bp = __ballot_sync(FULL_MASK, valid && d == 0);
@@ -425,7 +427,7 @@ classify_dna_emit_kernel(TextPacked2 text, u64 p_begin, u64 p_end, u32 h, u64 M,
   {
     const u64 p = tile_base + (u64) i * CD_THREADS + tid;
     const bool valid = p < p_end;
-    const u32 d = (u32) (dpk >> (4 * i)) & 15u;
+    const u32 d = (u32) (dpk[i >> 3] >> (8 * (i & 7))) & 255u;
     const bool is_full = valid && d == h, is_side = valid && d > 0 && d < h, is_spec = valid && d == 0;
     const u32 bf = __ballot_sync(FULL_MASK, is_full);
     const u32 bs = __ballot_sync(FULL_MASK, is_side);
@@ -2092,49 +2094,105 @@ static bool suffix_sort_sharded_impl(esa_ctx *ctx, esa_comm *comm, u32 prefixlen
   const u64 slice = div_up_u64(div_up_u64(N, (u64) G), KS_TILE) * KS_TILE;
   const u64 p_begin = min(N, (u64) me * slice), p_end = min(N, (u64) (me + 1) * slice);
   const u32 ktiles = (u32) div_up_u64(p_end - p_begin, KS_TILE);
-  u32 *tile_full = ar.alloc<u32>(ktiles + 1), *tile_side = ar.alloc<u32>(ktiles + 1), *tile_spec = ar.alloc<u32>(ktiles + 1);
+  // DNA over peer memory: the full suffixes are never emitted -- the splitter histogram and the partition pass take key
+  // and position from the packed text (radix_sort.cu: radix_bin_hist_dna, radix_partition_remote_dna), as on one GPU
+  static const bool no_text_pass = getenv("ESA_NO_TEXT_PASS") != nullptr;
+  const bool text_remote = sigma == 4 && ctx->d_pk != nullptr && comm->direct && !no_text_pass;
+  u32 *tile_full = nullptr, *tile_side = nullptr, *tile_spec = nullptr;
+  u32 *key_l = nullptr, *pos_l = nullptr, *key_t = nullptr, *pos_t = nullptr;
+  u32 *lside_key = nullptr, *lside_pos = nullptr, *lside_dj = nullptr, *lspec = nullptr;
   u64 nfull = 0, nside = 0, nspec = 0;
-  if (ktiles > 0)
+  if (text_remote)
   {
-    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin),
-               (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
-                                                                     tile_side, tile_spec)));
-    ESA_LAUNCH(ctx, ESA_K_MISC, 0,
-               (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
-                                                                       d_scalars, 0)));
-    read_back_u64(ctx, d_scalars, 4);
-    nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
-  }
-  if (nfull + nside + nspec != p_end - p_begin)
+    static_assert(CD_TILE == KS_TILE, "slices are aligned to both tile sizes");
+    const u32 dtiles = (u32) div_up_u64(p_end - p_begin, CD_TILE);
+    u32 gshift = 0;
+    while (((u64) 1 << (2 * gshift)) < dtiles)
+    {
+      gshift++;
+    }
+    u32 *tile_cnt = ar.alloc<u32>(dtiles + 1);
+    unsigned long long *group_cnt = reinterpret_cast<unsigned long long *>(ar.alloc<u64>((dtiles >> gshift) + 2));
+    if (dtiles > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(group_cnt, 0, ((dtiles >> gshift) + 2) * sizeof(u64), s)));
+      ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin) / 8,
+                 (classify_dna_count_kernel<<<dtiles, CD_TILE / 32, 0, s>>>(ctx->d_spm, p_begin, p_end, h0, gshift, tile_cnt,
+                                                                            group_cnt,
+                                                                            reinterpret_cast<unsigned long long *>(d_scalars + 1))));
+      read_back_u64(ctx, d_scalars, 4);
+      nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
+      nfull = (p_end - p_begin) - nside - nspec;
+    }
+    lside_key = ar.alloc<u32>(nside + 1), lside_pos = ar.alloc<u32>(nside + 1), lside_dj = ar.alloc<u32>(nside + 1);
+    lspec = ar.alloc<u32>(nspec + 1);
+    if (dtiles > 0)
+    {
+      const TextPacked2 text{ctx->d_pk, ctx->d_spm, ctx->d_tis};
+      ESA_LAUNCH(ctx, ESA_K_CLASSIFY, 0.125 * (double) (p_end - p_begin) + 12.0 * nside + 4.0 * nspec,
+                 (classify_dna_emit_kernel<<<dtiles, CD_THREADS, 0, s>>>(text, p_begin, p_end, h0, 0, nullptr, nullptr, lside_key,
+                                                                          lside_pos, lside_dj, nullptr, nullptr, lspec, gshift,
+                                                                          tile_cnt, group_cnt, key_shl)));
+    }
+  } else
   {
-    esa_throw(ESA_ERR_CUDA, "classification lost suffixes on rank %d", me);
-  }
-  u32 *key_l = ar.alloc<u32>(nfull + 64), *pos_l = ar.alloc<u32>(nfull + 64);
-  u32 *key_t = ar.alloc<u32>(nfull + 64), *pos_t = ar.alloc<u32>(nfull + 64);
-  u32 *lside_key = ar.alloc<u32>(nside + 1), *lside_pos = ar.alloc<u32>(nside + 1), *lside_dj = ar.alloc<u32>(nside + 1);
-  u32 *lspec = ar.alloc<u32>(nspec + 1);
-  if (ktiles > 0)
-  {
-    ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin) + 8.0 * (nfull + nside) + 4.0 * nspec,
-               (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
-                                                                    tile_side, tile_spec, 0, key_l, pos_l,
-                                                                    lside_key, lside_pos, lside_dj, nullptr, nullptr,
-                                                                    lspec, key_shl)));
+    tile_full = ar.alloc<u32>(ktiles + 1), tile_side = ar.alloc<u32>(ktiles + 1), tile_spec = ar.alloc<u32>(ktiles + 1);
+    if (ktiles > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin),
+                 (classify_count_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
+                                                                       tile_side, tile_spec)));
+      ESA_LAUNCH(ctx, ESA_K_MISC, 0,
+                 (tile_exclusive_sum_kernel<<<3, SCAN1_THREADS, 0, s>>>(tile_full, tile_side, tile_spec, ktiles,
+                                                                         d_scalars, 0)));
+      read_back_u64(ctx, d_scalars, 4);
+      nfull = ctx->h_scalars[0], nside = ctx->h_scalars[1], nspec = ctx->h_scalars[2];
+    }
+    if (nfull + nside + nspec != p_end - p_begin)
+    {
+      esa_throw(ESA_ERR_CUDA, "classification lost suffixes on rank %d", me);
+    }
+    key_l = ar.alloc<u32>(nfull + 64), pos_l = ar.alloc<u32>(nfull + 64);
+    key_t = ar.alloc<u32>(nfull + 64), pos_t = ar.alloc<u32>(nfull + 64);
+    lside_key = ar.alloc<u32>(nside + 1), lside_pos = ar.alloc<u32>(nside + 1), lside_dj = ar.alloc<u32>(nside + 1);
+    lspec = ar.alloc<u32>(nspec + 1);
+    if (ktiles > 0)
+    {
+      ESA_LAUNCH(ctx, ESA_K_CLASSIFY, (double) (p_end - p_begin) + 8.0 * (nfull + nside) + 4.0 * nspec,
+                 (classify_emit_kernel<<<ktiles, KS_THREADS, 0, s>>>(ctx->d_tis, n, p_begin, p_end, kp, tile_full,
+                                                                      tile_side, tile_spec, 0, key_l, pos_l,
+                                                                      lside_key, lside_pos, lside_dj, nullptr, nullptr,
+                                                                      lspec, key_shl)));
+    }
   }
 
   // ---- 2. splitter pass: bins of the top 8 key bits (= the first symbols, whichever key width)
   OwnerLut lut;
   lut.shift = key_bits > 8 ? key_bits - 8 : 0;
   lut.last = (u32) (G - 1);
-  if (nfull > 0)
-  {
-    const u32 grid = (u32) min((u64) ctx->num_sms * 8, div_up_u64(nfull, 256));
-    ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 4.0 * nfull,
-               (bin_hist_kernel<<<grid, 256, 0, s>>>(key_l, nfull, lut.shift, d_counts)));
-  }
   u64 local_hist[256 + 2];
-  CUDA_CHECK(cudaMemcpyAsync(local_hist, d_counts, 256 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (text_remote)
+  {
+    u32 *d_hist32 = reinterpret_cast<u32 *>(d_counts);  // (zeroed above)
+    u32 h32[256];
+    radix_bin_hist_dna(ctx, ctx->d_pk, ctx->d_spm, ctx->d_tis, p_begin, p_end, h0, key_shl, lut.shift, d_hist32);
+    CUDA_CHECK(cudaMemcpyAsync(h32, d_hist32, sizeof h32, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int b = 0; b < 256; b++)
+    {
+      local_hist[b] = h32[b];
+    }
+  } else
+  {
+    if (nfull > 0)
+    {
+      const u32 grid = (u32) min((u64) ctx->num_sms * 8, div_up_u64(nfull, 256));
+      ESA_LAUNCH(ctx, ESA_K_EXCHANGE, 4.0 * nfull,
+                 (bin_hist_kernel<<<grid, 256, 0, s>>>(key_l, nfull, lut.shift, d_counts)));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(local_hist, d_counts, 256 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   local_hist[256] = nside;
   local_hist[257] = nspec;
   // every rank learns every rank's bin counts: the splitters, all send/receive counts and, for the fused
@@ -2203,7 +2261,7 @@ static bool suffix_sort_sharded_impl(esa_ctx *ctx, esa_comm *comm, u32 prefixlen
 
   // ---- 3b. side suffixes: all-gather (rank order = position order), stable sort by h0-j, keep mine
   const size_t temp_bytes = max(max(radix_sort_temp_bytes(mfull + nside_tot + 64, 4), radix_sort_temp_bytes(mfull + nside_tot + 64, 8)),
-                                radix_sort_temp_bytes(nfull + 64, 4));
+                                radix_sort_temp_bytes((p_end - p_begin) + 16384, 4));
   void *sort_temp = ar.alloc<char>(temp_bytes);
   u32 *gs_key = ar.alloc<u32>(nside_tot + 1), *gs_pos = ar.alloc<u32>(nside_tot + 1), *gs_dj = ar.alloc<u32>(nside_tot + 1);
   u32 *gs_tmp = ar.alloc<u32>(nside_tot + 1), *gs_key2 = ar.alloc<u32>(nside_tot + 1), *gs_pos2 = ar.alloc<u32>(nside_tot + 1);
@@ -2312,8 +2370,15 @@ static bool suffix_sort_sharded_impl(esa_ctx *ctx, esa_comm *comm, u32 prefixlen
     u32 *d_start = ar.alloc<u32>(256);
     CUDA_CHECK(cudaMemcpyAsync(d_dst, &h_dst, sizeof h_dst, cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(d_start, owner_start, sizeof owner_start, cudaMemcpyHostToDevice, s));
-    radix_partition_remote_u32(ctx, key_l, pos_l, nfull, lut.shift, key_bits > lut.shift ? key_bits : lut.shift + 1,
-                               d_dst, d_start, sort_temp, temp_bytes);
+    if (text_remote)
+    {
+      radix_partition_remote_dna(ctx, ctx->d_pk, ctx->d_spm, ctx->d_tis, p_begin, p_end, h0, key_shl, nfull, lut.shift, d_dst,
+                                 d_start, sort_temp, temp_bytes);
+    } else
+    {
+      radix_partition_remote_u32(ctx, key_l, pos_l, nfull, lut.shift, key_bits > lut.shift ? key_bits : lut.shift + 1,
+                                 d_dst, d_start, sort_temp, temp_bytes);
+    }
     comm->bytes_sent += 8 * (nfull - send_cnt[me]);
     CUDA_CHECK(cudaStreamSynchronize(s));  // my stores are done; the exchange below tells me when everybody's are
   } else
