@@ -108,6 +108,7 @@ enum
   ESA_K_MEMOP,          /* cudaMemsetAsync / device-to-device cudaMemcpyAsync nodes (not kernels of this library) */
   ESA_K_COMM,           /* sharded builds: collectives (NCCL or in-process peer copies) between the ranks */
   ESA_K_EXCHANGE,       /* sharded builds: owner tagging, request serving and answer merging around the collectives */
+  ESA_K_RADIX_PASS_TEXT,/* first pass of the initial DNA sort: keys and positions computed from the packed text inside the pass */
   ESA_K_NUM
 };
 

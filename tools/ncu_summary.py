@@ -44,7 +44,11 @@ if len(sys.argv) > 2:
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     h = rows[1]
-    d = rows[2:]
+    d = []
+    for r in rows[2:]:  # the SASS view; a report with imported sources repeats the header for the next view
+        if len(r) < len(h) or not r[h.index("# Samples")].isdigit():
+            break
+        d.append(r)
     jx = {x: i for i, x in enumerate(h)}
     tot = sum(int(r[jx["# Samples"]]) for r in d)
     toti = sum(int(r[jx["Instructions Executed"]]) for r in d)

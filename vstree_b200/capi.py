@@ -11,7 +11,7 @@ ROOT = os.path.dirname(_HERE)
 DEMAND_BITS = {"tis": 1 << 0, "ois": 1 << 1, "des": 1 << 2, "ssp": 1 << 3, "bwt": 1 << 4, "suf": 1 << 5,
                "lcp": 1 << 6, "bck": 1 << 7, "sti1": 1 << 8, "skp": 1 << 9, "sti": 1 << 13}
 KERNEL_FAMILIES = ["classify", "radix_hist", "radix_pass", "regroup", "gather_rank", "bck", "plcp", "finalize",
-                   "sti1", "misc", "memop", "comm", "exchange"]
+                   "sti1", "misc", "memop", "comm", "exchange", "radix_pass_text"]
 ERRBUF = 1024
 
 

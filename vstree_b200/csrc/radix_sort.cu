@@ -1267,7 +1267,7 @@ int radix_sort_dna_initial(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm, cons
   {
     const u32 bits = min((u32) RADIX_BITS, key_bits);
     ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) tiles1 * RADIX * 8, s)));
-    ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 0.5 * (double) N + 8.0 * (double) M + 8.0 * (double) nside,
+    ESA_LAUNCH(ctx, ESA_K_RADIX_PASS_TEXT, 0.5 * (double) N + 8.0 * (double) M + 8.0 * (double) nside,
                (radix_pass_dna_kernel<ITEMS><<<tiles1, SORT_THREADS, pass_dna_smem_bytes(), s>>>(
                    src, keys_b, vals_b, 0u, (1u << bits) - 1, base, status, tickets)));
   }
@@ -1350,7 +1350,7 @@ void radix_partition_remote_dna(esa_ctx *ctx, const u64 *d_pk, const u32 *d_spm,
              CUDA_CHECK(cudaMemcpyAsync(base, d_start, RADIX * sizeof(u32), cudaMemcpyDeviceToDevice, s)));
   ESA_LAUNCH(ctx, ESA_K_MEMOP, 0, CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t) src.text_tiles * RADIX * 8, s)));
   // algorithmic bytes: the text slice, one store of the pairs into peer memory
-  ESA_LAUNCH(ctx, ESA_K_RADIX_PASS, 0.5 * (double) (p_end - p_begin) + 8.0 * (double) nfull,
+  ESA_LAUNCH(ctx, ESA_K_RADIX_PASS_TEXT, 0.5 * (double) (p_end - p_begin) + 8.0 * (double) nfull,
              (radix_pass_dna_kernel<ITEMS, true><<<src.text_tiles, SORT_THREADS, pass_dna_smem_bytes(), s>>>(
                  src, nullptr, nullptr, bin_shift, 0xffu, base, status, tickets, d_remote)));
 }
