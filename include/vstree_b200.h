@@ -222,6 +222,21 @@ int esa_shard_plan(const uint64_t *hist, size_t stride, int nranks, int me, uint
  * property otherwise. ---- */
 int esa_check(esa_ctx *ctx, char *errbuf, size_t errlen);
 
+/* ---- the child table (.cld, .cld1) from the lcp table: SURVEY.md 8f row 4 ----
+ * Replaces makecldtabandoutput (src/Mkvtree/mkcld.mn.c:13-47) = mkcldtabnextlIndex + mkcldtabupdown + compresscldtab
+ * (src/kurtz/mkcld.c:41-284); the reference's mkcld maps SUFTAB | LCPTAB of an index and reads the lcp values only.
+ *   lcptab != NULL : host tables as mapped from an index: lcptab[totallength + 1] and the `nllv` large-value pairs
+ *                    (the .lcp and .llv files); works on any context, resident builds are left untouched
+ *   lcptab == NULL : the lcp table left resident by the last esa_construct / esa_build of this context (it must have
+ *                    demanded ESA_LCPTAB; one GPU); llv / nllv / totallength are ignored
+ * cldtab  : caller's buffer of 3 * (totallength + 1) bytes, Childinfo {up, down, nextlIndex} per entry
+ *           (src/include/virtualdef.h:165-179), the bytes of the .cld file
+ * cldtab1 : caller's buffer of totallength + 1 bytes (the .cld1 file) or NULL.  Entries the reference never writes
+ *           (the last one, mkcld.c:230-283 stops below totallength) are 0.
+ * Fails with ESA_ERR_ARGUMENT when the pairs do not belong to the lcp table (every 255 needs exactly one pair). */
+int esa_childtab(esa_ctx *ctx, const uint8_t *lcptab, const esa_pairuint *llv, uint64_t nllv, uint64_t totallength,
+                 uint8_t *cldtab, uint8_t *cldtab1, char *errbuf, size_t errlen);
+
 /* ---- host-side scalar math that must match the reference bit for bit ---- */
 /* vm_determinenumofcodes, src/kurtz-basic/detnumofcodes.c:8-11 */
 uint64_t esa_numofcodes(uint32_t numofchars, uint32_t prefixlength);

@@ -93,6 +93,33 @@ build_families() {
   gcc -o "$OUT/gpu/vmatch.x" "$O/main_vmatch.o" $L $L $GPU "$RPATH" "$O/libm.a" $KL
   rm -rf "$O"
 }
+# The reference's child-table tool (src/Mkvtree/Makefile:132-134: mkcld.mn.o + libkurtz + libkurtz-basic), unmodified:
+# reads .lcp/.llv of an index, writes .cld and .cld1.  Golden maker and live comparison of SURVEY.md 8f row 4
+# (tests/golden/make_cld_golden.py, tests/test_gpu_childtab.py).
+build_tools() {
+  local O="$OUT/objtools"
+  mkdir -p "$O"
+  ( for f in "$S"/kurtz-basic/*.c; do echo "gcc $CF -c $f -o $O/kb_$(basename "$f" .c).o"; done
+    for f in "$S"/kurtz/*.c;       do echo "gcc $CF -c $f -o $O/k_$(basename "$f" .c).o"; done
+    echo "gcc $CF -c $S/Mkvtree/mkcld.mn.c -o $O/main_mkcld.o"
+    echo "gcc $CF -c $HERE/stub/bzstub.c -o $O/bzstub.o"
+  ) | xargs -P "$J" -I{} sh -c "{}"
+  ar rcs "$O/libkb.a" "$O"/kb_*.o
+  ar rcs "$O/libk.a" "$O"/k_*.o
+  gcc -o "$OUT/mkcld.x" "$O/main_mkcld.o" "$O/libk.a" "$O/libkb.a" "$O/libk.a" "$O/libkb.a" "$O/bzstub.o" -lz -lm -ldl -lpthread
+  # the same main with the three child-table functions of libkurtz (mkcld.o) replaced by integration/mkcldgpu.c
+  local ROOT
+  ROOT="$(cd "$HERE/.." && pwd)"
+  if [ -f "$ROOT/vstree_b200/lib/libvstree_b200.so" ]; then
+    mkdir -p "$OUT/gpu"
+    gcc $CF -I"$ROOT/include" -Wall -c "$ROOT/integration/mkcldgpu.c" -o "$O/g_mkcldgpu.o"
+    rm -f "$O/k_mkcld.o" "$O/libk_nocld.a"
+    ar rcs "$O/libk_nocld.a" "$O"/k_*.o
+    gcc -o "$OUT/gpu/mkcld.x" "$O/main_mkcld.o" "$O/g_mkcldgpu.o" "$O/libk_nocld.a" "$O/libkb.a" "$O/libk_nocld.a" "$O/libkb.a" \
+        "$O/bzstub.o" -L"$ROOT/vstree_b200/lib" -lvstree_b200 '-Wl,-rpath,$ORIGIN/../../../vstree_b200/lib' -lz -lm -ldl -lpthread
+  fi
+  rm -rf "$O"
+}
 CF="-D_LARGEFILE_SOURCE -D_FILE_OFFSET_BITS=64 -O3 -m64 -fno-stack-protector -U_FORTIFY_SOURCE -D_GNU_SOURCE -DWITHSYSCONF -I$HERE/stub -I$S/include -w"
 J=$(nproc)
 ROOT_="$(cd "$HERE/.." && pwd)"
@@ -106,6 +133,9 @@ if [ -x "$OUT/mkvtree.x" ] && [ -x "$OUT/mkvtree.dbg.x" ] && [ "${1:-}" != "--fo
   fi
   if families_stale; then
     build_families || echo "build_ref.sh: the gpu family could not be built (tests/test_gpu_refseam.py will be skipped)" >&2
+  fi
+  if [ ! -x "$OUT/mkcld.x" ] || [ ! -x "$OUT/gpu/mkcld.x" ] || [ "$ROOT_/integration/mkcldgpu.c" -nt "$OUT/gpu/mkcld.x" ]; then
+    build_tools || echo "build_ref.sh: mkcld.x could not be built (the live child-table comparison will be skipped)" >&2
   fi
   exit 0
 fi
@@ -134,4 +164,5 @@ build_variant "$OUT/objdbg" "-DDEBUG" ".dbg.x"
 rm -rf "$OUT/obj" "$OUT/objdbg"
 build_vmatch || echo "build_ref.sh: vmatch.x could not be built (the acceptance test will be skipped)" >&2
 build_families || echo "build_ref.sh: the gpu family could not be built (tests/test_gpu_refseam.py will be skipped)" >&2
+build_tools || echo "build_ref.sh: mkcld.x could not be built (the live child-table comparison will be skipped)" >&2
 echo "built: $(ls "$OUT")"

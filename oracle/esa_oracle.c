@@ -480,6 +480,131 @@ int oracle_skiptable(const uint8_t *lcptab, const uint64_t *llv, uint64_t n, uin
 }
 
 /*
+ * Child table.  reference: src/kurtz/mkcld.c:41-108 (mkcldtabnextlIndex), :110-207 (mkcldtabupdown), :225-284
+ * (compresscldtab); driver src/Mkvtree/mkcld.mn.c:13-47.  Two walks over the lcp table with a stack of (depth, step)
+ * pairs that starts with (0, 0):
+ *   nextlIndex: pop everything deeper than the current value; if the top then has the same depth, the top's entry
+ *               points to the current index.  Push.
+ *   up / down:  while popping, remember the entry popped last; whenever the new top is at least as deep as the current
+ *               value and differs in depth from the entry just popped, the top's `down` points to that entry.  After the pops the current index gets `up` = distance to the entry popped last
+ *               (once).  Push.
+ * All three fields are distances, stored in one byte: 0 = undefined, 255 = "255 or more" (virtualdef.h:165-166).
+ * cld receives n + 1 records {up, down, nextlIndex} (the .cld file), cld1 -- when not NULL -- the n + 1 bytes of the
+ * .cld1 file: three loops over the same byte, the later one overwrites, none touches index n (and the third stops at
+ * n - 2); bytes no loop writes are 0 here (the reference leaves what malloc returned).
+ * Returns 0, or -1 when memory is exhausted.
+ */
+int oracle_childtab(const uint8_t *lcptab, const uint64_t *llv, uint64_t n, uint8_t *cld, uint8_t *cld1)
+{
+  uint64_t *depth = (uint64_t *) malloc((n + 2) * sizeof(uint64_t));
+  uint64_t *step = (uint64_t *) malloc((n + 2) * sizeof(uint64_t));
+  uint64_t *lcp = (uint64_t *) malloc((n + 1) * sizeof(uint64_t));
+  uint64_t top, exception = 0;
+  if (depth == NULL || step == NULL || lcp == NULL)
+  {
+    free(depth);
+    free(step);
+    free(lcp);
+    return -1;
+  }
+  lcp[0] = lcptab[0];
+  for (uint64_t i = 1; i <= n; i++)
+  {
+    lcp[i] = lcptab[i];
+    if (lcp[i] == 255)
+    {
+      lcp[i] = llv[2 * exception + 1];
+      exception++;
+    }
+  }
+  memset(cld, 0, 3 * (n + 1));
+#define CLD_CLAMP(D) ((uint8_t) ((D) >= 255 ? 255 : (D)))
+  /* walk 1: nextlIndex */
+  top = 0;
+  depth[top] = 0;
+  step[top] = 0;
+  top++;
+  for (uint64_t i = 1; i <= n; i++)
+  {
+    while (lcp[i] < depth[top - 1])
+    {
+      top--;
+    }
+    if (lcp[i] == depth[top - 1])
+    {
+      cld[3 * step[top - 1] + 2] = CLD_CLAMP(i - step[top - 1]);
+    }
+    depth[top] = lcp[i];
+    step[top] = i;
+    top++;
+  }
+  /* walk 2: up and down */
+  top = 0;
+  depth[top] = 0;
+  step[top] = 0;
+  top++;
+  {
+    uint64_t last_step = 0, last_depth = 0;  /* step 0 = nothing popped since the last `up` (index 0 is never popped) */
+    for (uint64_t i = 1; i <= n; i++)
+    {
+      while (lcp[i] < depth[top - 1])
+      {
+        last_step = step[top - 1];
+        last_depth = depth[top - 1];
+        top--;
+        if (lcp[i] <= depth[top - 1] && depth[top - 1] != last_depth)
+        {
+          cld[3 * step[top - 1] + 1] = CLD_CLAMP(last_step - step[top - 1]);
+        }
+      }
+      if (last_step != 0)
+      {
+        cld[3 * i] = CLD_CLAMP(i - last_step);
+        last_step = 0;
+      }
+      depth[top] = lcp[i];
+      step[top] = i;
+      top++;
+    }
+  }
+  if (cld1 != NULL)
+  {
+    memset(cld1, 0, n + 1);
+    for (uint64_t i = 0; i < n; i++)
+    {
+      if (cld[3 * i + 2] > 0)
+      {
+        cld1[i] = cld[3 * i + 2];
+      }
+    }
+    for (uint64_t i = 0; i < n; i++)
+    {
+      uint64_t next = i + cld[3 * i + 2], down = i + cld[3 * i + 1];
+      if ((next == i && down > i) || next == n)
+      {
+        cld1[i] = CLD_CLAMP(down - i);
+      }
+    }
+    for (uint64_t i = 0; i + 1 < n; i++)
+    {
+      if (lcp[i] > lcp[i + 1])
+      {
+        uint64_t up = i + 1 - cld[3 * (i + 1)], down = i + 1 + cld[3 * (i + 1) + 1];
+        if (up != down)
+        {
+          cld1[i] = CLD_CLAMP(i + 1 - up);
+        }
+      }
+    }
+  }
+#undef CLD_CLAMP
+  free(depth);
+  free(step);
+  free(lcp);
+  return 0;
+}
+
+/*
  * Property checks restating the reference's DEBUG invariants; return 0 when the tables are consistent,
  * otherwise a positive code naming the first violated property.
  *   1: suftab is not a permutation of 0..n            reference: src/Mkvtree/bese.c:355-451 (checksuftab)

@@ -39,6 +39,8 @@ def oracle_lib():
                                             ctypes.c_uint64, u8p, u64p, u8p]
         lib.oracle_skiptable.restype = ctypes.c_int
         lib.oracle_skiptable.argtypes = [u8p, u64p, ctypes.c_uint64, u64p]
+        lib.oracle_childtab.restype = ctypes.c_int
+        lib.oracle_childtab.argtypes = [u8p, u64p, ctypes.c_uint64, u8p, u8p]
         lib.oracle_numofcodes.restype = ctypes.c_uint64
         lib.oracle_numofcodes.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         lib.oracle_recommendedprefixlength.restype = ctypes.c_uint32
@@ -89,6 +91,21 @@ def oracle_skiptable(lcp, llv):
     if rc != 0:
         raise RuntimeError("oracle_skiptable failed")
     return skp
+
+
+def oracle_childtab(lcp, llv):
+    """Child table (.cld records, .cld1 bytes) from lcp/llv (restates src/kurtz/mkcld.c)."""
+    lib = oracle_lib()
+    lcp = np.ascontiguousarray(lcp, np.uint8)
+    llv = np.ascontiguousarray(np.concatenate([np.asarray(llv, np.uint64).ravel(), np.zeros(2, np.uint64)]), np.uint64)
+    n = len(lcp) - 1
+    cld = np.zeros(3 * (n + 1), np.uint8)
+    cld1 = np.zeros(n + 1, np.uint8)
+    rc = lib.oracle_childtab(_p(lcp, ctypes.c_uint8), _p(llv, ctypes.c_uint64), n, _p(cld, ctypes.c_uint8),
+                             _p(cld1, ctypes.c_uint8))
+    if rc != 0:
+        raise RuntimeError("oracle_childtab failed")
+    return cld, cld1
 
 
 def oracle_check(tis, numofchars, prefixlength, tables):

@@ -71,10 +71,35 @@ def test_sorter_replacement_compiles_against_the_reference_headers(tmp_path):
         assert pr.returncode == 0, pr.stderr[-3000:]
 
 
+def test_child_table_replacement_compiles_against_the_reference_headers(tmp_path):
+    """integration/mkcldgpu.c: mkcldtabnextlIndex / mkcldtabupdown / compresscldtab with the reference's signatures
+    (src/kurtz/mkcld.c:41,110,225; prototypes in src/include/mkcld.pr), on top of esa_childtab."""
+    if not os.path.isdir(os.path.join(REFSRC, "include")):
+        pytest.skip("reference tree not mounted")
+    obj = str(tmp_path / "mkcldgpu.o")
+    base = ["gcc", "-c", "-Wall", "-Werror=incompatible-pointer-types", "-Werror=int-conversion",
+            "-Werror=implicit-function-declaration", "-D_GNU_SOURCE", "-I" + os.path.join(REFSRC, "include"),
+            "-I" + os.path.join(REFSRC, "kurtz"), "-I" + os.path.join(ROOT, "oracle", "stub"),
+            "-I" + os.path.join(ROOT, "include")]
+    pr = subprocess.run(base + [os.path.join(ROOT, "integration", "mkcldgpu.c"), "-o", obj], capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    syms = subprocess.run(["nm", obj], capture_output=True, text=True).stdout
+    defined = {l.split()[-1] for l in syms.splitlines() if " T " in l}
+    undefined = {l.split()[-1] for l in syms.splitlines() if " U " in l}
+    assert {"mkcldtabnextlIndex", "mkcldtabupdown", "compresscldtab"} <= defined
+    assert {"esa_init", "esa_childtab"} <= undefined
+    if os.path.exists(os.path.join(REFSRC, "include", "mkcld.pr")):  # the reference's own prototypes in front of the file
+        proto = tmp_path / "proto.c"
+        proto.write_text('#include "types.h"\n#include "arraydef.h"\n#include "virtualdef.h"\n#include "mkcld.pr"\n')
+        pr = subprocess.run(base + ["-include", str(proto), os.path.join(ROOT, "integration", "mkcldgpu.c"), "-o",
+                                    str(tmp_path / "m2.o")], capture_output=True, text=True)
+        assert pr.returncode == 0, pr.stderr[-3000:]
+
+
 def test_family_binaries_are_built_where_the_reference_is_present():
     if not os.path.isdir(os.path.join(REFSRC, "include")):
         pytest.skip("reference tree not mounted")
-    for t in ("mkvtree.x", "mkvram.x", "mkrcidx.x", "mkdna6idx.x", "vmatch.x"):
+    for t in ("mkvtree.x", "mkvram.x", "mkrcidx.x", "mkdna6idx.x", "vmatch.x", "mkcld.x"):
         assert os.access(os.path.join(ROOT, "oracle", "_ref", "gpu", t), os.X_OK), t
-    for t in ("mkvram.x", "mkrcidx.x", "mkdna6idx.x"):
+    for t in ("mkvram.x", "mkrcidx.x", "mkdna6idx.x", "mkcld.x"):
         assert os.access(os.path.join(ROOT, "oracle", "_ref", t), os.X_OK), t

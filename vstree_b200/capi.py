@@ -101,6 +101,8 @@ def load_library():
     lib.esa_debug_radix_sort.argtypes = [vp, c.c_int, vp, vp, c.c_uint64, c.c_uint32, c.c_uint32, cp, sz]
     lib.esa_debug_corrupt.restype = c.c_int
     lib.esa_debug_corrupt.argtypes = [vp, c.c_uint32, c.c_uint64, c.c_uint64, cp, sz]
+    lib.esa_childtab.restype = c.c_int
+    lib.esa_childtab.argtypes = [vp, vp, vp, c.c_uint64, c.c_uint64, vp, vp, cp, sz]
     lib.esa_version.restype = cp
     lib.esa_version.argtypes = []
     lib.esa_comm_unique_id.restype = c.c_int
@@ -249,6 +251,25 @@ class Esa:
     def check(self):
         err = ctypes.create_string_buffer(ERRBUF)
         self._check(self.lib.esa_check(self.ctx, err, ERRBUF), err)
+
+    def childtab(self, lcp=None, llv=None, n=None, cld1=True):
+        """esa_childtab: (cld bytes [3 per entry], cld1 bytes or None).  lcp=None: from the lcp table of the last build
+        on this context (n = its totallength); else from host tables lcp[n+1] (uint8) and llv (uint64 pairs)."""
+        err = ctypes.create_string_buffer(ERRBUF)
+        if lcp is None:
+            lp, vp_, nllv, n = None, None, 0, int(n)
+        else:
+            lcp = np.ascontiguousarray(lcp, np.uint8)
+            llv = np.ascontiguousarray(np.zeros(0, np.uint64) if llv is None else llv, np.uint64).ravel()
+            n, nllv = len(lcp) - 1, len(llv) // 2
+            lp = ctypes.c_void_p(lcp.ctypes.data)
+            vp_ = ctypes.c_void_p(llv.ctypes.data) if nllv else None
+        cld = np.empty(3 * (n + 1), np.uint8)
+        c1 = np.empty(n + 1, np.uint8) if cld1 else None
+        rc = self.lib.esa_childtab(self.ctx, lp, vp_, nllv, n, ctypes.c_void_p(cld.ctypes.data),
+                                   ctypes.c_void_p(c1.ctypes.data) if cld1 else None, err, ERRBUF)
+        self._check(rc, err)
+        return cld, c1
 
     def debug_corrupt(self, table, index, xor_mask):
         """Testing hook: damages one element of a resident device table ("llv" addresses the .llv words)."""

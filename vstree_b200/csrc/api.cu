@@ -1234,6 +1234,62 @@ int esa_check(esa_ctx *c, char *errbuf, size_t errlen)
   return ESA_OK;
 }
 
+int esa_childtab(esa_ctx *c, const uint8_t *lcptab, const esa_pairuint *llv, uint64_t nllv, uint64_t totallength,
+                 uint8_t *cldtab, uint8_t *cldtab1, char *errbuf, size_t errlen)
+{
+  if (c == nullptr || cldtab == nullptr)
+  {
+    set_err(errbuf, errlen, c == nullptr ? "ctx is NULL" : "cldtab is NULL");
+    return ESA_ERR_ARGUMENT;
+  }
+  FullCtx *ctx = static_cast<FullCtx *>(c);
+  return guarded(errbuf, errlen, [&]() {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (lcptab == nullptr)
+    {
+      if (!ctx->constructed || ctx->d_lcp == nullptr || !(ctx->demand & ESA_LCPTAB))
+      {
+        esa_throw(ESA_ERR_STATE, "esa_childtab without tables needs a finished build that demanded the lcp table");
+      }
+      if (is_sharded(ctx))
+      {
+        esa_throw(ESA_ERR_STATE, "the child table needs the whole lcp table on one device: not available on a sharded context");
+      }
+      compute_childtab(ctx, ctx->d_lcp, ctx->d_llv, ctx->nllv, ctx->n, cldtab, cldtab1);
+      return;
+    }
+    if (totallength >= 0xfffffffeull)
+    {
+      esa_throw(ESA_ERR_TOOLARGE, "totallength %llu does not fit the 32-bit device index", (unsigned long long) totallength);
+    }
+    if (nllv > 0 && llv == nullptr)
+    {
+      esa_throw(ESA_ERR_ARGUMENT, "%llu large lcp values announced, none given", (unsigned long long) nllv);
+    }
+    const u64 N = totallength + 1;
+    u8 *d_lcp8 = nullptr;
+    u64 *d_pairs = nullptr;
+    struct Guard
+    {
+      u8 *&a;
+      u64 *&b;
+      ~Guard()
+      {
+        cudaFree(a);
+        cudaFree(b);
+      }
+    } guard{d_lcp8, d_pairs};
+    CUDA_CHECK(cudaMalloc((void **) &d_lcp8, N + 256));
+    CUDA_CHECK(cudaMemcpyAsync(d_lcp8, lcptab, N, cudaMemcpyHostToDevice, ctx->stream));
+    if (nllv > 0)
+    {
+      CUDA_CHECK(cudaMalloc((void **) &d_pairs, 16 * nllv));
+      CUDA_CHECK(cudaMemcpyAsync(d_pairs, llv, 16 * nllv, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    compute_childtab(ctx, d_lcp8, d_pairs, nllv, totallength, cldtab, cldtab1);
+  });
+}
+
 int esa_comm_unique_id(uint8_t id[ESA_COMM_ID_BYTES], char *errbuf, size_t errlen)
 {
   if (id == nullptr)

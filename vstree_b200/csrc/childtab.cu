@@ -1,0 +1,268 @@
+// childtab.cu -- the child table of the enhanced suffix array (.cld, 3 bytes per entry, and .cld1, 1 byte per entry)
+// from the lcp table: SURVEY.md 8f row 4.  Replaces makecldtabandoutput (reference: src/Mkvtree/mkcld.mn.c:13-47) =
+// mkcldtabnextlIndex + mkcldtabupdown + compresscldtab (src/kurtz/mkcld.c:41-284).  The per-entry definition and the
+// searches are in childtab_core.cuh; this file holds the kernels around them:
+//
+//   widen_lcp_kernel      lcp bytes -> 32-bit values                                    1 B read, 4 B written per entry
+//   scatter_llv_kernel    the exact values >= 255 from the (index, value) pairs         16 B per large value
+//   min_level_kernel      one level of the min-pyramid                                  4 (1 + 1/16) B per entry and level
+//   child_kernel          up / down / nextlIndex of every entry, staged through shared memory so that the 3-byte
+//                         records leave as whole words                                  >= 4 B read, 3 B written
+//   cld1_kernel           the one-byte table from the three-field table                 ~ 11 B read, 1 B written
+//
+// HBM-bound integer work over tables of n + 1 entries; the searches touch neighbours of the entry almost always (the
+// pyramid levels above level 0 together are 1/15 of the table and stay in L2).
+#include "common.cuh"
+#include "childtab_core.cuh"
+
+namespace
+{
+
+constexpr u32 CLD_THREADS = 256;
+
+__global__ void widen_lcp_kernel(u64 N, const u8 *__restrict__ lcp8, u32 *__restrict__ out)
+{
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < N)
+  {
+    out[r] = r == 0 ? 0u : (u32) lcp8[r];  // the reference's walks start from depth 0 at index 0 (mkcld.c:54,113)
+  }
+}
+
+// pairs are (index, value) of the entries whose byte is 255, increasing index (virtualdef.h:203, bese.c:553-566)
+__global__ void scatter_llv_kernel(u64 nllv, const u64 *__restrict__ llv, u64 N, u32 *__restrict__ out,
+                                   u32 *__restrict__ bad)
+{
+  const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nllv)
+  {
+    const u64 idx = llv[2 * t], val = llv[2 * t + 1];
+    if (idx == 0 || idx >= N || val < 255 || val > 0xfffffffeull || out[idx] != 255u)
+    {
+      atomicAdd(bad, 1u);  // not a large-value list of this lcp table
+    } else
+    {
+      out[idx] = (u32) val;
+    }
+  }
+}
+
+// bytes that are 255 without a pair behind them: the two tables do not belong together
+__global__ void count_saturated_kernel(u64 N, const u8 *__restrict__ lcp8, unsigned long long *__restrict__ count)
+{
+  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  const bool sat = r > 0 && r < N && lcp8[r] == 255;
+  const u32 m = __ballot_sync(0xffffffffu, sat);
+  if ((threadIdx.x & 31) == 0 && m != 0)
+  {
+    atomicAdd(count, (unsigned long long) __popc(m));
+  }
+}
+
+__global__ void min_level_kernel(const u32 *__restrict__ in, u64 in_size, u32 *__restrict__ out, u64 out_size)
+{
+  const u64 j = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < out_size)
+  {
+    u32 m = 0xffffffffu;
+    const u64 b = j * cld::FAN;
+#pragma unroll
+    for (u32 c = 0; c < cld::FAN; c++)
+    {
+      if (b + c < in_size)
+      {
+        m = min(m, in[b + c]);
+      }
+    }
+    out[j] = m;
+  }
+}
+
+__global__ void __launch_bounds__(CLD_THREADS) child_kernel(cld::Pyramid py, u8 *__restrict__ out)
+{
+  __shared__ __align__(16) u8 rec[CLD_THREADS * 3];
+  const u64 N = py.size[0];
+  const u64 first = (u64) blockIdx.x * CLD_THREADS;
+  const u64 i = first + threadIdx.x;
+  cld::Child c;
+  c.up = c.down = c.nextl = 0;
+  if (i < N)
+  {
+    c = cld::child_entry(py, i);
+  }
+  rec[3 * threadIdx.x] = c.up;
+  rec[3 * threadIdx.x + 1] = c.down;
+  rec[3 * threadIdx.x + 2] = c.nextl;
+  __syncthreads();
+  // first * 3 is a multiple of 4 (CLD_THREADS * 3 = 768): whole words while they are inside the table, bytes at its end
+  const u64 base = first * 3, total = N * 3;
+  if (threadIdx.x < CLD_THREADS * 3 / 4)
+  {
+    const u64 o = base + 4ull * threadIdx.x;
+    if (o + 4 <= total)
+    {
+      *reinterpret_cast<u32 *>(out + o) = reinterpret_cast<const u32 *>(rec)[threadIdx.x];
+    } else
+    {
+      for (u64 b = o; b < total; b++)
+      {
+        out[b] = rec[b - base];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CLD_THREADS) cld1_kernel(const u8 *__restrict__ cldtab, const u32 *__restrict__ L,
+                                                           u64 N, u8 *__restrict__ out)
+{
+  const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N)
+  {
+    out[i] = cld::cld1_entry(cldtab, L, i, N - 1);
+  }
+}
+
+struct DeviceBuf  // plain allocations: the call must not disturb the arena of a resident build
+{
+  void *p = nullptr;
+  DeviceBuf() = default;
+  DeviceBuf(const DeviceBuf &) = delete;
+  DeviceBuf &operator=(const DeviceBuf &) = delete;
+  void alloc(size_t bytes) { CUDA_CHECK(cudaMalloc(&p, bytes + 256)); }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+  ~DeviceBuf()
+  {
+    if (p != nullptr)
+    {
+      cudaFree(p);
+    }
+  }
+};
+
+inline u32 blocks_for(u64 count) { return (u32) div_up_u64(count, CLD_THREADS); }
+
+}  // namespace
+
+// d_lcp8 / d_llv: tables on the device (the resident ones of the last build, or uploaded copies of an index on file);
+// h_cld (3 N bytes) and h_cld1 (N bytes, may be null) are the caller's host buffers.
+void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv, u64 n, u8 *h_cld, u8 *h_cld1)
+{
+  const u64 N = n + 1;
+  cudaStream_t s = ctx->stream;
+  DeviceBuf levels, cldtab, cld1, flags;
+  // level sizes: N, ceil(N / 16), ... until at most 16 entries
+  u64 sizes[cld::MAX_LEVELS], offs[cld::MAX_LEVELS], total = 0;
+  int top = 0;
+  sizes[0] = N;
+  while (sizes[top] > cld::FAN && top + 1 < cld::MAX_LEVELS)
+  {
+    sizes[top + 1] = div_up_u64(sizes[top], cld::FAN);
+    top++;
+  }
+  for (int k = 0; k <= top; k++)
+  {
+    offs[k] = total;
+    total += (sizes[k] + 63) & ~(u64) 63;
+  }
+  levels.alloc(total * sizeof(u32));
+  cldtab.alloc(3 * N + 16);
+  flags.alloc(64);
+  CUDA_CHECK(cudaMemsetAsync(flags.p, 0, 64, s));
+  u32 *L = levels.as<u32>();
+  // ESA_CHILDTAB_TIMING=1: device times of the three stages on stderr (tools/childtab_probe.py)
+  const bool timing = getenv("ESA_CHILDTAB_TIMING") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  struct EventGuard
+  {
+    cudaEvent_t *e;
+    ~EventGuard()
+    {
+      for (int i = 0; i < 4; i++)
+      {
+        if (e[i] != nullptr)
+        {
+          cudaEventDestroy(e[i]);
+        }
+      }
+    }
+  } event_guard{ev};
+  if (timing)
+  {
+    for (int i = 0; i < 4; i++)
+    {
+      CUDA_CHECK(cudaEventCreate(&ev[i]));
+    }
+    CUDA_CHECK(cudaEventRecord(ev[0], s));
+  }
+  widen_lcp_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(N, d_lcp8, L);
+  CUDA_CHECK(cudaGetLastError());
+  count_saturated_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(N, d_lcp8, flags.as<unsigned long long>() + 1);
+  CUDA_CHECK(cudaGetLastError());
+  if (nllv > 0)
+  {
+    scatter_llv_kernel<<<blocks_for(nllv), CLD_THREADS, 0, s>>>(nllv, d_llv, N, L, flags.as<u32>());
+    CUDA_CHECK(cudaGetLastError());
+  }
+  cld::Pyramid py;
+  memset(&py, 0, sizeof py);
+  py.top = top;
+  for (int k = 0; k <= top; k++)
+  {
+    py.level[k] = L + offs[k];
+    py.size[k] = sizes[k];
+  }
+  for (int k = 0; k < top; k++)
+  {
+    min_level_kernel<<<blocks_for(sizes[k + 1]), CLD_THREADS, 0, s>>>(py.level[k], sizes[k], L + offs[k + 1],
+                                                                     sizes[k + 1]);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (h_cld1 != nullptr)
+  {
+    cld1.alloc(N);
+  }
+  if (timing)
+  {
+    CUDA_CHECK(cudaEventRecord(ev[1], s));
+  }
+  child_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(py, cldtab.as<u8>());
+  CUDA_CHECK(cudaGetLastError());
+  if (timing)
+  {
+    CUDA_CHECK(cudaEventRecord(ev[2], s));
+  }
+  if (h_cld1 != nullptr)
+  {
+    cld1_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(cldtab.as<u8>(), L, N, cld1.as<u8>());
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (timing)
+  {
+    CUDA_CHECK(cudaEventRecord(ev[3], s));
+  }
+  u64 h_flags[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof h_flags, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if ((u32) h_flags[0] != 0 || h_flags[1] != nllv)
+  {
+    esa_throw(ESA_ERR_ARGUMENT,
+              "the large lcp values do not belong to this lcp table: %llu entries are 255, %llu pairs given, %u of them "
+              "out of place",
+              (unsigned long long) h_flags[1], (unsigned long long) nllv, (unsigned) (u32) h_flags[0]);
+  }
+  if (timing)
+  {
+    float a = 0, b = 0, c = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    CUDA_CHECK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+    CUDA_CHECK(cudaEventElapsedTime(&c, ev[2], ev[3]));
+    fprintf(stderr, "childtab: entries %llu large %llu  widen+pyramid %.3f ms  child_kernel %.3f ms  cld1_kernel %.3f ms\n",
+            (unsigned long long) N, (unsigned long long) nllv, a, b, c);
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_cld, cldtab.p, 3 * N, cudaMemcpyDeviceToHost, s));
+  if (h_cld1 != nullptr)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(h_cld1, cld1.p, N, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}

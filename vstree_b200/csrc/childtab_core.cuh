@@ -1,0 +1,259 @@
+// childtab_core.cuh -- the child table (.cld / .cld1) as independent per-entry searches.
+//
+// The reference fills the table with two sequential stack walks over the lcp table (mkcldtabnextlIndex and
+// mkcldtabupdown, src/kurtz/mkcld.c:41-207) and folds the three fields into one byte per entry (compresscldtab,
+// mkcld.c:225-284).  What the walks leave behind has a closed form per entry; L is the exact lcp table with L[0] = 0
+// (the walks never read lcptab[0], they start from a stack entry of depth 0 at index 0), n = totallength:
+//
+//   j(i)        = the first index > i with L[j] <= L[i]                                   (none: off the table)
+//   nextlIndex  = j - i   when j exists and L[j] == L[i]                                  (mkcld.c:62-81)
+//   down        = m - i   when j exists and j > i + 1, m = leftmost minimum of L in (i, j) (mkcld.c:123-147)
+//   up          = i - m   when L[i-1] > L[i], q = the last index < i with L[q] <= L[i],
+//                 m = leftmost minimum of L in (q, i)                                      (mkcld.c:148-171)
+//   each clamped to LARGECHILDVALUE = 255, UNDEFCHILDVALUE = 0 otherwise                   (virtualdef.h:165-166)
+//
+// (an entry is on the reference's stack at step i exactly when nothing after it is smaller; the entry popped last by
+// L[i] is therefore the leftmost minimum of the stretch that L[i] closes.)
+//
+// The searches run on a min-pyramid over L (level k+1 = minimum of FAN consecutive entries of level k): next / previous
+// smaller-or-equal walk through siblings, climb at a group border and descend into the first block whose minimum
+// qualifies; the leftmost minimum of a range collects at most 2 (FAN - 1) fringe nodes per level.  Lcp tables are
+// locally rough, so most searches end inside level 0.
+//
+// Plain C++ on purpose: the same functions are compiled by nvcc for the device (childtab.cu) and by g++ into a model
+// that tests/test_childtab_model.py runs against the oracle's stack walk on the CPU.  They are not a product path on
+// the host: libvstree_b200 only ever calls them from kernels.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define CLD_HD __host__ __device__ __forceinline__
+#else
+#define CLD_HD static inline
+#endif
+
+namespace cld
+{
+
+constexpr uint32_t FAN = 16;
+constexpr int MAX_LEVELS = 10;  // 16^9 > 2^32
+constexpr uint64_t NONE = ~(uint64_t) 0;
+constexpr uint32_t LARGE = 255;  // LARGECHILDVALUE
+
+struct Pyramid
+{
+  const uint32_t *level[MAX_LEVELS];
+  uint64_t size[MAX_LEVELS];
+  int top;  // index of the highest level (at most FAN entries, or MAX_LEVELS - 1)
+};
+
+// first index > i with a value <= v; size[0] when there is none
+CLD_HD uint64_t next_le(const Pyramid &py, uint64_t i, uint32_t v)
+{
+  int k = 0;
+  uint64_t p = i + 1;
+  while (true)
+  {
+    if (p >= py.size[k])
+    {
+      return py.size[0];
+    }
+    if (py.level[k][p] <= v)
+    {
+      while (k > 0)
+      {
+        k--;
+        p *= FAN;
+        while (py.level[k][p] > v)
+        {
+          p++;
+        }
+      }
+      return p;
+    }
+    p++;
+    if (p % FAN == 0 && k < py.top)
+    {
+      p /= FAN;
+      k++;
+    }
+  }
+}
+
+// last index < i with a value <= v; NONE when there is none
+CLD_HD uint64_t prev_le(const Pyramid &py, uint64_t i, uint32_t v)
+{
+  if (i == 0)
+  {
+    return NONE;
+  }
+  int k = 0;
+  uint64_t p = i - 1;
+  while (true)
+  {
+    if (py.level[k][p] <= v)
+    {
+      while (k > 0)
+      {
+        k--;
+        p = p * FAN + (FAN - 1);
+        if (p >= py.size[k])
+        {
+          p = py.size[k] - 1;
+        }
+        while (py.level[k][p] > v)
+        {
+          p--;
+        }
+      }
+      return p;
+    }
+    if (p == 0)
+    {
+      return NONE;
+    }
+    if (p % FAN == 0 && k < py.top)
+    {
+      p = p / FAN - 1;  // the group that starts at p is done: go on with the block in front of its parent
+      k++;
+    } else
+    {
+      p--;
+    }
+  }
+}
+
+// position of the leftmost minimum of level 0 in the closed range [a, b], a <= b < size[0]
+CLD_HD uint64_t leftmost_min(const Pyramid &py, uint64_t a, uint64_t b)
+{
+  uint32_t best = 0xffffffffu;
+  uint64_t best_start = NONE, best_p = 0;
+  int best_k = 0;
+  int k = 0;
+  int64_t lo = (int64_t) a, hi = (int64_t) b;
+  uint64_t span = 1;  // leaves under one node of level k
+#define CLD_CONSIDER(P)                                                        \
+  do                                                                           \
+  {                                                                            \
+    const uint32_t val__ = py.level[k][(P)];                                   \
+    const uint64_t start__ = (uint64_t) (P) * span;                            \
+    if (val__ < best || (val__ == best && start__ < best_start))               \
+    {                                                                          \
+      best = val__;                                                            \
+      best_start = start__;                                                    \
+      best_p = (uint64_t) (P);                                                 \
+      best_k = k;                                                              \
+    }                                                                          \
+  } while (0)
+  while (lo <= hi)
+  {
+    if (k == py.top)
+    {
+      for (int64_t p = lo; p <= hi; p++)
+      {
+        CLD_CONSIDER(p);
+      }
+      break;
+    }
+    while (lo <= hi && lo % (int64_t) FAN != 0)
+    {
+      CLD_CONSIDER(lo);
+      lo++;
+    }
+    while (lo <= hi && (hi + 1) % (int64_t) FAN != 0)
+    {
+      CLD_CONSIDER(hi);
+      hi--;
+    }
+    if (lo > hi)
+    {
+      break;
+    }
+    lo /= (int64_t) FAN;
+    hi = (hi + 1) / (int64_t) FAN - 1;
+    k++;
+    span *= FAN;
+  }
+#undef CLD_CONSIDER
+  k = best_k;
+  uint64_t p = best_p;
+  while (k > 0)
+  {
+    k--;
+    p *= FAN;
+    while (py.level[k][p] != best)
+    {
+      p++;
+    }
+  }
+  return p;
+}
+
+struct Child
+{
+  uint8_t up, down, nextl;  // the order of Childinfo (virtualdef.h:174-179), which is also the order in the .cld file
+};
+
+CLD_HD uint8_t clamp_child(uint64_t d) { return (uint8_t) (d >= LARGE ? LARGE : d); }
+
+// the three fields of entry i (0 <= i <= n, size[0] == n + 1)
+CLD_HD Child child_entry(const Pyramid &py, uint64_t i)
+{
+  const uint32_t *L = py.level[0];
+  const uint64_t N = py.size[0];
+  const uint32_t v = L[i];
+  Child c;
+  c.up = c.down = c.nextl = 0;
+  const uint64_t j = next_le(py, i, v);
+  if (j < N)
+  {
+    if (L[j] == v)
+    {
+      c.nextl = clamp_child(j - i);
+    }
+    if (j > i + 1)
+    {
+      c.down = clamp_child(leftmost_min(py, i + 1, j - 1) - i);
+    }
+  }
+  if (i >= 1 && L[i - 1] > v)
+  {
+    const uint64_t q = prev_le(py, i, v);  // exists: L[0] = 0
+    c.up = clamp_child(i - leftmost_min(py, q == NONE ? 0 : q + 1, i - 1));
+  }
+  return c;
+}
+
+// entry i of the one-byte table, from the three-field table (3 bytes per entry) and L.  The reference runs three loops
+// one after the other over the same byte (mkcld.c:230-283), the later one overwrites; they stop below totallength
+// (the third below totallength - 1), so the last entry -- and an entry that no loop writes -- keeps what the
+// allocation held: 0 here.
+CLD_HD uint8_t cld1_entry(const uint8_t *cld, const uint32_t *L, uint64_t i, uint64_t n)
+{
+  if (i >= n)
+  {
+    return 0;
+  }
+  const uint8_t down = cld[3 * i + 1], nextl = cld[3 * i + 2];
+  uint8_t out = 0;
+  const uint64_t next = i + nextl;  // decoded from the clamped byte, like DECODENEXTLINDEX (mkcld.c:209-210)
+  if (next > i)
+  {
+    out = nextl;
+  }
+  if ((next == i && down > 0) || next == n)
+  {
+    out = down;
+  }
+  if (i + 1 < n && L[i] > L[i + 1])
+  {
+    const uint8_t up1 = cld[3 * (i + 1)], down1 = cld[3 * (i + 1) + 1];
+    if (up1 != 0 || down1 != 0)  // DECODEUP(i+1) != DECODEDOWN(i+1)
+    {
+      out = up1;
+    }
+  }
+  return out;
+}
+
+}  // namespace cld

@@ -377,4 +377,6 @@ void finalize_tables_direct(esa_ctx *ctx, u32 demand, u64 count, u64 index_base,
 void compute_sti1(esa_ctx *ctx, u32 prefixlength);
 void compute_sti_sharded(esa_ctx *ctx, esa_comm *comm, u32 prefixlength, u32 demand);  // .sti1 / .sti of a sharded build
 void compute_skp(esa_ctx *ctx, const u32 *d_v, const u32 *d_lcpfull);  // skp.cu
+// childtab.cu: the child table from lcp bytes + large-value pairs on the device into the caller's host buffers
+void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv, u64 n, u8 *h_cld, u8 *h_cld1);
 int run_checks(esa_ctx *ctx, std::string &msg);
