@@ -43,12 +43,36 @@ struct HostPyramid
 extern "C" {
 
 // L has N = n + 1 entries (L[0] = 0); cld gets 3 N bytes, cld1 N bytes
-void cld_model_tables(const uint32_t *L, uint64_t N, uint8_t *cldtab, uint8_t *cld1)
+void cld_model_tables(const uint32_t *L, uint64_t N, uint32_t threads, uint32_t near, uint8_t *cldtab, uint8_t *cld1,
+                      uint64_t *near_count)
 {
   HostPyramid h(L, N);
+  // as child_kernel runs it: blocks of `threads` entries with a window of `near` entries on either side; the bounded
+  // scan first, the pyramid search for what it leaves open (near == 0: the pyramid search for every entry)
+  std::vector<uint32_t> win(threads + 2 * near);
   for (uint64_t i = 0; i < N; i++)
   {
-    const cld::Child c = cld::child_entry(h.py, i);
+    cld::Child c;
+    bool settled = false;
+    if (near > 0)
+    {
+      const uint64_t first = i / threads * threads;
+      const uint64_t w0 = first >= near ? first - near : 0;
+      const uint64_t wend = first + threads + near < N ? first + threads + near : N;
+      for (uint64_t t = w0; t < wend; t++)
+      {
+        win[t - w0] = L[t];
+      }
+      settled = cld::child_entry_near(win.data(), w0, wend - w0, N, i, near, c);
+      if (settled && near_count != nullptr)
+      {
+        ++*near_count;
+      }
+    }
+    if (!settled)
+    {
+      c = cld::child_entry(h.py, i);
+    }
     cldtab[3 * i] = c.up;
     cldtab[3 * i + 1] = c.down;
     cldtab[3 * i + 2] = c.nextl;

@@ -47,20 +47,25 @@ def model():
         lib = ctypes.CDLL(MODEL_SO)
         u8p, u32p, u64p = (ctypes.POINTER(t) for t in (ctypes.c_uint8, ctypes.c_uint32, ctypes.c_uint64))
         lib.cld_model_tables.restype = None
-        lib.cld_model_tables.argtypes = [u32p, ctypes.c_uint64, u8p, u8p]
+        lib.cld_model_tables.argtypes = [u32p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, u8p, u8p, u64p]
         lib.cld_model_queries.restype = None
         lib.cld_model_queries.argtypes = [u32p, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         _model = lib
     return _model
 
 
-def model_tables(L):
+def model_tables(L, threads=256, near=32, count=None):
+    """The tables as child_kernel computes them: blocks of `threads` entries, the bounded scan over `near` entries on
+    either side first (CLD_THREADS / CLD_NEAR of childtab.cu), the pyramid search for the rest; near=0: pyramid only."""
     L = np.ascontiguousarray(L, np.uint32)
     N = len(L)
     cld, cld1 = np.zeros(3 * N, np.uint8), np.zeros(N, np.uint8)
-    model().cld_model_tables(L.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), N,
+    settled = ctypes.c_uint64(0)
+    model().cld_model_tables(L.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), N, threads, near,
                              cld.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
-                             cld1.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+                             cld1.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(settled))
+    if count is not None:
+        count.append(settled.value)
     return cld, cld1
 
 
@@ -127,8 +132,12 @@ def test_oracle_childtab_against_reference_files(name):
     if "tables" in g:
         assert cld.tolist() == g["tables"]["cld"] and cld1.tolist() == g["tables"]["cld1"]
     # the same tables from the per-entry functions of the kernels
-    m_cld, m_cld1 = model_tables(exact_lcp(o["lcp"], o["llv"]))
-    assert np.array_equal(m_cld, cld) and np.array_equal(m_cld1, cld1)
+    near = []
+    for kw in ({"count": near}, {"near": 0}, {"threads": 16, "near": 3}):
+        m_cld, m_cld1 = model_tables(exact_lcp(o["lcp"], o["llv"]), **kw)
+        assert np.array_equal(m_cld, cld) and np.array_equal(m_cld1, cld1), kw
+    if len(tis) >= 20000 and "poly" not in name:
+        assert near[0] > 0.8 * len(tis), f"the bounded scan settles only {near[0]} of {len(tis)} entries"
 
 
 @pytest.mark.parametrize("name", list(SHAPED))
@@ -136,10 +145,11 @@ def test_kernel_functions_against_the_stack_walk(name):
     L = SHAPED[name]
     lcp, llv = split_lcp(L)
     cld, cld1 = ou.oracle_childtab(lcp, llv)
-    m_cld, m_cld1 = model_tables(L)
-    bad = np.nonzero(m_cld != cld)[0]
-    assert len(bad) == 0, f"{name}: record {bad[0] // 3} field {bad[0] % 3}: {m_cld[bad[0]]} != {cld[bad[0]]}"
-    assert np.array_equal(m_cld1, cld1)
+    for kw in ({}, {"near": 0}, {"threads": 16, "near": 3}, {"threads": 64, "near": 1}, {"threads": 32, "near": 64}):
+        m_cld, m_cld1 = model_tables(L, **kw)
+        bad = np.nonzero(m_cld != cld)[0]
+        assert len(bad) == 0, f"{name} {kw}: record {bad[0] // 3} field {bad[0] % 3}: {m_cld[bad[0]]} != {cld[bad[0]]}"
+        assert np.array_equal(m_cld1, cld1), kw
     c = cld.reshape(-1, 3)
     if name in ("long_intervals", "nested_deep", "falling"):
         assert (c == 255).any(), "the case is meant to reach LARGECHILDVALUE"

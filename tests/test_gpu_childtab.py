@@ -79,7 +79,8 @@ def test_twenty_million_entries_against_the_stack_walk(esa):
     N = 20_000_001
     L = rng.geometric(0.08, N) - 1
     L[rng.integers(0, N, N // 50)] = rng.integers(255, 3_000_000, N // 50)   # scattered large values
-    L[5_000_000:5_400_000] = 40 + (np.arange(400_000) % 3)                    # a long interval: distances >> 255
+    L[5_000_000:5_400_000] = 50 + rng.integers(0, 3, 400_000)                 # long intervals: every 300th entry closes
+    L[5_000_000:5_400_000:300] = 45                                           # one, distances beyond 255
     L[12_000_000:12_000_600] = np.arange(600) + 300                           # a staircase of large values
     L[0] = 0
     lcp, llv = split_lcp(L)

@@ -3,11 +3,12 @@
 // mkcldtabnextlIndex + mkcldtabupdown + compresscldtab (src/kurtz/mkcld.c:41-284).  The per-entry definition and the
 // searches are in childtab_core.cuh; this file holds the kernels around them:
 //
-//   widen_lcp_kernel      lcp bytes -> 32-bit values                                    1 B read, 4 B written per entry
+//   widen_lcp_kernel      lcp bytes -> 32-bit values, count of the saturated ones       1 B read, 4 B written per entry
 //   scatter_llv_kernel    the exact values >= 255 from the (index, value) pairs         16 B per large value
 //   min_level_kernel      one level of the min-pyramid                                  4 (1 + 1/16) B per entry and level
-//   child_kernel          up / down / nextlIndex of every entry, staged through shared memory so that the 3-byte
-//                         records leave as whole words                                  >= 4 B read, 3 B written
+//   child_kernel          up / down / nextlIndex of every entry: a bounded scan in a shared-memory window first, the
+//                         pyramid search for what that leaves open; the 3-byte records leave as whole words
+//                                                                                       >= 4 B read, 3 B written
 //   cld1_kernel           the one-byte table from the three-field table                 ~ 11 B read, 1 B written
 //
 // HBM-bound integer work over tables of n + 1 entries; the searches touch neighbours of the entry almost always (the
@@ -19,13 +20,24 @@ namespace
 {
 
 constexpr u32 CLD_THREADS = 256;
+constexpr u32 CLD_NEAR = 32;  // entries on either side that phase 1 of child_kernel looks at
 
-__global__ void widen_lcp_kernel(u64 N, const u8 *__restrict__ lcp8, u32 *__restrict__ out)
+// 32-bit copy of the lcp bytes (the reference's walks start from depth 0 at index 0 whatever lcptab[0] holds,
+// mkcld.c:54,113) and the number of saturated bytes: each of them needs exactly one large-value pair
+__global__ void widen_lcp_kernel(u64 N, const u8 *__restrict__ lcp8, u32 *__restrict__ out,
+                                 unsigned long long *__restrict__ saturated)
 {
   const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  u32 v = 0;
   if (r < N)
   {
-    out[r] = r == 0 ? 0u : (u32) lcp8[r];  // the reference's walks start from depth 0 at index 0 (mkcld.c:54,113)
+    v = r == 0 ? 0u : (u32) lcp8[r];
+    out[r] = v;
+  }
+  const u32 m = __ballot_sync(0xffffffffu, v == 255u);
+  if ((threadIdx.x & 31) == 0 && m != 0)
+  {
+    atomicAdd(saturated, (unsigned long long) __popc(m));
   }
 }
 
@@ -44,18 +56,6 @@ __global__ void scatter_llv_kernel(u64 nllv, const u64 *__restrict__ llv, u64 N,
     {
       out[idx] = (u32) val;
     }
-  }
-}
-
-// bytes that are 255 without a pair behind them: the two tables do not belong together
-__global__ void count_saturated_kernel(u64 N, const u8 *__restrict__ lcp8, unsigned long long *__restrict__ count)
-{
-  const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-  const bool sat = r > 0 && r < N && lcp8[r] == 255;
-  const u32 m = __ballot_sync(0xffffffffu, sat);
-  if ((threadIdx.x & 31) == 0 && m != 0)
-  {
-    atomicAdd(count, (unsigned long long) __popc(m));
   }
 }
 
@@ -78,21 +78,49 @@ __global__ void min_level_kernel(const u32 *__restrict__ in, u64 in_size, u32 *_
   }
 }
 
+// Two phases per block of CLD_THREADS entries.  Phase 1: every thread scans at most CLD_NEAR entries on either side of
+// its entry in a shared-memory window (child_entry_near); on real lcp tables that settles more than nine entries in ten.
+// Phase 2: the entries it could not settle are queued and shared out over the threads of the block for the full search
+// on the pyramid (child_entry), so that one far-reaching entry does not hold up the 31 other lanes of its warp.
 __global__ void __launch_bounds__(CLD_THREADS) child_kernel(cld::Pyramid py, u8 *__restrict__ out)
 {
   __shared__ __align__(16) u8 rec[CLD_THREADS * 3];
+  __shared__ u32 win[CLD_THREADS + 2 * CLD_NEAR];
+  __shared__ uint16_t queue[CLD_THREADS];
+  __shared__ u32 queued;
   const u64 N = py.size[0];
   const u64 first = (u64) blockIdx.x * CLD_THREADS;
+  const u64 w0 = first >= CLD_NEAR ? first - CLD_NEAR : 0;
+  const u64 wend = min(N, first + CLD_THREADS + CLD_NEAR);
+  const u64 wn = wend - w0;
+  for (u64 t = threadIdx.x; t < wn; t += CLD_THREADS)
+  {
+    win[t] = py.level[0][w0 + t];
+  }
+  if (threadIdx.x == 0)
+  {
+    queued = 0;
+  }
+  __syncthreads();
   const u64 i = first + threadIdx.x;
   cld::Child c;
   c.up = c.down = c.nextl = 0;
-  if (i < N)
+  if (i < N && !cld::child_entry_near(win, w0, wn, N, i, CLD_NEAR, c))
   {
-    c = cld::child_entry(py, i);
+    queue[atomicAdd(&queued, 1u)] = (uint16_t) threadIdx.x;
   }
   rec[3 * threadIdx.x] = c.up;
   rec[3 * threadIdx.x + 1] = c.down;
   rec[3 * threadIdx.x + 2] = c.nextl;
+  __syncthreads();
+  for (u32 t = threadIdx.x; t < queued; t += CLD_THREADS)
+  {
+    const u32 e = queue[t];
+    const cld::Child far = cld::child_entry(py, first + e);
+    rec[3 * e] = far.up;
+    rec[3 * e + 1] = far.down;
+    rec[3 * e + 2] = far.nextl;
+  }
   __syncthreads();
   // first * 3 is a multiple of 4 (CLD_THREADS * 3 = 768): whole words while they are inside the table, bytes at its end
   const u64 base = first * 3, total = N * 3;
@@ -194,9 +222,7 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
     }
     CUDA_CHECK(cudaEventRecord(ev[0], s));
   }
-  widen_lcp_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(N, d_lcp8, L);
-  CUDA_CHECK(cudaGetLastError());
-  count_saturated_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(N, d_lcp8, flags.as<unsigned long long>() + 1);
+  widen_lcp_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(N, d_lcp8, L, flags.as<unsigned long long>() + 1);
   CUDA_CHECK(cudaGetLastError());
   if (nllv > 0)
   {

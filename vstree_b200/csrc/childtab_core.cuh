@@ -224,6 +224,93 @@ CLD_HD Child child_entry(const Pyramid &py, uint64_t i)
   return c;
 }
 
+// The common case without the pyramid: `win` holds L[w0, w0 + wn) (shared memory on the device: the entries of a thread
+// block and `cap` entries on either side, clipped to the table).  Scans at most `cap` entries to the right for j and at
+// most `cap` to the left for q, keeping the leftmost minimum of what it passes, and fills `c` when both scans end
+// inside the window; returns false otherwise (the caller then runs child_entry).  N = size of the table.
+CLD_HD bool child_entry_near(const uint32_t *win, uint64_t w0, uint64_t wn, uint64_t N, uint64_t i, uint32_t cap,
+                             Child &c)
+{
+  const uint32_t v = win[i - w0];
+  c.up = c.down = c.nextl = 0;
+  // to the right: j, and the leftmost minimum of (i, j)
+  bool found = false;
+  uint32_t minv = 0xffffffffu;
+  uint64_t minp = 0, j = N;
+  for (uint32_t s = 1; s <= cap; s++)
+  {
+    const uint64_t p = i + s;
+    if (p >= N)
+    {
+      found = true;  // off the table: no j, nothing defined on this side
+      break;
+    }
+    if (p >= w0 + wn)
+    {
+      break;
+    }
+    const uint32_t x = win[p - w0];
+    if (x <= v)
+    {
+      j = p;
+      found = true;
+      break;
+    }
+    if (x < minv)
+    {
+      minv = x;
+      minp = p;
+    }
+  }
+  if (!found)
+  {
+    return false;
+  }
+  if (j < N)
+  {
+    if (win[j - w0] == v)
+    {
+      c.nextl = clamp_child(j - i);
+    }
+    if (j > i + 1)
+    {
+      c.down = clamp_child(minp - i);
+    }
+  }
+  // to the left: q, and the leftmost minimum of (q, i)
+  if (i >= 1 && win[i - 1 - w0] > v)
+  {
+    found = false;
+    minv = 0xffffffffu;
+    minp = 0;
+    for (uint32_t s = 1; s <= cap && s <= i; s++)
+    {
+      const uint64_t p = i - s;
+      if (p < w0)
+      {
+        break;
+      }
+      const uint32_t x = win[p - w0];
+      if (x <= v)
+      {
+        found = true;
+        break;
+      }
+      if (x <= minv)  // walking leftwards: an equal value further left replaces the one found before
+      {
+        minv = x;
+        minp = p;
+      }
+    }
+    if (!found)
+    {
+      return false;
+    }
+    c.up = clamp_child(i - minp);
+  }
+  return true;
+}
+
 // entry i of the one-byte table, from the three-field table (3 bytes per entry) and L.  The reference runs three loops
 // one after the other over the same byte (mkcld.c:230-283), the later one overwrites; they stop below totallength
 // (the third below totallength - 1), so the last entry -- and an entry that no loop writes -- keeps what the
