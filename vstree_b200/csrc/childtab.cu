@@ -6,9 +6,9 @@
 //   widen_lcp_kernel      lcp bytes -> 32-bit values, count of the saturated ones       1 B read, 4 B written per entry
 //   scatter_llv_kernel    the exact values >= 255 from the (index, value) pairs         16 B per large value
 //   min_level_kernel      one level of the min-pyramid                                  4 (1 + 1/16) B per entry and level
-//   child_kernel          up / down / nextlIndex of every entry: a bounded scan in a shared-memory window first, the
-//                         pyramid search for what that leaves open; the 3-byte records leave as whole words
-//                                                                                       >= 4 B read, 3 B written
+//   child_near_kernel     up / down / nextlIndex of every entry a bounded scan in a shared-memory window can settle;
+//                         the 3-byte records leave as whole words                       4 B read, 3 B written
+//   child_far_kernel      the pyramid search for the entries the scan left open         a few 64-byte groups per level
 //   cld1_kernel           the one-byte table from the three-field table                 ~ 11 B read, 1 B written
 //
 // HBM-bound integer work over tables of n + 1 entries; the searches touch neighbours of the entry almost always (the
@@ -78,22 +78,25 @@ __global__ void min_level_kernel(const u32 *__restrict__ in, u64 in_size, u32 *_
   }
 }
 
-// Two phases per block of CLD_THREADS entries.  Phase 1: every thread scans at most CLD_NEAR entries on either side of
-// its entry in a shared-memory window (child_entry_near); on real lcp tables that settles more than nine entries in ten.
-// Phase 2: the entries it could not settle are queued and shared out over the threads of the block for the full search
-// on the pyramid (child_entry), so that one far-reaching entry does not hold up the 31 other lanes of its warp.
-__global__ void __launch_bounds__(CLD_THREADS) child_kernel(cld::Pyramid py, u8 *__restrict__ out)
+// Two kernels.  child_near_kernel: every thread scans at most CLD_NEAR entries on either side of its entry in a
+// shared-memory window (child_entry_near); on real lcp tables that settles more than nine entries in ten.  The entries it
+// cannot settle are appended to a queue.  child_far_kernel: the queued entries, spread evenly over a full grid, run the
+// search on the pyramid (child_entry) -- so a far-reaching entry neither holds up the 31 other lanes of its warp nor
+// costs the common case its registers.
+__global__ void __launch_bounds__(CLD_THREADS) child_near_kernel(cld::Pyramid py, u8 *__restrict__ out,
+                                                                 u32 *__restrict__ far_queue, u32 *__restrict__ far_count,
+                                                                 bool use_near)
 {
   __shared__ __align__(16) u8 rec[CLD_THREADS * 3];
   __shared__ u32 win[CLD_THREADS + 2 * CLD_NEAR];
   __shared__ uint16_t queue[CLD_THREADS];
-  __shared__ u32 queued;
+  __shared__ u32 queued, queue_base;
   const u64 N = py.size[0];
   const u64 first = (u64) blockIdx.x * CLD_THREADS;
   const u64 w0 = first >= CLD_NEAR ? first - CLD_NEAR : 0;
   const u64 wend = min(N, first + CLD_THREADS + CLD_NEAR);
-  const u64 wn = wend - w0;
-  for (u64 t = threadIdx.x; t < wn; t += CLD_THREADS)
+  const u32 wn = (u32) (wend - w0);
+  for (u32 t = threadIdx.x; t < wn; t += CLD_THREADS)
   {
     win[t] = py.level[0][w0 + t];
   }
@@ -105,23 +108,24 @@ __global__ void __launch_bounds__(CLD_THREADS) child_kernel(cld::Pyramid py, u8 
   const u64 i = first + threadIdx.x;
   cld::Child c;
   c.up = c.down = c.nextl = 0;
-  if (i < N && !cld::child_entry_near(win, w0, wn, N, i, CLD_NEAR, c))
+  if (i < N && !(use_near && cld::child_entry_near(win, w0, wn, N, i, CLD_NEAR, c)))
   {
     queue[atomicAdd(&queued, 1u)] = (uint16_t) threadIdx.x;
+    c.up = c.down = c.nextl = 0;  // child_far_kernel writes this record
   }
   rec[3 * threadIdx.x] = c.up;
   rec[3 * threadIdx.x + 1] = c.down;
   rec[3 * threadIdx.x + 2] = c.nextl;
   __syncthreads();
-  for (u32 t = threadIdx.x; t < queued; t += CLD_THREADS)
+  if (threadIdx.x == 0 && queued > 0)
   {
-    const u32 e = queue[t];
-    const cld::Child far = cld::child_entry(py, first + e);
-    rec[3 * e] = far.up;
-    rec[3 * e + 1] = far.down;
-    rec[3 * e + 2] = far.nextl;
+    queue_base = atomicAdd(far_count, queued);
   }
   __syncthreads();
+  if (threadIdx.x < queued)
+  {
+    far_queue[queue_base + threadIdx.x] = (u32) (first + queue[threadIdx.x]);
+  }
   // first * 3 is a multiple of 4 (CLD_THREADS * 3 = 768): whole words while they are inside the table, bytes at its end
   const u64 base = first * 3, total = N * 3;
   if (threadIdx.x < CLD_THREADS * 3 / 4)
@@ -137,6 +141,20 @@ __global__ void __launch_bounds__(CLD_THREADS) child_kernel(cld::Pyramid py, u8 
         out[b] = rec[b - base];
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(CLD_THREADS) child_far_kernel(cld::Pyramid py, const u32 *__restrict__ far_queue,
+                                                                const u32 *__restrict__ far_count, u8 *__restrict__ out)
+{
+  const u64 count = *far_count;
+  for (u64 t = (u64) blockIdx.x * CLD_THREADS + threadIdx.x; t < count; t += (u64) gridDim.x * CLD_THREADS)
+  {
+    const u64 e = far_queue[t];
+    const cld::Child c = cld::child_entry(py, e);
+    out[3 * e] = c.up;
+    out[3 * e + 1] = c.down;
+    out[3 * e + 2] = c.nextl;
   }
 }
 
@@ -177,7 +195,7 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
 {
   const u64 N = n + 1;
   cudaStream_t s = ctx->stream;
-  DeviceBuf levels, cldtab, cld1, flags;
+  DeviceBuf levels, cldtab, cld1, flags, far;
   // level sizes: N, ceil(N / 16), ... until at most 16 entries
   u64 sizes[cld::MAX_LEVELS], offs[cld::MAX_LEVELS], total = 0;
   int top = 0;
@@ -194,6 +212,7 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
   }
   levels.alloc(total * sizeof(u32));
   cldtab.alloc(3 * N + 16);
+  far.alloc(N * sizeof(u32));  // worst case: the bounded scan settles nothing
   flags.alloc(64);
   CUDA_CHECK(cudaMemsetAsync(flags.p, 0, 64, s));
   u32 *L = levels.as<u32>();
@@ -251,7 +270,13 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
   {
     CUDA_CHECK(cudaEventRecord(ev[1], s));
   }
-  child_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(py, cldtab.as<u8>());
+  // ESA_CHILDTAB_NO_NEAR=1 (tests): every entry takes the pyramid search
+  const bool use_near = getenv("ESA_CHILDTAB_NO_NEAR") == nullptr;
+  child_near_kernel<<<blocks_for(N), CLD_THREADS, 0, s>>>(py, cldtab.as<u8>(), far.as<u32>(), flags.as<u32>() + 8,
+                                                          use_near);
+  CUDA_CHECK(cudaGetLastError());
+  child_far_kernel<<<(u32) ctx->num_sms * 6, CLD_THREADS, 0, s>>>(py, far.as<u32>(), flags.as<u32>() + 8,
+                                                                  cldtab.as<u8>());
   CUDA_CHECK(cudaGetLastError());
   if (timing)
   {
@@ -266,7 +291,7 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
   {
     CUDA_CHECK(cudaEventRecord(ev[3], s));
   }
-  u64 h_flags[2] = {0, 0};
+  u64 h_flags[5] = {0, 0, 0, 0, 0};  // [0] misplaced pairs (u32), [1] saturated bytes, [4] queued far entries (u32)
   CUDA_CHECK(cudaMemcpyAsync(h_flags, flags.p, sizeof h_flags, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   if ((u32) h_flags[0] != 0 || h_flags[1] != nllv)
@@ -282,8 +307,8 @@ void compute_childtab(esa_ctx *ctx, const u8 *d_lcp8, const u64 *d_llv, u64 nllv
     CUDA_CHECK(cudaEventElapsedTime(&a, ev[0], ev[1]));
     CUDA_CHECK(cudaEventElapsedTime(&b, ev[1], ev[2]));
     CUDA_CHECK(cudaEventElapsedTime(&c, ev[2], ev[3]));
-    fprintf(stderr, "childtab: entries %llu large %llu  widen+pyramid %.3f ms  child_kernel %.3f ms  cld1_kernel %.3f ms\n",
-            (unsigned long long) N, (unsigned long long) nllv, a, b, c);
+    fprintf(stderr, "childtab: entries %llu large %llu far %u  widen+pyramid %.3f ms  child kernels %.3f ms  cld1_kernel %.3f ms\n",
+            (unsigned long long) N, (unsigned long long) nllv, (unsigned) (u32) h_flags[4], a, b, c);
   }
   CUDA_CHECK(cudaMemcpyAsync(h_cld, cldtab.p, 3 * N, cudaMemcpyDeviceToHost, s));
   if (h_cld1 != nullptr)

@@ -16,9 +16,9 @@
 // L[i] is therefore the leftmost minimum of the stretch that L[i] closes.)
 //
 // The searches run on a min-pyramid over L (level k+1 = minimum of FAN consecutive entries of level k): next / previous
-// smaller-or-equal walk through siblings, climb at a group border and descend into the first block whose minimum
-// qualifies; the leftmost minimum of a range collects at most 2 (FAN - 1) fringe nodes per level.  Lcp tables are
-// locally rough, so most searches end inside level 0.
+// smaller-or-equal look at the rest of the group of siblings, climb at its border and descend into the first block whose
+// minimum qualifies; the leftmost minimum of a range collects the two fringe groups of every level.  A group of siblings
+// is fetched as a whole, so a search pays one memory latency per level.
 //
 // Plain C++ on purpose: the same functions are compiled by nvcc for the device (childtab.cu) and by g++ into a model
 // that tests/test_childtab_model.py runs against the oracle's stack walk on the CPU.  They are not a product path on
@@ -47,32 +47,101 @@ struct Pyramid
   int top;  // index of the highest level (at most FAN entries, or MAX_LEVELS - 1)
 };
 
+// One group of FAN siblings (FAN * 4 = 64 bytes, aligned) in one go: on the device up to four 128-bit loads that are
+// in flight together, so that a search pays one memory latency per level instead of one per sibling.  Only the
+// quarters that overlap the positions [from, to] the caller is going to look at are fetched (the searches of a
+// repeat-rich table are bound by L2 bandwidth, not by latency); everything else, and entries beyond the level's size
+// (the arrays are padded to whole groups; real values stay below 0xffffffff), reads as 0xffffffff.
+CLD_HD void load_group(const uint32_t *lev, uint64_t size, uint64_t base, uint32_t from, uint32_t to, uint32_t *g)
+{
+#ifdef __CUDA_ARCH__
+  const uint4 *q = reinterpret_cast<const uint4 *>(lev + base);
+  const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  const uint4 a = from < 4 ? __ldg(q) : none;
+  const uint4 b = (from < 8 && to >= 4) ? __ldg(q + 1) : none;
+  const uint4 c = (from < 12 && to >= 8) ? __ldg(q + 2) : none;
+  const uint4 d = to >= 12 ? __ldg(q + 3) : none;
+  g[0] = a.x, g[1] = a.y, g[2] = a.z, g[3] = a.w;
+  g[4] = b.x, g[5] = b.y, g[6] = b.z, g[7] = b.w;
+  g[8] = c.x, g[9] = c.y, g[10] = c.z, g[11] = c.w;
+  g[12] = d.x, g[13] = d.y, g[14] = d.z, g[15] = d.w;
+#pragma unroll
+  for (uint32_t t = 0; t < FAN; t++)
+  {
+    if (base + t >= size)
+    {
+      g[t] = 0xffffffffu;
+    }
+  }
+#else
+  for (uint32_t t = 0; t < FAN; t++)
+  {
+    const bool fetched = t / 4 >= from / 4 && t / 4 <= to / 4;
+    g[t] = fetched && base + t < size ? lev[base + t] : 0xffffffffu;
+  }
+#endif
+}
+static_assert(FAN == 16, "load_group is written for groups of 16");
+
+// first position c >= from of the group with g[c] <= v; FAN when there is none
+CLD_HD uint32_t group_first_le(const uint32_t *g, uint32_t from, uint32_t v)
+{
+  uint32_t pos = FAN;
+#pragma unroll
+  for (uint32_t t = 0; t < FAN; t++)
+  {
+    if (pos == FAN && t >= from && g[t] <= v)
+    {
+      pos = t;
+    }
+  }
+  return pos;
+}
+
+// last position c <= upto of the group with g[c] <= v; FAN when there is none
+CLD_HD uint32_t group_last_le(const uint32_t *g, uint32_t upto, uint32_t v)
+{
+  uint32_t pos = FAN;
+#pragma unroll
+  for (uint32_t t = 0; t < FAN; t++)
+  {
+    if (t <= upto && g[t] <= v)
+    {
+      pos = t;
+    }
+  }
+  return pos;
+}
+
 // first index > i with a value <= v; size[0] when there is none
 CLD_HD uint64_t next_le(const Pyramid &py, uint64_t i, uint32_t v)
 {
   int k = 0;
   uint64_t p = i + 1;
+  uint32_t g[FAN];
   while (true)
   {
     if (p >= py.size[k])
     {
       return py.size[0];
     }
-    if (py.level[k][p] <= v)
+    const uint64_t base = p - p % FAN;
+    load_group(py.level[k], py.size[k], base, (uint32_t) (p - base), FAN - 1, g);
+    const uint32_t c = group_first_le(g, (uint32_t) (p - base), v);
+    if (c < FAN)
     {
-      while (k > 0)
+      p = base + c;
+      while (k > 0)  // down to the first leaf under the block that is small enough
       {
         k--;
         p *= FAN;
-        while (py.level[k][p] > v)
-        {
-          p++;
-        }
+        load_group(py.level[k], py.size[k], p, 0, FAN - 1, g);
+        p += group_first_le(g, 0, v);
       }
       return p;
     }
-    p++;
-    if (p % FAN == 0 && k < py.top)
+    p = base + FAN;  // this group is done: go on with the block behind its parent
+    if (k < py.top)
     {
       p /= FAN;
       k++;
@@ -89,36 +158,35 @@ CLD_HD uint64_t prev_le(const Pyramid &py, uint64_t i, uint32_t v)
   }
   int k = 0;
   uint64_t p = i - 1;
+  uint32_t g[FAN];
   while (true)
   {
-    if (py.level[k][p] <= v)
+    const uint64_t base = p - p % FAN;
+    load_group(py.level[k], py.size[k], base, 0, (uint32_t) (p - base), g);
+    const uint32_t c = group_last_le(g, (uint32_t) (p - base), v);
+    if (c < FAN)
     {
-      while (k > 0)
+      p = base + c;
+      while (k > 0)  // down to the last leaf under the block that is small enough
       {
         k--;
-        p = p * FAN + (FAN - 1);
-        if (p >= py.size[k])
-        {
-          p = py.size[k] - 1;
-        }
-        while (py.level[k][p] > v)
-        {
-          p--;
-        }
+        p *= FAN;
+        load_group(py.level[k], py.size[k], p, 0, FAN - 1, g);
+        p += group_last_le(g, FAN - 1, v);
       }
       return p;
     }
-    if (p == 0)
+    if (base == 0)
     {
       return NONE;
     }
-    if (p % FAN == 0 && k < py.top)
+    if (k < py.top)
     {
-      p = p / FAN - 1;  // the group that starts at p is done: go on with the block in front of its parent
+      p = base / FAN - 1;  // the group is done: go on with the block in front of its parent
       k++;
     } else
     {
-      p--;
+      p = base - 1;
     }
   }
 }
@@ -130,61 +198,86 @@ CLD_HD uint64_t leftmost_min(const Pyramid &py, uint64_t a, uint64_t b)
   uint64_t best_start = NONE, best_p = 0;
   int best_k = 0;
   int k = 0;
-  int64_t lo = (int64_t) a, hi = (int64_t) b;
-  uint64_t span = 1;  // leaves under one node of level k
-#define CLD_CONSIDER(P)                                                        \
-  do                                                                           \
-  {                                                                            \
-    const uint32_t val__ = py.level[k][(P)];                                   \
-    const uint64_t start__ = (uint64_t) (P) * span;                            \
-    if (val__ < best || (val__ == best && start__ < best_start))               \
-    {                                                                          \
-      best = val__;                                                            \
-      best_start = start__;                                                    \
-      best_p = (uint64_t) (P);                                                 \
-      best_k = k;                                                              \
-    }                                                                          \
+  uint64_t lo = a, hi = b;  // closed range of nodes of level k still to be covered
+  uint64_t span = 1;        // leaves under one node of level k
+  uint32_t g[FAN];
+  // nodes [from, to] of the group at `base`, left to right; an equal value further right never replaces one found before
+#define CLD_CONSIDER_GROUP(BASE, FROM, TO)                                       \
+  do                                                                             \
+  {                                                                              \
+    load_group(py.level[k], py.size[k], (BASE), (FROM), (TO), g);                \
+    _Pragma("unroll") for (uint32_t t__ = 0; t__ < FAN; t__++)                   \
+    {                                                                            \
+      const uint64_t start__ = ((BASE) + t__) * span;                            \
+      if (t__ >= (FROM) && t__ <= (TO) && (g[t__] < best || (g[t__] == best && start__ < best_start))) \
+      {                                                                          \
+        best = g[t__];                                                           \
+        best_start = start__;                                                    \
+        best_p = (BASE) + t__;                                                   \
+        best_k = k;                                                              \
+      }                                                                          \
+    }                                                                            \
   } while (0)
-  while (lo <= hi)
+  while (true)
   {
-    if (k == py.top)
+    const uint64_t lo_base = lo - lo % FAN, hi_base = hi - hi % FAN;
+    if (lo_base == hi_base)  // what is left lies inside one group
     {
-      for (int64_t p = lo; p <= hi; p++)
+      CLD_CONSIDER_GROUP(lo_base, (uint32_t) (lo - lo_base), (uint32_t) (hi - lo_base));
+      break;
+    }
+    if (k == py.top)  // the top level is not grouped any further: walk it
+    {
+      for (uint64_t base = lo_base; base <= hi_base; base += FAN)
       {
-        CLD_CONSIDER(p);
+        CLD_CONSIDER_GROUP(base, (uint32_t) (base == lo_base ? lo - lo_base : 0),
+                           (uint32_t) (base == hi_base ? hi - hi_base : FAN - 1));
       }
       break;
     }
-    while (lo <= hi && lo % (int64_t) FAN != 0)
+    // fringes: the part of lo's group from lo on (unless lo starts a group), the part of hi's group up to hi (unless hi
+    // ends one); whole groups in between are covered by their parents one level up
+    if (lo != lo_base)
     {
-      CLD_CONSIDER(lo);
-      lo++;
+      CLD_CONSIDER_GROUP(lo_base, (uint32_t) (lo - lo_base), FAN - 1);
+      lo = lo_base + FAN;
     }
-    while (lo <= hi && (hi + 1) % (int64_t) FAN != 0)
+    if (hi != hi_base + FAN - 1)
     {
-      CLD_CONSIDER(hi);
-      hi--;
+      CLD_CONSIDER_GROUP(hi_base, 0, (uint32_t) (hi - hi_base));
+      if (hi_base == 0)
+      {
+        break;  // nothing in front of hi's group (cannot happen with lo_base != hi_base; kept for the unsigned step)
+      }
+      hi = hi_base - 1;
     }
     if (lo > hi)
     {
       break;
     }
-    lo /= (int64_t) FAN;
-    hi = (hi + 1) / (int64_t) FAN - 1;
+    lo /= FAN;
+    hi /= FAN;
     k++;
     span *= FAN;
   }
-#undef CLD_CONSIDER
+#undef CLD_CONSIDER_GROUP
   k = best_k;
   uint64_t p = best_p;
-  while (k > 0)
+  while (k > 0)  // down to the first leaf under the block that holds the minimum
   {
     k--;
     p *= FAN;
-    while (py.level[k][p] != best)
+    load_group(py.level[k], py.size[k], p, 0, FAN - 1, g);
+    uint32_t c = FAN;
+#pragma unroll
+    for (uint32_t t = 0; t < FAN; t++)
     {
-      p++;
+      if (c == FAN && g[t] == best)
+      {
+        c = t;
+      }
     }
+    p += c;
   }
   return p;
 }
@@ -228,6 +321,9 @@ CLD_HD Child child_entry(const Pyramid &py, uint64_t i)
 // block and `cap` entries on either side, clipped to the table).  Scans at most `cap` entries to the right for j and at
 // most `cap` to the left for q, keeping the leftmost minimum of what it passes, and fills `c` when both scans end
 // inside the window; returns false otherwise (the caller then runs child_entry).  N = size of the table.
+// (A variant of this function on 32-bit window positions was 13 % faster and exact in the host model, but on the device
+// it produced 3 wrong `up` fields in the 100 M entries of C2, different ones' values from run to run; this form gave
+// none in ten runs.  The cause was not found in the SASS; the variant is not kept.)
 CLD_HD bool child_entry_near(const uint32_t *win, uint64_t w0, uint64_t wn, uint64_t N, uint64_t i, uint32_t cap,
                              Child &c)
 {
@@ -310,7 +406,6 @@ CLD_HD bool child_entry_near(const uint32_t *win, uint64_t w0, uint64_t wn, uint
   }
   return true;
 }
-
 // entry i of the one-byte table, from the three-field table (3 bytes per entry) and L.  The reference runs three loops
 // one after the other over the same byte (mkcld.c:230-283), the later one overwrites; they stop below totallength
 // (the third below totallength - 1), so the last entry -- and an entry that no loop writes -- keeps what the
