@@ -74,6 +74,15 @@ def test_host_tables_against_the_stack_walk(esa, name):
     assert_child_tables(esa.childtab(lcp, llv), ou.oracle_childtab(lcp, llv), name)
 
 
+@pytest.mark.parametrize("name", ["uniform4_4097", "uniform300_65537", "plateaus", "nested_deep", "long_intervals",
+                                  "large_values", "walk"])
+def test_pyramid_search_for_every_entry(esa, name, monkeypatch):
+    """ESA_CHILDTAB_NO_NEAR=1: the bounded scan is skipped, every entry goes through the queue and child_far_kernel"""
+    monkeypatch.setenv("ESA_CHILDTAB_NO_NEAR", "1")
+    lcp, llv = split_lcp(SHAPED[name])
+    assert_child_tables(esa.childtab(lcp, llv), ou.oracle_childtab(lcp, llv), name + " (pyramid only)")
+
+
 def test_twenty_million_entries_against_the_stack_walk(esa):
     rng = np.random.default_rng(99)
     N = 20_000_001
