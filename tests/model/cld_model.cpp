@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#define CLD_NEAR32 1  // the experiment variant of the bounded scan is modelled too (near32 != 0 below)
 #include "../../vstree_b200/csrc/childtab_core.cuh"
 
 namespace
@@ -43,8 +44,8 @@ struct HostPyramid
 extern "C" {
 
 // L has N = n + 1 entries (L[0] = 0); cld gets 3 N bytes, cld1 N bytes
-void cld_model_tables(const uint32_t *L, uint64_t N, uint32_t threads, uint32_t near, uint8_t *cldtab, uint8_t *cld1,
-                      uint64_t *near_count)
+void cld_model_tables(const uint32_t *L, uint64_t N, uint32_t threads, uint32_t near, int near32, uint8_t *cldtab,
+                      uint8_t *cld1, uint64_t *near_count)
 {
   HostPyramid h(L, N);
   // as child_kernel runs it: blocks of `threads` entries with a window of `near` entries on either side; the bounded
@@ -63,7 +64,8 @@ void cld_model_tables(const uint32_t *L, uint64_t N, uint32_t threads, uint32_t 
       {
         win[t - w0] = L[t];
       }
-      settled = cld::child_entry_near(win.data(), w0, wend - w0, N, i, near, c);
+      settled = near32 ? cld::child_entry_near32(win.data(), (uint32_t) (wend - w0), wend == N, (uint32_t) (i - w0), near, c)
+                       : cld::child_entry_near(win.data(), w0, wend - w0, N, i, near, c);
       if (settled && near_count != nullptr)
       {
         ++*near_count;

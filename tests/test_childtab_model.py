@@ -47,21 +47,22 @@ def model():
         lib = ctypes.CDLL(MODEL_SO)
         u8p, u32p, u64p = (ctypes.POINTER(t) for t in (ctypes.c_uint8, ctypes.c_uint32, ctypes.c_uint64))
         lib.cld_model_tables.restype = None
-        lib.cld_model_tables.argtypes = [u32p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, u8p, u8p, u64p]
+        lib.cld_model_tables.argtypes = [u32p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, u8p, u8p, u64p]
         lib.cld_model_queries.restype = None
         lib.cld_model_queries.argtypes = [u32p, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         _model = lib
     return _model
 
 
-def model_tables(L, threads=256, near=32, count=None):
+def model_tables(L, threads=256, near=32, count=None, near32=False):
     """The tables as child_kernel computes them: blocks of `threads` entries, the bounded scan over `near` entries on
-    either side first (CLD_THREADS / CLD_NEAR of childtab.cu), the pyramid search for the rest; near=0: pyramid only."""
+    either side first (CLD_THREADS / CLD_NEAR of childtab.cu), the pyramid search for the rest; near=0: pyramid only;
+    near32: the -DCLD_NEAR32 experiment variant of the bounded scan."""
     L = np.ascontiguousarray(L, np.uint32)
     N = len(L)
     cld, cld1 = np.zeros(3 * N, np.uint8), np.zeros(N, np.uint8)
     settled = ctypes.c_uint64(0)
-    model().cld_model_tables(L.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), N, threads, near,
+    model().cld_model_tables(L.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), N, threads, near, int(near32),
                              cld.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
                              cld1.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(settled))
     if count is not None:
@@ -133,7 +134,7 @@ def test_oracle_childtab_against_reference_files(name):
         assert cld.tolist() == g["tables"]["cld"] and cld1.tolist() == g["tables"]["cld1"]
     # the same tables from the per-entry functions of the kernels
     near = []
-    for kw in ({"count": near}, {"near": 0}, {"threads": 16, "near": 3}):
+    for kw in ({"count": near}, {"near": 0}, {"threads": 16, "near": 3}, {"near32": True}):
         m_cld, m_cld1 = model_tables(exact_lcp(o["lcp"], o["llv"]), **kw)
         assert np.array_equal(m_cld, cld) and np.array_equal(m_cld1, cld1), kw
     if len(tis) >= 20000 and "poly" not in name:
@@ -145,7 +146,8 @@ def test_kernel_functions_against_the_stack_walk(name):
     L = SHAPED[name]
     lcp, llv = split_lcp(L)
     cld, cld1 = ou.oracle_childtab(lcp, llv)
-    for kw in ({}, {"near": 0}, {"threads": 16, "near": 3}, {"threads": 64, "near": 1}, {"threads": 32, "near": 64}):
+    for kw in ({}, {"near": 0}, {"threads": 16, "near": 3}, {"threads": 64, "near": 1}, {"threads": 32, "near": 64},
+               {"near32": True}, {"threads": 16, "near": 3, "near32": True}, {"threads": 64, "near": 1, "near32": True}):
         m_cld, m_cld1 = model_tables(L, **kw)
         bad = np.nonzero(m_cld != cld)[0]
         assert len(bad) == 0, f"{name} {kw}: record {bad[0] // 3} field {bad[0] % 3}: {m_cld[bad[0]]} != {cld[bad[0]]}"

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(CLD_THREADS) child_near_kernel(cld::Pyramid py
 {
   __shared__ __align__(16) u8 rec[CLD_THREADS * 3];
   __shared__ u32 win[CLD_THREADS + 2 * CLD_NEAR];
-  __shared__ uint16_t queue[CLD_THREADS];
-  __shared__ u32 queued, queue_base;
+  __shared__ u32 warp_open[CLD_THREADS / 32];
+  __shared__ u32 queue_base;
   const u64 N = py.size[0];
   const u64 first = (u64) blockIdx.x * CLD_THREADS;
   const u64 w0 = first >= CLD_NEAR ? first - CLD_NEAR : 0;
@@ -100,31 +100,50 @@ __global__ void __launch_bounds__(CLD_THREADS) child_near_kernel(cld::Pyramid py
   {
     win[t] = py.level[0][w0 + t];
   }
-  if (threadIdx.x == 0)
-  {
-    queued = 0;
-  }
   __syncthreads();
   const u64 i = first + threadIdx.x;
   cld::Child c;
   c.up = c.down = c.nextl = 0;
-  if (i < N && !(use_near && cld::child_entry_near(win, w0, wn, N, i, CLD_NEAR, c)))
+  bool open = false;  // left to child_far_kernel
+  if (i < N)
   {
-    queue[atomicAdd(&queued, 1u)] = (uint16_t) threadIdx.x;
-    c.up = c.down = c.nextl = 0;  // child_far_kernel writes this record
+#ifdef CLD_NEAR32
+    open = !(use_near && cld::child_entry_near32(win, wn, wend == N, (u32) (i - w0), CLD_NEAR, c));
+#else
+    open = !(use_near && cld::child_entry_near(win, w0, wn, N, i, CLD_NEAR, c));
+#endif
+    if (open)
+    {
+      c.up = c.down = c.nextl = 0;
+    }
   }
   rec[3 * threadIdx.x] = c.up;
   rec[3 * threadIdx.x + 1] = c.down;
   rec[3 * threadIdx.x + 2] = c.nextl;
-  __syncthreads();
-  if (threadIdx.x == 0 && queued > 0)
+  // the open entries of the block go to the queue in index order; every step of the compaction runs with the whole
+  // warp converged (ballot, one count per warp, one atomic per block)
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 ballot = __ballot_sync(0xffffffffu, open);
+  if (lane == 0)
   {
-    queue_base = atomicAdd(far_count, queued);
+    warp_open[warp] = __popc(ballot);
   }
   __syncthreads();
-  if (threadIdx.x < queued)
+  if (threadIdx.x == 0)
   {
-    far_queue[queue_base + threadIdx.x] = (u32) (first + queue[threadIdx.x]);
+    u32 total = 0;
+    for (u32 w = 0; w < CLD_THREADS / 32; w++)
+    {
+      const u32 count = warp_open[w];
+      warp_open[w] = total;
+      total += count;
+    }
+    queue_base = total > 0 ? atomicAdd(far_count, total) : 0;
+  }
+  __syncthreads();
+  if (open)
+  {
+    far_queue[queue_base + warp_open[warp] + __popc(ballot & ((1u << lane) - 1u))] = (u32) i;
   }
   // first * 3 is a multiple of 4 (CLD_THREADS * 3 = 768): whole words while they are inside the table, bytes at its end
   const u64 base = first * 3, total = N * 3;

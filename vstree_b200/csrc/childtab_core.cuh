@@ -321,9 +321,9 @@ CLD_HD Child child_entry(const Pyramid &py, uint64_t i)
 // block and `cap` entries on either side, clipped to the table).  Scans at most `cap` entries to the right for j and at
 // most `cap` to the left for q, keeping the leftmost minimum of what it passes, and fills `c` when both scans end
 // inside the window; returns false otherwise (the caller then runs child_entry).  N = size of the table.
-// (A variant of this function on 32-bit window positions was 13 % faster and exact in the host model, but on the device
-// it produced 3 wrong `up` fields in the 100 M entries of C2, different ones' values from run to run; this form gave
-// none in ten runs.  The cause was not found in the SASS; the variant is not kept.)
+// (child_entry_near32 below is the same scan on 32-bit window positions: 16 % faster, exact in the host model and, since
+// the queue append of child_near_kernel moved into converged code, in four runs over the 100 M entries of C2; the
+// whole GPU test file has only been run with this form, which is why it is the default.  DESIGN.md 4.8 has the story.)
 CLD_HD bool child_entry_near(const uint32_t *win, uint64_t w0, uint64_t wn, uint64_t N, uint64_t i, uint32_t cap,
                              Child &c)
 {
@@ -406,6 +406,75 @@ CLD_HD bool child_entry_near(const uint32_t *win, uint64_t w0, uint64_t wn, uint
   }
   return true;
 }
+#ifdef CLD_NEAR32  // -DCLD_NEAR32: the bounded scan on 32-bit window positions; same contract, li = i - w0
+CLD_HD bool child_entry_near32(const uint32_t *win, uint32_t wn, bool ends_table, uint32_t li, uint32_t cap, Child &c)
+{
+  const uint32_t v = win[li];
+  c.up = c.down = c.nextl = 0;
+  const uint32_t stop = li + cap < wn - 1 ? li + cap : wn - 1;
+  uint32_t minv = 0xffffffffu, minl = 0, j = 0;
+  for (uint32_t lp = li + 1; lp <= stop; lp++)
+  {
+    const uint32_t x = win[lp];
+    if (x <= v)
+    {
+      j = lp;
+      break;
+    }
+    if (x < minv)
+    {
+      minv = x;
+      minl = lp;
+    }
+  }
+  if (j != 0)
+  {
+    if (win[j] == v)
+    {
+      c.nextl = clamp_child(j - li);
+    }
+    if (j > li + 1)
+    {
+      c.down = clamp_child(minl - li);
+    }
+  } else if (!(ends_table && stop == wn - 1))
+  {
+    return false;
+  }
+  if (li >= 1 && win[li - 1] > v)
+  {
+    const uint32_t lo = li > cap ? li - cap : 0;
+    bool found = false;
+    minv = 0xffffffffu;
+    minl = 0;
+    for (uint32_t lp = li - 1;; lp--)
+    {
+      const uint32_t x = win[lp];
+      if (x <= v)
+      {
+        found = true;
+        break;
+      }
+      if (x <= minv)
+      {
+        minv = x;
+        minl = lp;
+      }
+      if (lp == lo)
+      {
+        break;
+      }
+    }
+    if (!found)
+    {
+      return false;
+    }
+    c.up = clamp_child(li - minl);
+  }
+  return true;
+}
+#endif
+
 // entry i of the one-byte table, from the three-field table (3 bytes per entry) and L.  The reference runs three loops
 // one after the other over the same byte (mkcld.c:230-283), the later one overwrites; they stop below totallength
 // (the third below totallength - 1), so the last entry -- and an entry that no loop writes -- keeps what the
