@@ -26,8 +26,8 @@ def built():
         __graft_entry__.build()
 
 
-def run(binary, args, cwd):
-    pr = subprocess.run([binary] + args, cwd=cwd, capture_output=True)
+def run(binary, args, cwd, env=None):
+    pr = subprocess.run([binary] + args, cwd=cwd, capture_output=True, env=dict(os.environ, **env) if env else None)
     files = {}
     for fn in sorted(os.listdir(cwd)):
         if "." in fn and fn.split(".")[-1] in EXTS:
@@ -107,14 +107,19 @@ def test_host_driver_equals_reference_on_random_inputs(tmp_path, block):
     for seed in range(block * 40, block * 40 + 40):
         files, args = make_case(seed)
         res = []
-        for which, binary in (("ref", ou.REF_MKVTREE), ("ours", OURS)):
+        # "threaded": the FASTA parser cut into pieces whatever the size of the input (vstree_b200/host/mkvtree.c:
+        # parsefastathreaded); it must agree with the sequential one and with the reference on every case
+        threaded = {"MKVTREE_PARSE_THREADS": str(2 + seed % 4), "MKVTREE_PARSE_MIN": "1"}
+        for which, binary, env in (("ref", ou.REF_MKVTREE, None), ("ours", OURS, {"MKVTREE_PARSE_THREADS": "1"}),
+                                   ("threaded", OURS, threaded)):
             d = tmp_path / f"{seed}_{which}"
             d.mkdir()
             for name, content in files.items():
                 (d / name).write_bytes(content)
-            r = run(binary, args, str(d))
+            r = run(binary, args, str(d), env)
             res.append((r[0], r[1], r[2], {k: v for k, v in r[3].items() if k not in files}))
-        ref, ours = res
+        ref, ours, piecewise = res
+        assert piecewise == ours, f"seed {seed} {args}: the threaded parser differs from the sequential one"
         prj = b"".join(v for k, v in ref[3].items() if k.endswith(".prj"))
         if ref[0] < 0 or "cannot find position" in ref[2] or b"1844674407370955" in prj:
             continue  # the reference crashed, or lost the file borders (a file that ends inside a description)
@@ -126,3 +131,63 @@ def test_host_driver_equals_reference_on_random_inputs(tmp_path, block):
         for k in ref[3]:
             assert ours[3][k] == ref[3][k], f"seed {seed} {args}: {k} differs"
     assert compared >= 30
+
+
+def big_fasta(rng, records, kind="dna"):
+    """many records with everything that crosses a piece border: N runs at the ends of sequences (special ranges that
+    continue into the separator), empty lines, CR/LF, '>' inside descriptions, ragged lines"""
+    out = []
+    for r in range(records):
+        nl = "\r\n" if rng.random() < 0.1 else "\n"
+        out.append(">" + "".join(rng.choice("abc >XYZ123|_.-") for _ in range(rng.randint(0, 30))) + nl)
+        body = rand_seq(rng, kind, rng.randint(1, 400))
+        if rng.random() < 0.3:
+            body += ("N" if kind == "dna" else "X") * rng.randint(1, 5)
+        if rng.random() < 0.3:
+            body = ("n" if kind == "dna" else "*") * rng.randint(1, 5) + body
+        w = rng.choice([7, 60, 61, 1000])
+        for ln in [body[i:i + w] for i in range(0, len(body), w)]:
+            out.append(ln + nl)
+        if rng.random() < 0.1:
+            out.append(nl)
+    return "".join(out).encode()
+
+
+@pytest.mark.parametrize("seed,kind", [(1, "dna"), (2, "dna"), (3, "protein")])
+def test_threaded_fasta_parser_on_many_records(tmp_path, seed, kind):
+    rng = random.Random(1000 + seed)
+    data = big_fasta(rng, 1500, kind)
+    args = ["-db", "in.fa", "-dna" if kind == "dna" else "-protein", "-tis", "-ois", "-v"]
+    outs = {}
+    for which, binary, env in [("ref", ou.REF_MKVTREE, None), ("seq", OURS, {"MKVTREE_PARSE_THREADS": "1"})] + [
+            (f"t{t}", OURS, {"MKVTREE_PARSE_THREADS": str(t), "MKVTREE_PARSE_MIN": "1"}) for t in (2, 3, 7, 16, 64)]:
+        d = tmp_path / which
+        d.mkdir()
+        (d / "in.fa").write_bytes(data)
+        outs[which] = run(binary, args, str(d), env)
+    assert outs["ref"][0] == 0 and len(outs["ref"][3]) >= 6
+    for which in outs:
+        assert outs[which] == outs["ref"], f"{which} differs from the reference"
+    # and the pieces really ran
+    d = tmp_path / "report"
+    d.mkdir()
+    (d / "in.fa").write_bytes(data)
+    r = run(OURS, args, str(d), {"MKVTREE_PARSE_THREADS": "7", "MKVTREE_PARSE_MIN": "1", "MKVTREE_PARSE_REPORT": "1"})
+    assert "parsefasta: 7 pieces" in r[2]
+
+
+def test_threaded_fasta_parser_falls_back_on_errors(tmp_path):
+    """an illegal character or a '>' inside a line in ANY piece: the message (file, line number) of the sequential parser"""
+    rng = random.Random(5)
+    good = big_fasta(rng, 300).decode()
+    pos = good.index("\n", 2 * len(good) // 3)
+    for bad in (good[:pos] + "!" + good[pos:], good[:pos] + ">x" + good[pos:]):
+        res = []
+        for which, binary, env in (("ref", ou.REF_MKVTREE, None),
+                                   ("threaded", OURS, {"MKVTREE_PARSE_THREADS": "4", "MKVTREE_PARSE_MIN": "1"})):
+            d = tmp_path / f"{which}{len(res)}{len(bad)}"
+            d.mkdir()
+            (d / "in.fa").write_bytes(bad.encode())
+            res.append(run(binary, ["-db", "in.fa", "-dna", "-tis"], str(d)) if env is None else
+                       run(binary, ["-db", "in.fa", "-dna", "-tis"], str(d), env))
+        assert res[0][0] != 0 and res[1][:3] == res[0][:3], (res[0][2], res[1][2])

@@ -24,6 +24,7 @@
 #include <errno.h>
 #include <limits.h>
 #include <pthread.h>
+#include <sched.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <stdarg.h>
@@ -883,6 +884,53 @@ static uint8_t *concatfiles(const Options *o, Multiseq *ms, uint64_t *concatfile
     (ARR)[(CNT)++] = (VAL);                                        \
   } while (0)
 
+/* what follows the sweep over the input: special prefix and suffix, empty sequences (both parsers end here) */
+static int finishfasta(Multiseq *ms)
+{
+  const uint64_t out = ms->totallength;
+  if (ms->numofsequences == 0)
+  {
+    return fail("no sequences in multiple fasta file");
+  }
+  for (uint64_t p = 0; p < out && ISSPECIAL(ms->tis[p]); p++)
+  {
+    ms->lengthofspecialprefix++;
+  }
+  if (out > 0)
+  {
+    for (uint64_t p = out - 1; ISSPECIAL(ms->tis[p]); p--)
+    {
+      ms->lengthofspecialsuffix++;
+      if (p == 0)
+      {
+        break;
+      }
+    }
+  }
+  if (ms->numofsequences >= 2)
+  {
+    for (uint64_t m = 1; m < ms->numofsequences - 1; m++)
+    {
+      if (ms->markpos[m - 1] + 1 == ms->markpos[m])
+      {
+        return fail("sequence %lu is empty", (unsigned long) (m - 1));
+      }
+    }
+    if (ms->markpos[0] == 0)
+    {
+      return fail("sequence 0 is empty");
+    }
+    if (ms->markpos[ms->numofsequences - 2] == out - 1)
+    {
+      return fail("sequence %lu is empty", (unsigned long) (ms->numofsequences - 1));
+    }
+  }
+  return 0;
+}
+
+static int parsefastathreaded(Multiseq *ms, const Alphabet *alpha, const Options *o, const uint8_t *input,
+                              uint64_t inputlen, int wantois);
+
 /* multiple FASTA -> tis, ois, descriptions, separator positions, special statistics
    (src/kurtz-basic/multiseq-adv.c:1036-1250 readmultiplefastafilesep, :1260-1291 readmultiplefastafileagain) */
 static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, const uint8_t *input, uint64_t inputlen,
@@ -893,6 +941,10 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
   int indesc = 0, lastwasspecial = 0;
   uint8_t letter[UCHAR_MAX + 1];  /* code of an ordinary letter, 255 for everything that needs a closer look */
   uint8_t *ois = NULL;
+  if (parsefastathreaded(ms, alpha, o, input, inputlen, wantois))
+  {
+    return finishfasta(ms);
+  }
   ms->tis = malloc(inputlen + 1);
   if (ms->tis == NULL)
   {
@@ -1012,45 +1064,358 @@ static int parsefasta(Multiseq *ms, const Alphabet *alpha, const Options *o, con
     }
   }
   PUSH(ms->startdesc, sdcnt, sdcap, ms->desclen);
-  if (ms->numofsequences == 0)
-  {
-    return fail("no sequences in multiple fasta file");
-  }
   ms->totallength = out;
-  for (uint64_t p = 0; p < out && ISSPECIAL(ms->tis[p]); p++)
+  return finishfasta(ms);
+}
+
+/* ---- the same parse by several threads ------------------------------------------------------
+   A '>' at the start of a line is always the start of a record (a description ends at its newline), so the input can
+   be cut at such places and every piece parsed on its own: parsefastapiece is parsefasta's state machine without the
+   parts that need the whole file (several input files, line numbers for messages).  Each piece writes its symbols into
+   the shared tis / ois buffers at the offset of its own input (a piece never produces more symbols than it has bytes),
+   the pieces are moved together afterwards, descriptions, separator positions and the special statistics are joined.
+   Anything a piece cannot handle (an illegal character, memory) makes the caller fall back to parsefasta, which then
+   produces the reference's message.  MKVTREE_PARSE_THREADS (default: usable CPUs, at most 8; 1 = off) and
+   MKVTREE_PARSE_MIN (default 4 MB of input) control it; tests/test_cli_fuzz.py runs both parsers against each other and
+   against the reference binary. */
+typedef struct
+{
+  const uint8_t *input;
+  uint64_t begin, end;            /* this piece of the input; input[begin] == '>' at the start of a line */
+  const uint8_t *letter;          /* see parsefasta */
+  const Alphabet *alpha;
+  uint8_t *tis, *ois;             /* shared buffers; the piece writes from offset `begin` on */
+  int first;                      /* the piece that starts the file: no separator in front of its first record */
+  uint64_t out;                   /* symbols produced */
+  uint8_t *desc;
+  uint64_t desclen, desccap;
+  uint64_t *startdesc, sdcnt, sdcap;   /* offsets into this piece's desc */
+  uint64_t *markpos, mpcnt, mpcap;     /* separator positions, relative to the piece's first symbol */
+  uint64_t numofsequences, specialcharacters, specialranges;
+  int lastwasspecial;             /* state behind the last symbol of the piece */
+  int failed;
+  pthread_t thread;
+} Fastapiece;
+
+#define PIECEPUSH(ARR, CNT, CAP, VAL)                              \
+  do                                                               \
+  {                                                                \
+    if ((CNT) == (CAP))                                            \
+    {                                                              \
+      void *grown__;                                               \
+      (CAP) = (CAP) ? 2 * (CAP) : 1024;                            \
+      grown__ = realloc((ARR), (CAP) * sizeof *(ARR));             \
+      if (grown__ == NULL)                                         \
+      {                                                            \
+        pc->failed = 1;                                            \
+        return NULL;                                               \
+      }                                                            \
+      (ARR) = grown__;                                             \
+    }                                                              \
+    (ARR)[(CNT)++] = (VAL);                                        \
+  } while (0)
+
+static void *parsefastapiece(void *arg)
+{
+  Fastapiece *pc = (Fastapiece *) arg;
+  const uint8_t *input = pc->input, *letter = pc->letter;
+  uint8_t *tis = pc->tis + pc->begin, *ois = pc->ois != NULL ? pc->ois + pc->begin : NULL;
+  uint64_t out = 0;
+  int indesc = 0, lastwasspecial = 0;
+
+  for (uint64_t i = pc->begin; i < pc->end; i++)
   {
-    ms->lengthofspecialprefix++;
-  }
-  if (out > 0)
-  {
-    for (uint64_t p = out - 1; ISSPECIAL(ms->tis[p]); p--)
+    const uint8_t current = input[i];
+    if (!indesc && letter[current] != 255)
     {
-      ms->lengthofspecialsuffix++;
-      if (p == 0)
+      uint64_t j = i;
+      if (ois != NULL)
+      {
+        for (; j < pc->end && letter[input[j]] != 255; j++)
+        {
+          tis[out + (j - i)] = letter[input[j]];
+          ois[out + (j - i)] = input[j];
+        }
+      } else
+      {
+        for (; j < pc->end && letter[input[j]] != 255; j++)
+        {
+          tis[out + (j - i)] = letter[input[j]];
+        }
+      }
+      out += j - i;
+      lastwasspecial = 0;
+      i = j - 1;
+      continue;
+    }
+    if (indesc)
+    {
+      PIECEPUSH(pc->desc, pc->desclen, pc->desccap, current);
+      if (current == '\n')
+      {
+        indesc = 0;
+      }
+    } else if (current == '>')
+    {
+      if (i > 0 && input[i - 1] != '\n')
+      {
+        pc->failed = 1;  /* the sequential parser reports it */
+        return NULL;
+      }
+      PIECEPUSH(pc->startdesc, pc->sdcnt, pc->sdcap, pc->desclen);
+      if (!pc->first || pc->numofsequences > 0)
+      {
+        PIECEPUSH(pc->markpos, pc->mpcnt, pc->mpcap, out);
+        if (!lastwasspecial)
+        {
+          pc->specialranges++;
+        }
+        pc->specialcharacters++;
+        lastwasspecial = 1;
+        if (ois != NULL)
+        {
+          ois[out] = SEPARATOR;
+        }
+        tis[out++] = SEPARATOR;
+      }
+      pc->numofsequences++;
+      indesc = 1;
+    } else if (!isspace(current))
+    {
+      const unsigned acode = pc->alpha->symbolmap[current];
+      if (acode == UNDEFCHAR)
+      {
+        pc->failed = 1;
+        return NULL;
+      }
+      if (ISSPECIAL(acode))
+      {
+        if (!lastwasspecial)
+        {
+          pc->specialranges++;
+        }
+        pc->specialcharacters++;
+        lastwasspecial = 1;
+      } else
+      {
+        lastwasspecial = 0;
+      }
+      if (ois != NULL)
+      {
+        ois[out] = current;
+      }
+      tis[out++] = (uint8_t) acode;
+    }
+  }
+  pc->out = out;
+  pc->lastwasspecial = lastwasspecial;
+  return NULL;
+}
+
+static unsigned parsethreads(uint64_t inputlen)
+{
+  const char *e = getenv("MKVTREE_PARSE_THREADS"), *m = getenv("MKVTREE_PARSE_MIN");
+  const uint64_t minbytes = m != NULL ? strtoull(m, NULL, 10) : ((uint64_t) 4 << 20);
+  long n = e != NULL ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+  if (e == NULL)
+  {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0 && CPU_COUNT(&set) < n)
+    {
+      n = CPU_COUNT(&set);
+    }
+    if (n > 8)
+    {
+      n = 8;
+    }
+  }
+  if (n > 64)
+  {
+    n = 64;
+  }
+  return (n < 2 || inputlen < minbytes) ? 1u : (unsigned) n;
+}
+
+/* 1: parsed by several threads, ms is complete up to totallength (the caller finishes like parsefasta does);
+   0: not applicable or a piece gave up, ms untouched, use parsefasta */
+static int parsefastathreaded(Multiseq *ms, const Alphabet *alpha, const Options *o, const uint8_t *input,
+                              uint64_t inputlen, int wantois)
+{
+  Fastapiece pcs[64];
+  uint8_t letter[UCHAR_MAX + 1];
+  unsigned want = parsethreads(inputlen), npieces = 0;
+  uint8_t *tis = NULL, *ois = NULL;
+  uint64_t prev = 0, outtotal = 0, desctotal = 0, sdtotal = 0, mptotal = 0;
+  int ok = 1;
+
+  if (want < 2 || o->numoffiles != 1 || inputlen == 0 || input[0] != '>')
+  {
+    return 0;
+  }
+  memset(pcs, 0, sizeof pcs);
+  /* pieces start at the first record start at or behind k / want of the input */
+  for (unsigned k = 0; k < want; k++)
+  {
+    uint64_t b = k == 0 ? 0 : inputlen / want * k;
+    if (k > 0)
+    {
+      const uint8_t *hit = NULL;
+      if (b <= prev)
+      {
+        b = prev + 1;
+      }
+      for (uint64_t p = b; p + 1 < inputlen; p++)
+      {
+        const uint8_t *nl = memchr(input + p, '\n', inputlen - 1 - p);
+        if (nl == NULL)
+        {
+          break;
+        }
+        if (nl[1] == '>')
+        {
+          hit = nl + 1;
+          break;
+        }
+        p = (uint64_t) (nl - input);
+      }
+      if (hit == NULL)
       {
         break;
       }
+      b = (uint64_t) (hit - input);
+      pcs[npieces - 1].end = b;
     }
+    pcs[npieces].begin = b;
+    pcs[npieces].end = inputlen;
+    pcs[npieces].first = k == 0;
+    prev = b;
+    npieces++;
   }
-  if (ms->numofsequences >= 2)
+  if (npieces < 2)
   {
-    for (uint64_t m = 1; m < ms->numofsequences - 1; m++)
+    return 0;
+  }
+  tis = malloc(inputlen + 1);
+  ois = wantois ? malloc(inputlen + 1) : NULL;
+  if (tis == NULL || (wantois && ois == NULL))
+  {
+    free(tis);
+    free(ois);
+    return 0;
+  }
+  for (unsigned c = 0; c <= UCHAR_MAX; c++)
+  {
+    const unsigned acode = alpha->symbolmap[c];
+    letter[c] = (c != '>' && !isspace((int) c) && acode != UNDEFCHAR && !ISSPECIAL(acode)) ? (uint8_t) acode : 255;
+  }
+  for (unsigned k = 0; k < npieces; k++)
+  {
+    pcs[k].input = input;
+    pcs[k].letter = letter;
+    pcs[k].alpha = alpha;
+    pcs[k].tis = tis;
+    pcs[k].ois = ois;
+  }
+  for (unsigned k = 1; k < npieces; k++)
+  {
+    if (pthread_create(&pcs[k].thread, NULL, parsefastapiece, &pcs[k]) != 0)
     {
-      if (ms->markpos[m - 1] + 1 == ms->markpos[m])
-      {
-        return fail("sequence %lu is empty", (unsigned long) (m - 1));
-      }
-    }
-    if (ms->markpos[0] == 0)
-    {
-      return fail("sequence 0 is empty");
-    }
-    if (ms->markpos[ms->numofsequences - 2] == out - 1)
-    {
-      return fail("sequence %lu is empty", (unsigned long) (ms->numofsequences - 1));
+      pcs[k].failed = 2;  /* not started */
+      ok = 0;
     }
   }
-  return 0;
+  parsefastapiece(&pcs[0]);
+  for (unsigned k = 1; k < npieces; k++)
+  {
+    if (pcs[k].failed != 2)
+    {
+      pthread_join(pcs[k].thread, NULL);
+    }
+  }
+  for (unsigned k = 0; k < npieces; k++)
+  {
+    ok = ok && !pcs[k].failed;
+    desctotal += pcs[k].desclen;
+    sdtotal += pcs[k].sdcnt;
+    mptotal += pcs[k].mpcnt;
+  }
+  if (ok)
+  {
+    ms->desc = malloc(desctotal + 1);
+    ms->startdesc = malloc((sdtotal + 1) * sizeof *ms->startdesc);
+    ms->markpos = malloc((mptotal + 1) * sizeof *ms->markpos);
+    ok = ms->desc != NULL && ms->startdesc != NULL && ms->markpos != NULL;
+  }
+  if (!ok)
+  {
+    for (unsigned k = 0; k < npieces; k++)
+    {
+      free(pcs[k].desc);
+      free(pcs[k].startdesc);
+      free(pcs[k].markpos);
+    }
+    free(ms->desc);
+    free(ms->startdesc);
+    free(ms->markpos);
+    ms->desc = NULL;
+    ms->startdesc = ms->markpos = NULL;
+    free(tis);
+    free(ois);
+    return 0;
+  }
+  /* join: symbols move left to where the pieces in front of them end (a piece starts at or behind that place) */
+  {
+    uint64_t sd = 0, mp = 0;
+    int lastwasspecial = 0;
+    desctotal = 0;
+    for (unsigned k = 0; k < npieces; k++)
+    {
+      Fastapiece *pc = &pcs[k];
+      if (k > 0)
+      {
+        memmove(tis + outtotal, tis + pc->begin, pc->out);
+        if (ois != NULL)
+        {
+          memmove(ois + outtotal, ois + pc->begin, pc->out);
+        }
+        if (lastwasspecial)
+        {
+          pc->specialranges--;  /* its leading separator continues the special range the piece in front ended with */
+        }
+      }
+      if (pc->out > 0)
+      {
+        lastwasspecial = pc->lastwasspecial;
+      }
+      memcpy(ms->desc + desctotal, pc->desc, pc->desclen);
+      for (uint64_t t = 0; t < pc->sdcnt; t++)
+      {
+        ms->startdesc[sd++] = desctotal + pc->startdesc[t];
+      }
+      for (uint64_t t = 0; t < pc->mpcnt; t++)
+      {
+        ms->markpos[mp++] = outtotal + pc->markpos[t];
+      }
+      ms->numofsequences += pc->numofsequences;
+      ms->specialcharacters += pc->specialcharacters;
+      ms->specialranges += pc->specialranges;
+      desctotal += pc->desclen;
+      outtotal += pc->out;
+      free(pc->desc);
+      free(pc->startdesc);
+      free(pc->markpos);
+    }
+    ms->startdesc[sd] = desctotal;
+    ms->desclen = desctotal;
+  }
+  ms->tis = tis;
+  ms->ois = ois;
+  ms->totallength = outtotal;
+  if (getenv("MKVTREE_PARSE_REPORT") != NULL)
+  {
+    fprintf(stderr, "parsefasta: %u pieces on %u threads\n", npieces, npieces);
+  }
+  return 1;
 }
 
 /* a file that is not FASTA is taken verbatim as one sequence (src/Mkvtree/mkvinput.c:78-128) */
