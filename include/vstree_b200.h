@@ -233,7 +233,10 @@ int esa_check(esa_ctx *ctx, char *errbuf, size_t errlen);
  *           (src/include/virtualdef.h:165-179), the bytes of the .cld file
  * cldtab1 : caller's buffer of totallength + 1 bytes (the .cld1 file) or NULL.  Entries the reference never writes
  *           (the last one, mkcld.c:230-283 stops below totallength) are 0.
- * Fails with ESA_ERR_ARGUMENT when the pairs do not belong to the lcp table (every 255 needs exactly one pair). */
+ * Fails with ESA_ERR_ARGUMENT when the pairs do not belong to the lcp table (every 255 needs exactly one pair), with
+ * ESA_ERR_MEMORY when the device cannot hold the working set: about 12.3 bytes per entry (32-bit lcp values and their
+ * min-pyramid 4.3, the records 3, the queue of far-reaching entries 4, .cld1 1) next to whatever a resident build
+ * keeps -- a 3 Gbp index therefore needs a context without a resident build of that size. */
 int esa_childtab(esa_ctx *ctx, const uint8_t *lcptab, const esa_pairuint *llv, uint64_t nllv, uint64_t totallength,
                  uint8_t *cldtab, uint8_t *cldtab1, char *errbuf, size_t errlen);
 
